@@ -1,0 +1,275 @@
+// Fused non-causal multi-head attention for head_dim 64 on tcgen05/TMEM:  O = softmax(scale * Q K^T) V.
+// Replaces WhisperAttention's SDPA ($TF/models/whisper/modeling_whisper.py:284-358; T = 1500, scale 1 because q is
+// pre-scaled) and the eager Bert self / cross attention of the Q-Former ($TF/models/bert/modeling_bert.py:168-207,
+// 234-284; 64 queries x 64 or 1500 keys, scale 1/8).
+//
+// One CTA = 128 query rows of one (batch, head); two CTAs are co-resident per SM (112 KB smem, 256 TMEM columns each)
+// so one CTA's softmax overlaps the other's MMAs.
+//   warp 0   : TMA producer  (Q once; K/V blocks of 128 keys through a 2-stage mbarrier ring, SWIZZLE_128B)
+//   warp 1   : TMEM allocator + MMA issuer: S = Q K^T (UMMA 128x128x16, both operands K-major),
+//              O += P V (UMMA 128x64x16, A = P from shared memory K-major, B = V MN-major as it lies in memory)
+//   warps 2-5: softmax, one query row per thread (TMEM lane == row): running max / sum in fp32, exp2 with the scale
+//              folded in, lazy rescale of the O accumulator in TMEM (only when the max grows by > 2^8), P written as
+//              bf16 into the 128B-swizzled A-operand layout, final 1/l normalisation and 128-byte row stores.
+#include "common.cuh"
+#include "desta_b200.h"
+
+namespace desta {
+
+constexpr int AT_BQ = 128, AT_BKV = 128, AT_HD = 64, AT_STAGES = 2;
+constexpr int AT_Q_BYTES = AT_BQ * AT_HD * 2;      // 16 KB
+constexpr int AT_KV_BYTES = AT_BKV * AT_HD * 2;    // 16 KB (K) + 16 KB (V) per stage
+constexpr int AT_P_BYTES = AT_BQ * AT_BKV * 2;     // 32 KB
+constexpr int AT_SMEM = AT_Q_BYTES + AT_STAGES * 2 * AT_KV_BYTES + AT_P_BYTES + 128;   // 114,816 B -> 2 CTAs / SM
+constexpr int AT_THREADS = 192;
+constexpr int AT_TMEM_COLS = 256;                  // S: [0,128)  O: [128,192)
+
+struct AttnArgs {
+  __nv_bfloat16* out; int ldo;
+  int Tq, Tk;
+  float scale_log2;    // scale * log2(e)
+  int q_rows, kv_rows; // TMA box rows actually loaded (min(128, T))
+};
+
+__global__ void __launch_bounds__(AT_THREADS, 2)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const AttnArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];   // SWIZZLE_128B tiles need 1024-byte alignment
+  if (smem_u32(smem) & 1023) __trap();
+  uint8_t* sQ = smem;
+  uint8_t* sKV = sQ + AT_Q_BYTES;                       // stage s: K at s*32K, V at s*32K + 16K
+  uint8_t* sP = sKV + AT_STAGES * 2 * AT_KV_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + AT_P_BYTES);
+  uint64_t* q_full = bars;            // 1
+  uint64_t* kv_full = bars + 1;       // [2]
+  uint64_t* kv_empty = bars + 3;      // [2]
+  uint64_t* s_full = bars + 5;
+  uint64_t* p_ready = bars + 6;
+  uint64_t* pv_done = bars + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * AT_BQ, head = blockIdx.y, batch = blockIdx.z;
+  const int n_kv = (a.Tk + AT_BKV - 1) / AT_BKV;
+
+  if (a.kv_rows < AT_BKV) {   // short key sequences: rows the TMA box never writes must read as zeros (P = 0 there)
+    uint4* z = reinterpret_cast<uint4*>(sKV);
+    for (int i = threadIdx.x; i < AT_STAGES * 2 * AT_KV_BYTES / 16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async_smem();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < AT_STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    mbar_init(s_full, 1); mbar_init(p_ready, 128); mbar_init(pv_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<AT_TMEM_COLS>(tmem_slot);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, a.q_rows * AT_HD * 2);
+      tma_load_3d(sQ, &tmQ, q_full, head * AT_HD, q0, batch);
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j & 1;
+        mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&kv_full[st], 2 * a.kv_rows * AT_HD * 2);
+        tma_load_3d(sKV + st * 2 * AT_KV_BYTES, &tmK, &kv_full[st], head * AT_HD, j * AT_BKV, batch);
+        tma_load_3d(sKV + st * 2 * AT_KV_BYTES + AT_KV_BYTES, &tmV, &kv_full[st], head * AT_HD, j * AT_BKV, batch);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = umma_idesc_bf16(AT_BQ, AT_BKV, 0, 0);
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(AT_BQ, AT_HD, 0, 1);   // B (= V) is MN-major
+      const uint64_t qdesc = umma_desc_sw128(smem_u32(sQ), 16, 1024);
+      const uint64_t pdesc = umma_desc_sw128(smem_u32(sP), 16, 1024);
+      mbar_wait(q_full, 0);
+      mbar_wait(&kv_full[0], 0);
+      tcgen05_fence_after();
+      {
+        const uint64_t kdesc = umma_desc_sw128(smem_u32(sKV), 16, 1024);
+#pragma unroll
+        for (int k = 0; k < AT_HD / 16; ++k) umma_bf16_ss(tmem_S, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, k != 0);
+        umma_commit(s_full);
+      }
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j & 1;
+        mbar_wait(p_ready, j & 1);           // P_j in smem, S_j consumed, O rescaled if needed
+        tcgen05_fence_after();
+        // V stage: 128 key rows x 128 B (64 head-dim values) -> MN-major B operand, 8-row groups 1024 B apart
+        const uint64_t vdesc = umma_desc_sw128(smem_u32(sKV + st * 2 * AT_KV_BYTES + AT_KV_BYTES), 1024, 1024);
+#pragma unroll
+        for (int k = 0; k < AT_BKV / 16; ++k) {
+          // A = P[:, 16k .. 16k+16): atom (k / 4) of 16 KB, 32 B per step inside the 128-byte swizzle row
+          const uint64_t pd = pdesc + (uint64_t)((k >> 2) * (AT_BQ * 128 / 16) + (k & 3) * 2);
+          const uint64_t vd = vdesc + (uint64_t)(k * (16 * 128 / 16));
+          umma_bf16_ss(tmem_O, pd, vd, idesc_pv, (j | k) != 0);
+        }
+        umma_commit(&kv_empty[st]);
+        umma_commit(pv_done);
+        if (j + 1 < n_kv) {
+          const int sn = (j + 1) & 1;
+          mbar_wait(&kv_full[sn], ((j + 1) >> 1) & 1);
+          tcgen05_fence_after();
+          const uint64_t kdesc = umma_desc_sw128(smem_u32(sKV + sn * 2 * AT_KV_BYTES), 16, 1024);
+#pragma unroll
+          for (int k = 0; k < AT_HD / 16; ++k) umma_bf16_ss(tmem_S, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, k != 0);
+          umma_commit(s_full);
+        }
+      }
+    }
+  } else {
+    // ---- softmax warps: TMEM lane quarter = warp % 4, one query row per thread ----
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;                 // row inside the tile
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    const float c = a.scale_log2;
+    float m_run = -INFINITY, l_run = 0.f;
+    uint8_t* prow = sP + r * 128;
+    const int rx = r & 7;
+    for (int j = 0; j < n_kv; ++j) {
+      mbar_wait(s_full, j & 1);
+      tcgen05_fence_after();
+      const int kv_valid = a.Tk - j * AT_BKV;          // columns >= kv_valid are padding
+      // pass 1: block row max
+      float m_blk = -INFINITY;
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_S + lane_off + ch * 32, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float s = (ch * 32 + i < kv_valid) ? __uint_as_float(v[i]) : -INFINITY;
+          m_blk = fmaxf(m_blk, s);
+        }
+      }
+      const float m_new = fmaxf(m_run, m_blk);
+      const bool need = (m_new - m_run) * c > 8.0f;    // also true on the first block (m_run = -inf)
+      if (__any_sync(0xffffffffu, need)) {
+        if (j > 0) {
+          // PV_{j-1} was issued before QK_j, so it has completed; wait anyway (cheap) before touching O
+          mbar_wait(pv_done, (j - 1) & 1);
+          tcgen05_fence_after();
+          const float f = exp2f((m_run - m_new) * c);
+          l_run *= f;
+#pragma unroll 1
+          for (int ch = 0; ch < 4; ++ch) {
+            uint32_t o[16];
+            tmem_ld_32x16(tmem_O + lane_off + ch * 16, o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+            tmem_st_32x16(tmem_O + lane_off + ch * 16, o);
+          }
+          tmem_wait_st();
+        }
+        m_run = m_new;
+      }
+      // pass 2: p = exp2(c*s - c*m_run), row sum, bf16 P into the swizzled A-operand layout
+      const float mc = m_run * c;
+      float l_blk = 0.f;
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_S + lane_off + ch * 32, v);
+        tmem_wait_ld();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float p0 = (ch * 32 + i < kv_valid) ? fast_exp2(fmaf(__uint_as_float(v[i]), c, -mc)) : 0.f;
+          float p1 = (ch * 32 + i + 1 < kv_valid) ? fast_exp2(fmaf(__uint_as_float(v[i + 1]), c, -mc)) : 0.f;
+          l_blk += p0 + p1;
+          pk[i >> 1] = pack_bf16(p0, p1);
+        }
+        // 32 columns = 4 chunks of 16 B; column chunk index inside the 64-column atom: (ch & 1) * 4 + q
+        uint8_t* atom = prow + (ch >> 1) * (AT_BQ * 128);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int chunk = ((ch & 1) * 4 + q) ^ rx;
+          *reinterpret_cast<uint4*>(atom + chunk * 16) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+        }
+      }
+      l_run += l_blk;
+      fence_proxy_async_smem();       // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      tcgen05_fence_before();         // orders this thread's TMEM loads/stores before the MMA warp's next MMAs
+      mbar_arrive(p_ready);
+    }
+    // ---- epilogue: O / l -> bf16, one 128-byte row per thread ----
+    mbar_wait(pv_done, (n_kv - 1) & 1);
+    tcgen05_fence_after();
+    const float inv = 1.0f / l_run;
+    const int row = q0 + r;
+    __nv_bfloat16* orow = a.out + ((size_t)batch * a.Tq + row) * a.ldo + head * AT_HD;
+#pragma unroll 1
+    for (int ch = 0; ch < 2; ++ch) {
+      uint32_t o[32];
+      tmem_ld_32x32(tmem_O + lane_off + ch * 32, o);
+      tmem_wait_ld();
+      if (row < a.Tq) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          uint4 u;
+          u.x = pack_bf16(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv);
+          u.y = pack_bf16(__uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv);
+          u.z = pack_bf16(__uint_as_float(o[i + 4]) * inv, __uint_as_float(o[i + 5]) * inv);
+          u.w = pack_bf16(__uint_as_float(o[i + 6]) * inv, __uint_as_float(o[i + 7]) * inv);
+          *reinterpret_cast<uint4*>(orow + ch * 32 + i) = u;
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc<AT_TMEM_COLS>(tmem_base);
+  }
+}
+
+static int make_qkv_tmap(CUtensorMap* m, const void* base, int heads, int T, int ld, int batch, int box_rows) {
+  uint64_t dims[3] = {(uint64_t)heads * AT_HD, (uint64_t)T, (uint64_t)batch};
+  uint64_t strides[3] = {0, (uint64_t)ld * 2, (uint64_t)T * ld * 2};
+  uint32_t box[3] = {AT_HD, (uint32_t)box_rows, 1};
+  return make_tmap(m, base, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+}  // namespace desta
+
+using namespace desta;
+
+extern "C" int desta_attention(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo,
+                               int batch, int heads, int Tq, int Tk, float scale, void* stream) {
+  if (!q || !k || !v || !out) { set_error("desta_attention: null pointer"); return DESTA_ERR_ARG; }
+  if (batch <= 0 || heads <= 0 || Tq <= 0 || Tk <= 0) { set_error("desta_attention: bad shape"); return DESTA_ERR_ARG; }
+  if ((ldq % 8) || (ldk % 8) || (ldv % 8) || (ldo % 8) || ldq < heads * 64 || ldk < heads * 64 || ldv < heads * 64 || ldo < heads * 64) {
+    set_error("desta_attention: leading dims must be multiples of 8 and >= heads*64");
+    return DESTA_ERR_ARG;
+  }
+  if (((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)out) & 15) { set_error("desta_attention: pointers must be 16-byte aligned"); return DESTA_ERR_ARG; }
+  if (heads > 65535 || batch > 65535) { set_error("desta_attention: heads/batch too large for one launch"); return DESTA_ERR_ARG; }
+  AttnArgs a;
+  a.out = (__nv_bfloat16*)out; a.ldo = ldo; a.Tq = Tq; a.Tk = Tk;
+  a.scale_log2 = scale * 1.4426950408889634f;
+  a.q_rows = Tq < AT_BQ ? Tq : AT_BQ;
+  a.kv_rows = Tk < AT_BKV ? Tk : AT_BKV;
+  CUtensorMap tmQ, tmK, tmV;
+  if (make_qkv_tmap(&tmQ, q, heads, Tq, ldq, batch, a.q_rows)) return DESTA_ERR_CUDA;
+  if (make_qkv_tmap(&tmK, k, heads, Tk, ldk, batch, a.kv_rows)) return DESTA_ERR_CUDA;
+  if (make_qkv_tmap(&tmV, v, heads, Tk, ldv, batch, a.kv_rows)) return DESTA_ERR_CUDA;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
+    if (e != cudaSuccess) { set_error("attention smem attribute: %s", cudaGetErrorString(e)); return DESTA_ERR_CUDA; }
+    attr_set = true;
+  }
+  const dim3 grid((Tq + AT_BQ - 1) / AT_BQ, heads, batch);
+  attn_fwd_kernel<<<grid, AT_THREADS, AT_SMEM, (cudaStream_t)stream>>>(tmQ, tmK, tmV, a);
+  return check_launch("attn_fwd_kernel");
+}

@@ -1,0 +1,138 @@
+"""Thin torch-tensor wrappers over the C ABI (device pointers + the current CUDA stream).  No torch compute here."""
+import ctypes
+
+import numpy as np
+import torch
+
+from ._lib import GemmEpilogue, SpliceDesc, check, lib
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _cuda(t, dtype=None):
+    assert t.is_cuda, "desta_b200 ops run on CUDA tensors only (no CPU fallback)"
+    if dtype is not None:
+        assert t.dtype == dtype, (t.dtype, dtype)
+    return t
+
+
+def gemm(a, w, bias=None, *, out_bf16=None, out_f32=None, resid=None, pos=None, scale=1.0, scale_cols=0, gelu=False):
+    """C = epi(a[M,K] @ w[N,K]^T).  a, w bf16 row-major (last dim contiguous); outputs written in place."""
+    _cuda(a, torch.bfloat16), _cuda(w, torch.bfloat16)
+    M, K = a.shape
+    N, K2 = w.shape
+    assert K == K2 and a.stride(1) == 1 and w.stride(1) == 1
+    ep = GemmEpilogue()
+    if out_f32 is not None:
+        _cuda(out_f32, torch.float32)
+        assert out_f32.shape == (M, N) and out_f32.stride(1) == 1
+        ep.out_f32, ep.ld_f32 = out_f32.data_ptr(), out_f32.stride(0)
+    if out_bf16 is not None:
+        _cuda(out_bf16, torch.bfloat16)
+        assert out_bf16.shape == (M, N) and out_bf16.stride(1) == 1
+        ep.out_bf16, ep.ld_bf16 = out_bf16.data_ptr(), out_bf16.stride(0)
+    if bias is not None:
+        _cuda(bias, torch.float32)
+        assert bias.numel() == N and bias.is_contiguous()
+        ep.bias = bias.data_ptr()
+    if resid is not None:
+        _cuda(resid, torch.float32)
+        assert resid.shape == (M, N) and resid.stride(1) == 1
+        ep.resid, ep.ld_resid = resid.data_ptr(), resid.stride(0)
+    if pos is not None:
+        _cuda(pos, torch.float32)
+        assert pos.shape[1] == N and pos.is_contiguous()
+        ep.pos, ep.pos_rows = pos.data_ptr(), pos.shape[0]
+    ep.scale, ep.scale_cols, ep.gelu = float(scale), int(scale_cols), int(bool(gelu))
+    check(lib().desta_gemm_bf16(_p(a), a.stride(0), _p(w), w.stride(0), M, N, K, ctypes.byref(ep), _stream()), "desta_gemm_bf16")
+
+
+def layernorm(x, gamma, beta, eps, *, out_bf16=None, out_f32=None):
+    _cuda(x, torch.float32)
+    M, D = x.shape
+    assert x.stride(1) == 1
+    check(lib().desta_layernorm(_p(x), x.stride(0), _p(gamma), _p(beta), float(eps), M, D,
+                                _p(out_bf16), out_bf16.stride(0) if out_bf16 is not None else 0,
+                                _p(out_f32), out_f32.stride(0) if out_f32 is not None else 0, _stream()), "desta_layernorm")
+
+
+def attention(q, k, v, out, batch, heads, Tq, Tk, scale):
+    """q/k/v/out: 2-D bf16 views [batch*T, >= heads*64] (row stride = leading dim; may be slices of a fused buffer)."""
+    for t in (q, k, v, out):
+        _cuda(t, torch.bfloat16)
+        assert t.stride(1) == 1
+    assert q.shape[0] == batch * Tq and k.shape[0] == batch * Tk and v.shape[0] == batch * Tk and out.shape[0] == batch * Tq
+    check(lib().desta_attention(_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(out), out.stride(0),
+                                batch, heads, Tq, Tk, float(scale), _stream()), "desta_attention")
+
+
+def im2col_k3(x, N, T_in, C, stride, cols):
+    _cuda(x, torch.bfloat16), _cuda(cols, torch.bfloat16)
+    assert x.is_contiguous() and cols.is_contiguous() and cols.numel() == N * (T_in // stride) * 3 * C
+    check(lib().desta_im2col_k3(_p(x), N, T_in, C, stride, _p(cols), _stream()), "desta_im2col_k3")
+
+
+def layer_mix(x, layer_weights, N, Q, out):
+    _cuda(x, torch.float32), _cuda(layer_weights, torch.float32), _cuda(out, torch.float32)
+    taps, rows, D = x.shape
+    assert rows == N * Q and x.is_contiguous() and out.is_contiguous() and layer_weights.is_contiguous()
+    check(lib().desta_layer_mix(_p(x), _p(layer_weights), taps, N, Q, D, _p(out), _stream()), "desta_layer_mix")
+
+
+_plans = {}
+
+
+def logmel_plan(n_mels, device):
+    key = (n_mels, str(device))
+    if key not in _plans:
+        nbytes = lib().desta_logmel_plan_bytes(n_mels)
+        if nbytes == 0:
+            raise ValueError(f"unsupported n_mels {n_mels}")
+        host = np.zeros(nbytes // 4, dtype=np.int32)
+        check(lib().desta_logmel_plan_build(n_mels, host.ctypes.data_as(ctypes.c_void_p), nbytes), "desta_logmel_plan_build")
+        _plans[key] = torch.from_numpy(host).to(device)
+    return _plans[key]
+
+
+def logmel(wave, n_mels, *, n_valid=None, want_bf16_tm=False):
+    """wave [N,480000] f32 CUDA -> (mel f32 [N,n_mels,3000], optional bf16 time-major [N,3000,n_mels])."""
+    _cuda(wave, torch.float32)
+    assert wave.dim() == 2 and wave.shape[1] == 480000 and wave.is_contiguous()
+    N = wave.shape[0]
+    plan = logmel_plan(n_mels, wave.device)
+    out = torch.empty(N, n_mels, 3000, dtype=torch.float32, device=wave.device)
+    out_tm = torch.empty(N, 3000, n_mels, dtype=torch.bfloat16, device=wave.device) if want_bf16_tm else None
+    cmax = torch.empty(max(N, 1), dtype=torch.float32, device=wave.device)
+    if n_valid is not None:
+        _cuda(n_valid, torch.int32)
+    check(lib().desta_logmel(_p(wave), _p(n_valid), N, n_mels, _p(plan), _p(out), _p(out_tm), _p(cmax), _stream()), "desta_logmel")
+    return out, out_tm
+
+
+def splice(input_ids, table, descs, trans_ids, feats, Q, out=None):
+    """descs: list of (prompt, start, n_trans, trans_off); trans_ids: 1-D int64 CUDA tensor (concatenated) or None."""
+    _cuda(input_ids, torch.int64), _cuda(table, torch.bfloat16)
+    B, S = input_ids.shape
+    V, d = table.shape
+    n = len(descs)
+    host = (SpliceDesc * max(n, 1))()
+    for i, (p_, s_, t_, o_) in enumerate(descs):
+        host[i] = SpliceDesc(int(p_), int(s_), int(t_), int(o_))
+    dev = torch.frombuffer(bytearray(bytes(host)), dtype=torch.int32).to(input_ids.device, non_blocking=False)
+    if out is None:
+        out = torch.empty(B, S, d, dtype=torch.bfloat16, device=input_ids.device)
+    row_map = torch.empty(B * S, dtype=torch.int32, device=input_ids.device)
+    feat_dtype = 0
+    if feats is not None:
+        assert feats.is_contiguous() and feats.shape[-1] == d
+        feat_dtype = 0 if feats.dtype == torch.float32 else 1
+        assert feats.dtype in (torch.float32, torch.bfloat16)
+    check(lib().desta_splice(_p(input_ids.contiguous()), _p(table), V, _p(dev), host, n, _p(trans_ids), _p(feats), feat_dtype,
+                             Q, _p(out), B, S, d, _p(row_map), _stream()), "desta_splice")
+    return out

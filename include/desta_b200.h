@@ -1,0 +1,97 @@
+/* libdesta_b200.so — C ABI of the B200-native waveform -> LLM-embedding front-end for DeSTA2.5-Audio.
+ *
+ * Every entry point takes plain device pointers + sizes + a CUDA stream (passed as void*), launches
+ * asynchronously on that stream, allocates nothing, and returns 0 or a negative DESTA_ERR_* code
+ * (message via desta_last_error()).  There is no CPU fallback.
+ *
+ * Each function cites the reference interface it replaces (paths relative to voidful/DeSTA2.5-Audio;
+ * $TF = the pinned third-party `transformers` package holding the arithmetic).
+ */
+#ifndef DESTA_B200_H
+#define DESTA_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DESTA_OK 0
+#define DESTA_ERR_ARG (-1)
+#define DESTA_ERR_CUDA (-2)
+#define DESTA_ERR_SHAPE (-3)
+
+int desta_version(void);
+const char* desta_last_error(void);
+
+/* ---- (1) log-mel: replaces WhisperFeatureExtractor.__call__ -> _torch_extract_fbank_features
+ *      ($TF/models/whisper/feature_extraction_whisper.py:135-164, 189-342), called at
+ *      desta/models/modeling_desta25.py:1570,1583 and desta/trainer/data/simple_dataset.py:239-243. ---- */
+#define DESTA_MEL_SAMPLES 480000
+#define DESTA_MEL_FRAMES 3000
+/* Host-side plan (Hann window, FFT twiddles, sparse slaney mel filters built in fp64, cast fp32).
+ * Call with host_buf == NULL to get the size; the caller copies the filled buffer to the device. */
+size_t desta_logmel_plan_bytes(int n_mels);
+int desta_logmel_plan_build(int n_mels, void* host_buf, size_t bytes);
+/* wave [N,480000] f32 (already right-padded/truncated; n_valid[N] optional: samples >= n_valid[i] read as 0).
+ * out_f32 [N,n_mels,3000] (reference layout) and/or out_bf16_tm [N,3000,n_mels] (time-major, feeds conv1).
+ * clip_max [N] f32 scratch.  plan = device copy of the plan buffer. */
+int desta_logmel(const float* wave, const int32_t* n_valid, int N, int n_mels, const void* plan,
+                 float* out_f32, void* out_bf16_tm, float* clip_max, void* stream);
+
+/* ---- building blocks of (2)/(3): tcgen05 GEMM with fused epilogue.  C = epi(A[M,K] W[N,K]^T), bf16 in, fp32 acc.
+ *      Replaces nn.Linear / Conv1d-as-GEMM calls of $TF/models/whisper/modeling_whisper.py:310-355,404-408,
+ *      $TF/models/bert/modeling_bert.py:168-207,258-259,294-298,339-356, modeling_desta25.py:563-570,606. ---- */
+typedef struct desta_gemm_epilogue {
+  float* out_f32;  int ld_f32;          /* optional fp32 output */
+  void* out_bf16;  int ld_bf16;         /* optional bf16 output */
+  const float* bias;                    /* [N] or NULL */
+  const float* resid; int ld_resid;     /* fp32 residual added last, or NULL */
+  const float* pos;   int pos_rows;     /* fp32 [pos_rows,N] table, row (m % pos_rows) added after activation */
+  float scale;        int scale_cols;   /* columns < scale_cols are multiplied by scale after the bias */
+  int gelu;                             /* erf-GELU after bias/scale */
+} desta_gemm_epilogue;
+int desta_gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int K,
+                    const desta_gemm_epilogue* ep, void* stream);
+
+/* LayerNorm over the last dim (fp32 in; fp32 statistics).  out_bf16 and/or out_f32.
+ * Replaces nn.LayerNorm at modeling_whisper.py:393,403 (eps 1e-5), modeling_bert.py:297,355 (eps 1e-12),
+ * modeling_desta25.py:166 (proj.0). */
+int desta_layernorm(const float* x, int ldx, const float* gamma, const float* beta, float eps, int M, int D,
+                    void* out_bf16, int ld_bf16, float* out_f32, int ld_f32, void* stream);
+
+/* Non-causal multi-head attention  softmax(scale * Q K^T) V, head_dim 64, bf16 in/out, fp32 softmax.
+ * Q rows:  q + (b*Tq + t)*ldq + h*64 ; K/V likewise with Tk, ldk, ldv ; out + (b*Tq + t)*ldo + h*64.
+ * Replaces WhisperAttention (modeling_whisper.py:284-358, scale 1 because q is pre-scaled) and the eager
+ * Bert self/cross attention (modeling_bert.py:168-207, 234-284, scale head_dim^-1/2). */
+int desta_attention(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo,
+                    int batch, int heads, int Tq, int Tk, float scale, void* stream);
+
+/* im2col for the conv stem (modeling_desta25.py:563-564): Conv1d(k=3,pad=1,stride s) as GEMM rows.
+ * x time-major bf16 [N, T_in, C] -> cols bf16 [N*T_out, 3*C] with column index = tap*C + c  (T_out = T_in/stride). */
+int desta_im2col_k3(const void* x, int N, int T_in, int C, int stride, void* cols, void* stream);
+
+/* Q-Former layer mix (modeling_desta25.py:600-604): out[n,q,:] = sum_k softmax(layer_weights[q,:])[k] * x[k,n,q,:]
+ * x fp32 [taps, N*Q, D] -> out fp32 [N*Q, D]. */
+int desta_layer_mix(const float* x, const float* layer_weights, int taps, int N, int Q, int D, float* out, void* stream);
+
+/* ---- (4) splice: replaces the gathers + per-audio scatter loop of
+ *      DeSTA25AudioModel._prepare_inputs_for_llm (modeling_desta25.py:940-1050; gathers :975-982,1009; loop :1014-1045).
+ *      out[b,s,:] = table[input_ids[b,s]] for text rows; rows [start, start+Q) of prompt b <- bf16_rne(audio_feats[i]);
+ *      rows [start+Q, start+Q+T_i) <- table[trans_ids[trans_off[i] + j]].  Later clips win on overlap (loop order). ---- */
+typedef struct desta_splice_desc {
+  int32_t prompt;      /* text_batch_idx */
+  int32_t start;       /* audio_start_position */
+  int32_t n_trans;     /* T_i */
+  int32_t trans_off;   /* offset into trans_ids */
+} desta_splice_desc;
+/* row_map [B*S] int32 scratch (device).  feat_dtype: 0 = fp32, 1 = bf16.  Returns DESTA_ERR_SHAPE if a span
+ * leaves [0,S) (the reference raises at :1041); descs are validated on the host copy `descs_host`. */
+int desta_splice(const int64_t* input_ids, const void* table, int64_t vocab, const desta_splice_desc* descs_dev,
+                 const desta_splice_desc* descs_host, int n_desc, const int64_t* trans_ids, const void* audio_feats,
+                 int feat_dtype, int Q, void* out, int B, int S, int d, int32_t* row_map, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,233 @@
+"""Kernel-level parity on the GPU, through the C ABI (desta_b200.ops -> libdesta_b200.so)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from desta_b200 import ops
+
+
+def _rel(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).item()
+
+
+def _cos(a, b):
+    a, b = a.float().flatten(), b.float().flatten()
+    return (torch.dot(a, b) / (a.norm() * b.norm()).clamp_min(1e-20)).item()
+
+
+# ------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (128, 256, 128), (256, 512, 1280), (1500, 1280, 1280),
+                                   (3000, 384, 240), (200, 1152, 384), (64, 1024, 3072), (4500, 3840, 1280)])
+def test_gemm_plain(M, N, K):
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = (torch.randn(M, K, device="cuda", generator=g)).to(torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.05).to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda", generator=g)
+    out = torch.empty(M, N, device="cuda", dtype=torch.float32)
+    outb = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(a, w, bias, out_f32=out, out_bf16=outb)
+    ref = a.float() @ w.float().t() + bias
+    torch.cuda.synchronize()
+    err = _rel(out, ref)
+    assert err < 2e-5, f"fp32-out rel err {err}"
+    assert _rel(outb, ref) < 6e-3
+
+
+def test_gemm_epilogues():
+    M, N, K = 3000, 1280, 384
+    g = torch.Generator(device="cuda").manual_seed(1)
+    a = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.05).to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda", generator=g)
+    resid = torch.randn(M, N, device="cuda", generator=g)
+    pos = torch.randn(1500, N, device="cuda", generator=g)
+    acc = a.float() @ w.float().t() + bias
+    # q-scale on the first 640 columns
+    out = torch.empty(M, N, device="cuda")
+    ops.gemm(a, w, bias, out_f32=out, scale=0.125, scale_cols=640)
+    ref = acc.clone(); ref[:, :640] *= 0.125
+    assert _rel(out, ref) < 2e-5
+    # gelu + pos
+    ops.gemm(a, w, bias, out_f32=out, gelu=True, pos=pos)
+    ref = torch.nn.functional.gelu(acc) + pos.repeat(2, 1)
+    assert _rel(out, ref) < 2e-5
+    # residual, fp32 + bf16 copy, in-place on the residual buffer
+    buf = resid.clone()
+    tap = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(a, w, bias, out_f32=buf, out_bf16=tap, resid=buf)
+    ref = acc + resid
+    assert _rel(buf, ref) < 2e-5
+    assert torch.equal(tap, buf.to(torch.bfloat16))
+
+
+def test_gemm_strided_output():
+    M, N, K = 300, 256, 128
+    a = torch.randn(M, K, device="cuda").to(torch.bfloat16)
+    w = torch.randn(N, K, device="cuda").to(torch.bfloat16)
+    big = torch.zeros(M, 3 * N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(a, w, None, out_bf16=big[:, N:2 * N])
+    ref = a.float() @ w.float().t()
+    assert _rel(big[:, N:2 * N], ref) < 6e-3
+    assert big[:, :N].abs().max() == 0 and big[:, 2 * N:].abs().max() == 0
+
+
+# ------------------------------------------------------------------ LayerNorm / im2col / mix
+@pytest.mark.parametrize("M,D,eps", [(1500, 1280, 1e-5), (777, 384, 1e-12), (64, 128, 1e-5)])
+def test_layernorm(M, D, eps):
+    x = torch.randn(M, D, device="cuda") * 3 + 1
+    gmm, bta = torch.randn(D, device="cuda"), torch.randn(D, device="cuda")
+    ob = torch.empty(M, D, device="cuda", dtype=torch.bfloat16)
+    of = torch.empty(M, D, device="cuda")
+    ops.layernorm(x, gmm, bta, eps, out_bf16=ob, out_f32=of)
+    ref = torch.nn.functional.layer_norm(x, (D,), gmm, bta, eps)
+    assert (of - ref).abs().max().item() < 2e-5
+    assert torch.equal(ob, of.to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("stride", [1, 2])
+def test_im2col(stride):
+    N, T, C = 2, 3000, 128
+    x = torch.randn(N, T, C, device="cuda").to(torch.bfloat16)
+    cols = torch.empty(N * (T // stride), 3 * C, device="cuda", dtype=torch.bfloat16)
+    ops.im2col_k3(x, N, T, C, stride, cols)
+    xp = torch.nn.functional.pad(x, (0, 0, 1, 1))
+    ref = torch.stack([xp[:, j:j + T:stride][:, : T // stride] for j in range(3)], dim=2).reshape(N * (T // stride), 3 * C)
+    assert torch.equal(cols, ref)
+
+
+def test_layer_mix():
+    taps, N, Q, D = 4, 3, 64, 1280
+    x = torch.randn(taps, N * Q, D, device="cuda")
+    lw = torch.randn(Q, taps, device="cuda")
+    out = torch.empty(N * Q, D, device="cuda")
+    ops.layer_mix(x, lw, N, Q, out)
+    w = torch.softmax(lw, -1)
+    ref = (x.view(taps, N, Q, D).permute(1, 2, 0, 3) * w[None, :, :, None]).sum(2).reshape(N * Q, D)
+    assert (out - ref).abs().max().item() < 1e-5
+
+
+# ------------------------------------------------------------------ attention
+@pytest.mark.parametrize("B,H,Tq,Tk,scale", [(1, 1, 128, 128, 1.0), (2, 3, 128, 256, 0.125), (2, 6, 1500, 1500, 1.0),
+                                             (3, 2, 64, 1500, 0.125), (2, 2, 64, 64, 0.125), (1, 20, 300, 700, 0.3)])
+def test_attention(B, H, Tq, Tk, scale):
+    g = torch.Generator(device="cuda").manual_seed(Tq * 7 + Tk)
+    d = H * 64
+    qkv = torch.randn(B * max(Tq, Tk), 3 * d, device="cuda", generator=g).to(torch.bfloat16)
+    q = qkv[: B * Tq, :d]
+    k = qkv[: B * Tk, d:2 * d]
+    v = qkv[: B * Tk, 2 * d:]
+    out = torch.zeros(B * Tq, d, device="cuda", dtype=torch.bfloat16)
+    ops.attention(q, k, v, out, B, H, Tq, Tk, scale)
+    qf = q.float().reshape(B, Tq, H, 64).transpose(1, 2)
+    kf = k.float().reshape(B, Tk, H, 64).transpose(1, 2)
+    vf = v.float().reshape(B, Tk, H, 64).transpose(1, 2)
+    ref = torch.softmax(qf @ kf.transpose(-1, -2) * scale, -1) @ vf
+    ref = ref.transpose(1, 2).reshape(B * Tq, d)
+    torch.cuda.synchronize()
+    err = _rel(out, ref)
+    assert err < 2e-2 and _cos(out, ref) > 0.9995, f"attention rel err {err} cos {_cos(out, ref)}"
+
+
+def test_attention_peaky_softmax():
+    """Large logits: exercises the lazy O-rescale path (running max grows by more than 2^8)."""
+    B, H, Tq, Tk = 1, 2, 128, 512
+    d = H * 64
+    g = torch.Generator(device="cuda").manual_seed(3)
+    q = (torch.randn(B * Tq, d, device="cuda", generator=g) * 4).to(torch.bfloat16)
+    k = (torch.randn(B * Tk, d, device="cuda", generator=g) * 4).to(torch.bfloat16)
+    k[Tk // 2:] *= 2.0
+    v = torch.randn(B * Tk, d, device="cuda", generator=g).to(torch.bfloat16)
+    out = torch.zeros(B * Tq, d, device="cuda", dtype=torch.bfloat16)
+    ops.attention(q, k, v, out, B, H, Tq, Tk, 1.0)
+    qf = q.float().reshape(B, Tq, H, 64).transpose(1, 2)
+    kf = k.float().reshape(B, Tk, H, 64).transpose(1, 2)
+    vf = v.float().reshape(B, Tk, H, 64).transpose(1, 2)
+    ref = (torch.softmax(qf @ kf.transpose(-1, -2), -1) @ vf).transpose(1, 2).reshape(B * Tq, d)
+    assert _rel(out, ref) < 2e-2
+
+
+# ------------------------------------------------------------------ log-mel
+@pytest.mark.parametrize("n_mels", [80, 128])
+def test_logmel_vs_oracle_and_golden(n_mels, golden_dir):
+    from oracle import logmel as o_mel
+    from oracle.synth import synth_waves
+    kinds = ("noise_full", "speechy_12s", "short_3p5s", "silence", "long_31s", "tone_clip")
+    waves = synth_waves(seed=7, kinds=kinds)
+    padded = np.stack([o_mel.pad_or_truncate(w) for w in waves])
+    mel, mel_tm = ops.logmel(torch.from_numpy(padded).cuda(), n_mels, want_bf16_tm=True)
+    mel = mel.cpu().numpy()
+    ref = o_mel.logmel(waves, n_mels)
+    err = np.abs(mel - ref).max()
+    assert err < 1e-4, f"log-mel max abs err vs oracle {err}"      # north_star tolerance: 1e-4 absolute
+    assert np.all(mel[3] == -1.5)                                   # all-zero clip
+    gold = np.load(os.path.join(golden_dir, "logmel.npz"))
+    assert np.abs(mel[:, ::7, ::5] - gold[f"mel{n_mels}_strided"]).max() < 1e-4
+    assert np.abs(mel[:, :, :32] - gold[f"mel{n_mels}_head"]).max() < 1e-4
+    assert np.abs(mel[:, :, -32:] - gold[f"mel{n_mels}_tail"]).max() < 1e-4
+    tm = mel_tm.float().cpu().numpy().transpose(0, 2, 1)
+    assert np.abs(tm - mel).max() < 1e-2                            # bf16 rounding of values in [-1.5, 2]
+    # ragged input through n_valid instead of host-side zero padding
+    lens = torch.tensor([min(len(w), 480000) for w in waves], dtype=torch.int32, device="cuda")
+    noisy = padded.copy()
+    for i, w in enumerate(waves):
+        noisy[i, min(len(w), 480000):] = 9.0                        # garbage beyond n_valid must be ignored
+    mel2, _ = ops.logmel(torch.from_numpy(noisy).cuda(), n_mels, n_valid=lens)
+    assert np.array_equal(mel2.cpu().numpy(), mel)
+
+
+# ------------------------------------------------------------------ splice
+def _bits(t):
+    return t.contiguous().view(torch.int16).cpu().numpy().view(np.uint16)
+
+
+def test_splice_golden(golden_dir):
+    from oracle.configs import CONFIGS
+    from oracle.weights import make_weights
+    gold = np.load(os.path.join(golden_dir, "micro_path.npz"))
+    cfg = CONFIGS["micro"]
+    W = make_weights(cfg, seed=11)
+    table = W["llm_model.model.embed_tokens.weight"].cuda()
+    feats = torch.from_numpy(gold["feats"]).cuda()
+    trans = [gold["trans0"].reshape(-1), gold["trans1"].reshape(-1), gold["trans2"].reshape(-1)]
+    offs = np.cumsum([0] + [len(t) for t in trans])
+    descs = [(int(p), int(s), len(t), int(o)) for (p, s), t, o in zip(gold["positions"], trans, offs)]
+    tids = torch.from_numpy(np.concatenate(trans).astype(np.int64)).cuda()
+    out = ops.splice(torch.from_numpy(gold["input_ids"]).cuda(), table, descs, tids, feats, cfg.prompt_size)
+    assert np.array_equal(_bits(out), gold["embeds_bits"]), "splice is not bit-exact vs the reference's inputs_embeds"
+
+
+@pytest.mark.parametrize("feat_dtype", [torch.float32, torch.bfloat16])
+def test_splice_vs_oracle(feat_dtype):
+    from oracle import splice as o_sp
+    rng = np.random.default_rng(5)
+    B, S, d, V, Q = 4, 512, 2560, 5000, 64
+    table = (torch.randn(V, d) * 0.02).to(torch.bfloat16)
+    ids = rng.integers(0, V, (B, S))
+    tl = [0, 3, 17, 40, 0, 5]
+    trans = [rng.integers(0, V, t) for t in tl]
+    pos = [(0, 5), (0, 5 + 64 + 0 + 10), (1, 0), (2, 100), (3, 512 - 64), (2, 300)]
+    feats = torch.randn(len(tl), Q, d) * 3
+    feats[0, 0, :8] = torch.tensor([float("inf"), -0.0, 1e-40, 3.3895313892515355e38, 1.0000001, -65504.0, 0.1, 1.00390625])
+    feats = feats.to(feat_dtype)
+    offs = np.cumsum([0] + tl)
+    descs = [(p, s, t, int(o)) for (p, s), t, o in zip(pos, tl, offs)]
+    out = ops.splice(torch.from_numpy(ids).cuda(), table.cuda(), descs, torch.from_numpy(np.concatenate(trans)).cuda(),
+                     feats.cuda(), Q)
+    ref = o_sp.splice(ids, _bits(table), feats.float().numpy(), trans, pos)
+    assert np.array_equal(_bits(out), ref)
+
+
+def test_splice_errors_and_empty():
+    table = torch.randn(100, 64).to(torch.bfloat16).cuda()
+    ids = torch.randint(0, 100, (2, 80)).cuda()
+    out = ops.splice(ids, table, [], None, None, 64)                 # N == 0 fast path: plain embeddings
+    assert torch.equal(out, table[ids])
+    feats = torch.randn(1, 64, 64).cuda()
+    with pytest.raises(ValueError):                                   # span leaves the sequence (reference raises too)
+        ops.splice(ids, table, [(0, 30, 0, 0)], None, feats, 64)
