@@ -1,0 +1,209 @@
+"""Device-side schedule of the hot path: conv stem -> Whisper encoder layers with taps -> Q-Former connector.
+
+This is host code that only sequences launches of libdesta_b200.so kernels over caller-owned buffers (torch is used
+for device memory and the stream).  Arithmetic contract: bf16 GEMM operands, fp32
+accumulation, fp32 residual stream, fp32 LayerNorm / softmax statistics; taps handed to the connector in bf16.
+
+ref: desta/models/modeling_desta25.py:544-608 (forward_whisper), $TF/models/whisper/modeling_whisper.py:380-414,
+$TF/models/bert/modeling_bert.py:379-421.
+"""
+from dataclasses import dataclass
+from typing import Dict, List
+
+import torch
+
+from . import ops
+
+ENC = "whisper.model.encoder."
+CON = "connector."
+
+
+@dataclass
+class PathDims:
+    n_mels: int
+    d_model: int
+    n_heads: int
+    ffn: int
+    n_layers: int
+    tap_layers: List[int]
+    qf_layers: int
+    qf_ffn: int
+    prompt_size: int
+    d_llm: int
+    max_pos: int = 1500
+
+    @property
+    def head_dim(self):
+        return self.d_model // self.n_heads
+
+
+def _bf16(t):
+    return t.detach().to(torch.bfloat16).contiguous()
+
+
+def _f32(t):
+    return t.detach().to(torch.float32).contiguous()
+
+
+class EncoderPack:
+    """Frozen Whisper encoder weights repacked once for the kernels (bf16 GEMM operands, fp32 bias / LN / positions)."""
+
+    def __init__(self, sd: Dict[str, torch.Tensor], dims: PathDims, device):
+        d = dims.d_model
+        dev = torch.device(device)
+
+        def get(name):
+            return sd[ENC + name].to(dev)
+
+        # Conv1d weight [out, in, k] -> GEMM weight [out, k*in] matching im2col column order (tap-major)
+        self.conv1_w = _bf16(get("conv1.weight").permute(0, 2, 1).reshape(d, 3 * dims.n_mels))
+        self.conv1_b = _f32(get("conv1.bias"))
+        self.conv2_w = _bf16(get("conv2.weight").permute(0, 2, 1).reshape(d, 3 * d))
+        self.conv2_b = _f32(get("conv2.bias"))
+        self.pos = _f32(get("embed_positions.weight")[: dims.max_pos])
+        self.layers = []
+        for i in range(dims.n_layers):
+            p = f"layers.{i}."
+            qw, kw, vw = get(p + "self_attn.q_proj.weight"), get(p + "self_attn.k_proj.weight"), get(p + "self_attn.v_proj.weight")
+            qb, vb = get(p + "self_attn.q_proj.bias"), get(p + "self_attn.v_proj.bias")
+            L = dict(
+                ln1_w=_f32(get(p + "self_attn_layer_norm.weight")), ln1_b=_f32(get(p + "self_attn_layer_norm.bias")),
+                qkv_w=_bf16(torch.cat([qw, kw, vw], 0)),
+                qkv_b=_f32(torch.cat([qb, torch.zeros_like(qb), vb], 0)),       # k_proj has no bias
+                o_w=_bf16(get(p + "self_attn.out_proj.weight")), o_b=_f32(get(p + "self_attn.out_proj.bias")),
+                ln2_w=_f32(get(p + "final_layer_norm.weight")), ln2_b=_f32(get(p + "final_layer_norm.bias")),
+                fc1_w=_bf16(get(p + "fc1.weight")), fc1_b=_f32(get(p + "fc1.bias")),
+                fc2_w=_bf16(get(p + "fc2.weight")), fc2_b=_f32(get(p + "fc2.bias")),
+            )
+            self.layers.append(L)
+
+
+class ConnectorPack:
+    """bf16 / fp32 kernel-side copies of the (trainable) connector parameters; rebuilt when a parameter changes."""
+
+    def __init__(self, sd: Dict[str, torch.Tensor], dims: PathDims, device):
+        dev = torch.device(device)
+        d = dims.d_model
+
+        def get(name):
+            return sd[CON + name].to(dev)
+
+        self.layer_weights = _f32(get("layer_weights"))
+        self.prompts = _f32(torch.cat([get(f"layer_prompts.{k}").reshape(dims.prompt_size, d) for k in range(len(dims.tap_layers))], 0))
+        self.layers = []
+        kv_w, kv_b = [], []
+        for l in range(dims.qf_layers):
+            p = f"qformer.layer.{l}."
+            sa, ca = p + "attention.", p + "crossattention."
+            L = dict(
+                s_qkv_w=_bf16(torch.cat([get(sa + "self.query.weight"), get(sa + "self.key.weight"), get(sa + "self.value.weight")], 0)),
+                s_qkv_b=_f32(torch.cat([get(sa + "self.query.bias"), get(sa + "self.key.bias"), get(sa + "self.value.bias")], 0)),
+                s_o_w=_bf16(get(sa + "output.dense.weight")), s_o_b=_f32(get(sa + "output.dense.bias")),
+                s_ln_w=_f32(get(sa + "output.LayerNorm.weight")), s_ln_b=_f32(get(sa + "output.LayerNorm.bias")),
+                c_q_w=_bf16(get(ca + "self.query.weight")), c_q_b=_f32(get(ca + "self.query.bias")),
+                c_o_w=_bf16(get(ca + "output.dense.weight")), c_o_b=_f32(get(ca + "output.dense.bias")),
+                c_ln_w=_f32(get(ca + "output.LayerNorm.weight")), c_ln_b=_f32(get(ca + "output.LayerNorm.bias")),
+                f1_w=_bf16(get(p + "intermediate.dense.weight")), f1_b=_f32(get(p + "intermediate.dense.bias")),
+                f2_w=_bf16(get(p + "output.dense.weight")), f2_b=_f32(get(p + "output.dense.bias")),
+                f_ln_w=_f32(get(p + "output.LayerNorm.weight")), f_ln_b=_f32(get(p + "output.LayerNorm.bias")),
+            )
+            self.layers.append(L)
+            kv_w += [get(ca + "self.key.weight"), get(ca + "self.value.weight")]
+            kv_b += [get(ca + "self.key.bias"), get(ca + "self.value.bias")]
+        # all layers' cross-attention K/V projections of a tap as ONE GEMM (78 % of connector FLOPs)
+        self.kv_w = _bf16(torch.cat(kv_w, 0))          # [L*2d, d]
+        self.kv_b = _f32(torch.cat(kv_b, 0))
+        self.proj_ln_w, self.proj_ln_b = _f32(get("proj.0.weight")), _f32(get("proj.0.bias"))
+        self.proj_w, self.proj_b = _bf16(get("proj.1.weight")), _f32(get("proj.1.bias"))
+
+
+class Workspace:
+    """Caller-owned device buffers for one batch size (the library allocates nothing)."""
+
+    def __init__(self, dims: PathDims, N: int, device, keep_for_backward: bool = False):
+        d, T, Q = dims.d_model, dims.max_pos, dims.prompt_size
+        M = N * T
+        K = len(dims.tap_layers)
+        bf, f32 = torch.bfloat16, torch.float32
+        e = lambda *s, dt=bf: torch.empty(*s, dtype=dt, device=device)  # noqa: E731
+        self.N = N
+        self.cols1 = e(N * 2 * T, 3 * dims.n_mels)
+        self.c1 = e(N * 2 * T, d)
+        self.cols2 = e(M, 3 * d)
+        self.h = e(M, d, dt=f32)
+        self.y = e(M, d)
+        self.qkv = e(M, 3 * d)
+        self.ao = e(M, d)
+        self.ff = e(M, dims.ffn)
+        self.taps = e(K, M, d)
+        self.kv = e(K * M, dims.qf_layers * 2 * d)
+        R = K * N * Q
+        self.R = R
+        self.x_f32 = e(R, d, dt=f32)
+        self.x_bf = e(R, d)
+        self.q_qkv = e(R, 3 * d)
+        self.q_ao = e(R, d)
+        self.q_tmp = e(R, d, dt=f32)
+        self.a_f32 = e(R, d, dt=f32)
+        self.a_bf = e(R, d)
+        self.q_q = e(R, d)
+        self.c_f32 = e(R, d, dt=f32)
+        self.c_bf = e(R, d)
+        self.q_ff = e(R, dims.qf_ffn)
+        self.mix = e(N * Q, d, dt=f32)
+        self.mix_bf = e(N * Q, d)
+
+
+def encoder_forward(enc: EncoderPack, dims: PathDims, ws: Workspace, mel_tm: torch.Tensor):
+    """mel_tm: bf16 time-major log-mel [N, 3000, n_mels].  Fills ws.taps[k] (bf16 [N*1500, d]) for every tap layer."""
+    N, d, T = ws.N, dims.d_model, dims.max_pos
+    hd = dims.head_dim
+    ops.im2col_k3(mel_tm, N, 2 * T, dims.n_mels, 1, ws.cols1)
+    ops.gemm(ws.cols1, enc.conv1_w, enc.conv1_b, out_bf16=ws.c1, gelu=True)
+    ops.im2col_k3(ws.c1, N, 2 * T, d, 2, ws.cols2)
+    ops.gemm(ws.cols2, enc.conv2_w, enc.conv2_b, out_f32=ws.h, gelu=True, pos=enc.pos)
+    tap_idx = 0
+    for i, L in enumerate(enc.layers):
+        ops.layernorm(ws.h, L["ln1_w"], L["ln1_b"], 1e-5, out_bf16=ws.y)
+        ops.gemm(ws.y, L["qkv_w"], L["qkv_b"], out_bf16=ws.qkv, scale=hd ** -0.5, scale_cols=d)
+        ops.attention(ws.qkv[:, :d], ws.qkv[:, d:2 * d], ws.qkv[:, 2 * d:], ws.ao, N, dims.n_heads, T, T, 1.0)
+        ops.gemm(ws.ao, L["o_w"], L["o_b"], out_f32=ws.h, resid=ws.h)
+        ops.layernorm(ws.h, L["ln2_w"], L["ln2_b"], 1e-5, out_bf16=ws.y)
+        ops.gemm(ws.y, L["fc1_w"], L["fc1_b"], out_bf16=ws.ff, gelu=True)
+        if i in dims.tap_layers:
+            ops.gemm(ws.ff, L["fc2_w"], L["fc2_b"], out_f32=ws.h, resid=ws.h, out_bf16=ws.taps[tap_idx])
+            tap_idx += 1
+        else:
+            ops.gemm(ws.ff, L["fc2_w"], L["fc2_b"], out_f32=ws.h, resid=ws.h)
+    assert tap_idx == len(dims.tap_layers)
+
+
+def connector_forward(con: ConnectorPack, dims: PathDims, ws: Workspace, out_f32: torch.Tensor):
+    """Q-Former over the taps in ws.taps (all taps batched as K*N sequences) -> out_f32 [N*Q, d_llm]."""
+    N, d, T, Q = ws.N, dims.d_model, dims.max_pos, dims.prompt_size
+    K = len(dims.tap_layers)
+    hd = dims.head_dim
+    B = K * N
+    scale = hd ** -0.5
+    # cross-attention K/V of every Q-Former layer for every tap: one GEMM over [K*N*1500, d]
+    ops.gemm(ws.taps.view(K * N * T, d), con.kv_w, con.kv_b, out_bf16=ws.kv)
+    # x0 = layer_prompts[k] broadcast over clips
+    ws.x_f32.view(K, N, Q, d).copy_(con.prompts.view(K, 1, Q, d).expand(K, N, Q, d))
+    ws.x_bf.copy_(ws.x_f32)
+    for l, L in enumerate(con.layers):
+        ops.gemm(ws.x_bf, L["s_qkv_w"], L["s_qkv_b"], out_bf16=ws.q_qkv)
+        ops.attention(ws.q_qkv[:, :d], ws.q_qkv[:, d:2 * d], ws.q_qkv[:, 2 * d:], ws.q_ao, B, dims.n_heads, Q, Q, scale)
+        ops.gemm(ws.q_ao, L["s_o_w"], L["s_o_b"], out_f32=ws.q_tmp, resid=ws.x_f32)
+        ops.layernorm(ws.q_tmp, L["s_ln_w"], L["s_ln_b"], 1e-12, out_bf16=ws.a_bf, out_f32=ws.a_f32)
+        ops.gemm(ws.a_bf, L["c_q_w"], L["c_q_b"], out_bf16=ws.q_q)
+        kcol = l * 2 * d
+        ops.attention(ws.q_q, ws.kv[:, kcol:kcol + d], ws.kv[:, kcol + d:kcol + 2 * d], ws.q_ao, B, dims.n_heads, Q, T, scale)
+        ops.gemm(ws.q_ao, L["c_o_w"], L["c_o_b"], out_f32=ws.q_tmp, resid=ws.a_f32)
+        ops.layernorm(ws.q_tmp, L["c_ln_w"], L["c_ln_b"], 1e-12, out_bf16=ws.c_bf, out_f32=ws.c_f32)
+        ops.gemm(ws.c_bf, L["f1_w"], L["f1_b"], out_bf16=ws.q_ff, gelu=True)
+        ops.gemm(ws.q_ff, L["f2_w"], L["f2_b"], out_f32=ws.q_tmp, resid=ws.c_f32)
+        ops.layernorm(ws.q_tmp, L["f_ln_w"], L["f_ln_b"], 1e-12, out_bf16=ws.x_bf, out_f32=ws.x_f32)
+    ops.layer_mix(ws.x_f32.view(K, N * Q, d), con.layer_weights, N, Q, ws.mix)
+    ops.layernorm(ws.mix, con.proj_ln_w, con.proj_ln_b, 1e-5, out_bf16=ws.mix_bf)
+    ops.gemm(ws.mix_bf, con.proj_w, con.proj_b, out_f32=out_f32)
+    return out_f32

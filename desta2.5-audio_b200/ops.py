@@ -6,6 +6,51 @@ import torch
 
 from ._lib import GemmEpilogue, SpliceDesc, check, lib
 
+N_SAMPLES = 480000
+N_FRAMES = 3000
+
+
+# ---- instrumentation (bench.py / profiling only): launch counter and optional per-family CUDA-event timing ----
+STATS = {"launches": 0}
+_PROFILE = None     # when a list: (family, work, unit, start_event, end_event) per op
+
+
+def start_profile():
+    global _PROFILE
+    _PROFILE = []
+
+
+def stop_profile():
+    """Returns {family: {"ms": total device ms, "work": total flops/bytes, "unit": ..., "calls": n}}."""
+    global _PROFILE
+    rec, _PROFILE = _PROFILE, None
+    torch.cuda.synchronize()
+    out = {}
+    for fam, work, unit, e0, e1 in rec:
+        d = out.setdefault(fam, {"ms": 0.0, "work": 0.0, "unit": unit, "calls": 0})
+        d["ms"] += e0.elapsed_time(e1)
+        d["work"] += work
+        d["calls"] += 1
+    return out
+
+
+class _op:
+    def __init__(self, family, launches, work=0.0, unit="flop"):
+        self.family, self.launches, self.work, self.unit = family, launches, work, unit
+
+    def __enter__(self):
+        STATS["launches"] += self.launches
+        if _PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *exc):
+        if _PROFILE is not None and exc[0] is None:
+            self.e1.record()
+            _PROFILE.append((self.family, self.work, self.unit, self.e0, self.e1))
+        return False
+
 
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -50,16 +95,19 @@ def gemm(a, w, bias=None, *, out_bf16=None, out_f32=None, resid=None, pos=None, 
         assert pos.shape[1] == N and pos.is_contiguous()
         ep.pos, ep.pos_rows = pos.data_ptr(), pos.shape[0]
     ep.scale, ep.scale_cols, ep.gelu = float(scale), int(scale_cols), int(bool(gelu))
-    check(lib().desta_gemm_bf16(_p(a), a.stride(0), _p(w), w.stride(0), M, N, K, ctypes.byref(ep), _stream()), "desta_gemm_bf16")
+    with _op("gemm", 1, 2.0 * M * N * K):
+        check(lib().desta_gemm_bf16(_p(a), a.stride(0), _p(w), w.stride(0), M, N, K, ctypes.byref(ep), _stream()), "desta_gemm_bf16")
 
 
 def layernorm(x, gamma, beta, eps, *, out_bf16=None, out_f32=None):
     _cuda(x, torch.float32)
     M, D = x.shape
     assert x.stride(1) == 1
-    check(lib().desta_layernorm(_p(x), x.stride(0), _p(gamma), _p(beta), float(eps), M, D,
-                                _p(out_bf16), out_bf16.stride(0) if out_bf16 is not None else 0,
-                                _p(out_f32), out_f32.stride(0) if out_f32 is not None else 0, _stream()), "desta_layernorm")
+    nbytes = M * D * (4 + (2 if out_bf16 is not None else 0) + (4 if out_f32 is not None else 0))
+    with _op("layernorm", 1, nbytes, "byte"):
+        check(lib().desta_layernorm(_p(x), x.stride(0), _p(gamma), _p(beta), float(eps), M, D,
+                                    _p(out_bf16), out_bf16.stride(0) if out_bf16 is not None else 0,
+                                    _p(out_f32), out_f32.stride(0) if out_f32 is not None else 0, _stream()), "desta_layernorm")
 
 
 def attention(q, k, v, out, batch, heads, Tq, Tk, scale):
@@ -68,21 +116,24 @@ def attention(q, k, v, out, batch, heads, Tq, Tk, scale):
         _cuda(t, torch.bfloat16)
         assert t.stride(1) == 1
     assert q.shape[0] == batch * Tq and k.shape[0] == batch * Tk and v.shape[0] == batch * Tk and out.shape[0] == batch * Tq
-    check(lib().desta_attention(_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(out), out.stride(0),
-                                batch, heads, Tq, Tk, float(scale), _stream()), "desta_attention")
+    with _op("attention", 1, 4.0 * batch * heads * Tq * Tk * 64):
+        check(lib().desta_attention(_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(out), out.stride(0),
+                                    batch, heads, Tq, Tk, float(scale), _stream()), "desta_attention")
 
 
 def im2col_k3(x, N, T_in, C, stride, cols):
     _cuda(x, torch.bfloat16), _cuda(cols, torch.bfloat16)
     assert x.is_contiguous() and cols.is_contiguous() and cols.numel() == N * (T_in // stride) * 3 * C
-    check(lib().desta_im2col_k3(_p(x), N, T_in, C, stride, _p(cols), _stream()), "desta_im2col_k3")
+    with _op("im2col", 1, cols.numel() * 4, "byte"):
+        check(lib().desta_im2col_k3(_p(x), N, T_in, C, stride, _p(cols), _stream()), "desta_im2col_k3")
 
 
 def layer_mix(x, layer_weights, N, Q, out):
     _cuda(x, torch.float32), _cuda(layer_weights, torch.float32), _cuda(out, torch.float32)
     taps, rows, D = x.shape
     assert rows == N * Q and x.is_contiguous() and out.is_contiguous() and layer_weights.is_contiguous()
-    check(lib().desta_layer_mix(_p(x), _p(layer_weights), taps, N, Q, D, _p(out), _stream()), "desta_layer_mix")
+    with _op("layer_mix", 1, (x.numel() + out.numel()) * 4, "byte"):
+        check(lib().desta_layer_mix(_p(x), _p(layer_weights), taps, N, Q, D, _p(out), _stream()), "desta_layer_mix")
 
 
 _plans = {}
@@ -111,7 +162,9 @@ def logmel(wave, n_mels, *, n_valid=None, want_bf16_tm=False):
     cmax = torch.empty(max(N, 1), dtype=torch.float32, device=wave.device)
     if n_valid is not None:
         _cuda(n_valid, torch.int32)
-    check(lib().desta_logmel(_p(wave), _p(n_valid), N, n_mels, _p(plan), _p(out), _p(out_tm), _p(cmax), _stream()), "desta_logmel")
+    nbytes = N * (480000 * 4 + n_mels * 3000 * 4)      # algorithmic bytes: waveform in + fp32 log-mel out
+    with _op("logmel", 2, nbytes, "byte"):
+        check(lib().desta_logmel(_p(wave), _p(n_valid), N, n_mels, _p(plan), _p(out), _p(out_tm), _p(cmax), _stream()), "desta_logmel")
     return out, out_tm
 
 
@@ -133,6 +186,10 @@ def splice(input_ids, table, descs, trans_ids, feats, Q, out=None):
         assert feats.is_contiguous() and feats.shape[-1] == d
         feat_dtype = 0 if feats.dtype == torch.float32 else 1
         assert feats.dtype in (torch.float32, torch.bfloat16)
-    check(lib().desta_splice(_p(input_ids.contiguous()), _p(table), V, _p(dev), host, n, _p(trans_ids), _p(feats), feat_dtype,
-                             Q, _p(out), B, S, d, _p(row_map), _stream()), "desta_splice")
+    fb = 4 if feat_dtype == 0 else 2
+    n_audio_rows = n * Q
+    nbytes = B * S * 8 + (B * S - n_audio_rows) * d * 2 + n_audio_rows * d * fb + B * S * d * 2
+    with _op("splice", 2, nbytes, "byte"):
+        check(lib().desta_splice(_p(input_ids.contiguous()), _p(table), V, _p(dev), host, n, _p(trans_ids), _p(feats), feat_dtype,
+                                 Q, _p(out), B, S, d, _p(row_map), _stream()), "desta_splice")
     return out

@@ -1,0 +1,109 @@
+"""Drop-in for the reference's WhisperPerception (ref: desta/models/modeling_desta25.py:498-627).
+
+Same call signature and return value:
+    perception(input_features=..., transcription_embeddings_list=...) -> (audio_features [N, prompt_size, d_llm], [prompt_size]*N)
+Same attributes: `.whisper` (frozen HF WhisperForConditionalGeneration: the freeze loops at :1451-1453 and
+`perception.whisper.generate` at :1586 keep working) and `.connector` (trainable parameters with the reference's
+names).  `input_features` may be the reference's log-mel [N, n_mels, 3000] or, from desta_b200.processor, the padded
+waveform [N, 480000] (then the log-mel kernel runs on the device).
+"""
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import engine, ops
+from .engine import ConnectorPack, EncoderPack, PathDims, Workspace
+
+
+class WhisperPerceptionB200(nn.Module):
+    def __init__(self, whisper: nn.Module, connector: nn.Module, tap_layers: List[int], prompt_size: int):
+        super().__init__()
+        self.whisper = whisper
+        self.connector = connector
+        ecfg = whisper.model.encoder.config
+        qcfg = connector.qformer.config
+        self.dims = PathDims(
+            n_mels=ecfg.num_mel_bins, d_model=ecfg.d_model, n_heads=ecfg.encoder_attention_heads, ffn=ecfg.encoder_ffn_dim,
+            n_layers=ecfg.encoder_layers, tap_layers=list(tap_layers), qf_layers=qcfg.num_hidden_layers,
+            qf_ffn=qcfg.intermediate_size, prompt_size=prompt_size, d_llm=connector.proj[1].out_features,
+            max_pos=ecfg.max_source_positions)
+        if self.dims.head_dim != 64:
+            raise NotImplementedError("the sm_100a attention kernel is specialised for head_dim 64 (all Whisper sizes)")
+        self._enc_pack = None
+        self._con_pack = None
+        self._con_versions = None
+        self._ws = {}
+
+    # ---- reference-compatible constructor: wrap an existing reference WhisperPerception ----
+    @classmethod
+    def from_reference(cls, ref_perception):
+        con = ref_perception.connector
+        return cls(ref_perception.whisper, con, list(con.config.target_layer_ids), ref_perception.config.prompt_size)
+
+    def _device(self):
+        return self.whisper.model.encoder.conv1.weight.device
+
+    def _packs(self):
+        dev = self._device()
+        if self._enc_pack is None or self._enc_pack.pos.device != dev:
+            sd = {"whisper.model.encoder." + k: v for k, v in self.whisper.model.encoder.state_dict().items()}
+            self._enc_pack = EncoderPack(sd, self.dims, dev)      # encoder is frozen (:1451-1453): packed once
+        versions = tuple(p._version for p in self.connector.parameters())
+        if self._con_pack is None or versions != self._con_versions or self._con_pack.proj_b.device != dev:
+            sd = {"connector." + k: v for k, v in self.connector.state_dict().items()}
+            self._con_pack = ConnectorPack(sd, self.dims, dev)    # refreshed after every optimizer step
+            self._con_versions = versions
+        return self._enc_pack, self._con_pack
+
+    def _workspace(self, N):
+        dev = self._device()
+        key = (N, str(dev))
+        if key not in self._ws:
+            self._ws = {key: Workspace(self.dims, N, dev)}        # keep one batch size resident
+        return self._ws[key]
+
+    def mel_time_major(self, input_features: torch.Tensor) -> torch.Tensor:
+        dev = self._device()
+        x = input_features
+        if x.dim() == 2:                                           # padded waveform from the processor shim
+            if x.shape[-1] != ops.N_SAMPLES:
+                raise ValueError(f"waveform input must be padded/truncated to {ops.N_SAMPLES} samples, found {x.shape[-1]}")
+            wave = x.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
+            _, mel_tm = ops.logmel(wave, self.dims.n_mels, want_bf16_tm=True)
+            return mel_tm
+        expected = self.dims.max_pos * 2
+        if x.shape[-1] != expected:                                # same check / message as modeling_desta25.py:555-560
+            raise ValueError(f"Whisper expects the mel input features to be of length {expected}, but found "
+                             f"{x.shape[-1]}. Make sure to pad the input mel features to {expected}.")
+        # reference-style input (log-mel computed by the caller): layout change only
+        return x.to(device=dev, non_blocking=True).transpose(1, 2).to(torch.bfloat16).contiguous()
+
+    @torch.no_grad()
+    def forward_features(self, input_features: torch.Tensor) -> torch.Tensor:
+        enc, con = self._packs()
+        N = input_features.size(0)
+        ws = self._workspace(N)
+        mel_tm = self.mel_time_major(input_features)
+        engine.encoder_forward(enc, self.dims, ws, mel_tm)
+        out = torch.empty(N * self.dims.prompt_size, self.dims.d_llm, dtype=torch.float32, device=mel_tm.device)
+        engine.connector_forward(con, self.dims, ws, out)
+        return out.view(N, self.dims.prompt_size, self.dims.d_llm)
+
+    def taps(self, input_features: torch.Tensor):
+        """The four tapped hidden states (bf16 [N, 1500, d]) — exposed for parity tests."""
+        enc, _ = self._packs()
+        N = input_features.size(0)
+        ws = self._workspace(N)
+        engine.encoder_forward(enc, self.dims, ws, self.mel_time_major(input_features))
+        return [ws.taps[k].view(N, self.dims.max_pos, self.dims.d_model) for k in range(len(self.dims.tap_layers))]
+
+    def forward(self, input_features: torch.Tensor, attention_mask: Optional[torch.Tensor] = None,
+                transcription_embeddings_list: Optional[List[torch.Tensor]] = None, **kwargs):
+        bs = input_features.size(0)
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.connector.parameters()):
+            from .autograd import connector_training_forward
+            feats = connector_training_forward(self, input_features)
+        else:
+            feats = self.forward_features(input_features)
+        return feats, [self.dims.prompt_size] * bs

@@ -1,0 +1,72 @@
+"""Processor shim (boundary b1): keeps the `processor(list_of_waveforms, sampling_rate=16000, return_tensors="pt")
+.input_features` call of the reference (ref: desta/models/modeling_desta25.py:1570,1583;
+desta/trainer/data/simple_dataset.py:239-243) but returns the right-padded / truncated WAVEFORM [N, 480000] fp32
+instead of a CPU log-mel: the log-mel runs on the GPU inside WhisperPerceptionB200 (DataLoader workers cannot touch
+CUDA).  Everything else is delegated to the wrapped WhisperProcessor (batch_decode, tokenizer, feature_extractor...).
+"""
+import numpy as np
+import torch
+
+N_SAMPLES = 480000
+SAMPLING_RATE = 16000
+
+
+def pad_or_truncate_batch(raw_speech) -> np.ndarray:
+    """$TF/models/whisper/feature_extraction_whisper.py:296-320: first 480000 samples, zero right-padding."""
+    if isinstance(raw_speech, np.ndarray) and raw_speech.ndim == 2:
+        clips = list(raw_speech)
+    elif isinstance(raw_speech, (list, tuple)) and len(raw_speech) and isinstance(raw_speech[0], (np.ndarray, list, tuple)):
+        clips = list(raw_speech)
+    else:
+        clips = [raw_speech]
+    out = np.zeros((len(clips), N_SAMPLES), dtype=np.float32)
+    lengths = np.zeros(len(clips), dtype=np.int32)
+    for i, c in enumerate(clips):
+        c = np.asarray(c, dtype=np.float32).reshape(-1)
+        if c.ndim != 1:
+            raise ValueError("Only mono-channel audio is supported")
+        n = min(c.shape[0], N_SAMPLES)
+        out[i, :n] = c[:n]
+        lengths[i] = n
+    return out, lengths
+
+
+class _Features(dict):
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+
+    def to(self, *a, **k):
+        return _Features({n: (v.to(*a, **k) if torch.is_tensor(v) else v) for n, v in self.items()})
+
+
+class WaveformProcessor:
+    def __init__(self, wrapped=None, sampling_rate: int = SAMPLING_RATE):
+        self._wrapped = wrapped
+        self.sampling_rate = sampling_rate
+
+    def __call__(self, raw_speech=None, sampling_rate=None, return_tensors="pt", **kwargs):
+        if raw_speech is None:
+            raw_speech = kwargs.pop("audio", None)
+        if sampling_rate is not None and sampling_rate != self.sampling_rate:
+            # same error as WhisperFeatureExtractor.__call__ (feature_extraction_whisper.py:261-267)
+            raise ValueError(
+                f"The model corresponding to this feature extractor: WhisperFeatureExtractor was trained using a"
+                f" sampling rate of {self.sampling_rate}. Please make sure that the provided `raw_speech` input"
+                f" was sampled with {self.sampling_rate} and not {sampling_rate}.")
+        wave, lengths = pad_or_truncate_batch(raw_speech)
+        feats = torch.from_numpy(wave) if return_tensors == "pt" else wave
+        return _Features(input_features=feats, num_samples=torch.from_numpy(lengths) if return_tensors == "pt" else lengths)
+
+    def mel_features(self, *a, **k):
+        """Genuine log-mel through the wrapped processor (the ASR pass at modeling_desta25.py:1583-1590 needs it)."""
+        if self._wrapped is None:
+            raise RuntimeError("no wrapped WhisperProcessor")
+        return self._wrapped(*a, **k)
+
+    def __getattr__(self, name):
+        if name.startswith("_") or self._wrapped is None:
+            raise AttributeError(name)
+        return getattr(self._wrapped, name)
