@@ -27,7 +27,19 @@ EXPORTS = {
     "desta_layernorm": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_float, c_int, c_int, c_void_p, c_int, c_void_p,
                                 c_int, c_void_p]),
     "desta_attention": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int,
-                                c_int, c_float, c_void_p]),
+                                c_int, c_float, c_void_p, c_void_p]),
+    "desta_gemm_bf16_wgrad": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "desta_attention_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int,
+                                    c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                    c_float, c_void_p]),
+    "desta_layernorm_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_float, c_int, c_int, c_void_p, c_int,
+                                    c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "desta_gelu_fwd": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "desta_gelu_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "desta_colsum": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "desta_layer_mix_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "desta_cast_f32_bf16": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "desta_splice_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "desta_im2col_k3": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "desta_layer_mix": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "desta_splice": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, POINTER(SpliceDesc), c_int, c_void_p, c_void_p, c_int,

@@ -1,0 +1,257 @@
+"""Connector training path: forward that keeps the activations the backward needs, and the hand-written backward
+(row a6 of the scope table: autograd of desta/models/modeling_desta25.py:587-606 over $TF/models/bert/modeling_bert.py).
+
+Only the connector's parameters receive gradients: the Whisper encoder is frozen (modeling_desta25.py:1451-1453), so
+taps are constants and the K/V projections need a weight gradient but no data gradient.  Dropout is not applied
+(eval-mode semantics; see DESIGN.md "Dropout").
+
+The autograd.Function exposes every connector parameter as an input so that HF Trainer / Adafactor / DDP see ordinary
+`.grad`s on the reference's own parameter names.
+"""
+from typing import Dict, List
+
+import torch
+
+from . import engine, ops
+from .engine import CON, PathDims
+
+
+def _bf16_t(w):
+    return w.detach().to(torch.bfloat16).t().contiguous()
+
+
+class ConnectorTPack:
+    """Transposed bf16 weights for the data-gradient GEMMs (dX = dY · W is run as a TN GEMM against W^T)."""
+
+    def __init__(self, sd: Dict[str, torch.Tensor], dims: PathDims, device):
+        dev = torch.device(device)
+
+        def get(name):
+            return sd[CON + name].to(dev)
+
+        self.layers = []
+        for l in range(dims.qf_layers):
+            p = f"qformer.layer.{l}."
+            sa, ca = p + "attention.", p + "crossattention."
+            self.layers.append(dict(
+                s_qkv=_bf16_t(torch.cat([get(sa + "self.query.weight"), get(sa + "self.key.weight"), get(sa + "self.value.weight")], 0)),
+                s_o=_bf16_t(get(sa + "output.dense.weight")),
+                c_q=_bf16_t(get(ca + "self.query.weight")),
+                c_o=_bf16_t(get(ca + "output.dense.weight")),
+                f1=_bf16_t(get(p + "intermediate.dense.weight")),
+                f2=_bf16_t(get(p + "output.dense.weight")),
+            ))
+        self.proj = _bf16_t(get("proj.1.weight"))
+
+
+class TrainState:
+    """Saved activations (per Q-Former layer) + gradient buffers for one batch size."""
+
+    def __init__(self, dims: PathDims, N: int, device):
+        d, Q, T = dims.d_model, dims.prompt_size, dims.max_pos
+        K, L, H = len(dims.tap_layers), dims.qf_layers, dims.n_heads
+        R, B = K * N * Q, K * N
+        bf, f32 = torch.bfloat16, torch.float32
+        e = lambda *s, dt=bf: torch.empty(*s, dtype=dt, device=device)  # noqa: E731
+        self.N = N
+        self.layers = [dict(x_bf=e(R, d), x_f32=e(R, d, dt=f32), qkv=e(R, 3 * d), lse_s=e(B * H * Q, dt=f32), ao_s=e(R, d),
+                            t1=e(R, d, dt=f32), a_bf=e(R, d), a_f32=e(R, d, dt=f32), q_c=e(R, d), lse_c=e(B * H * Q, dt=f32),
+                            ao_c=e(R, d), t2=e(R, d, dt=f32), c_bf=e(R, d), c_f32=e(R, d, dt=f32), h1=e(R, dims.qf_ffn),
+                            f=e(R, dims.qf_ffn), t3=e(R, d, dt=f32)) for _ in range(L)]
+        self.x_out = e(R, d, dt=f32)
+        self.x_out_bf = e(R, d)
+        self.mix = e(N * Q, d, dt=f32)
+        self.mix_bf = e(N * Q, d)
+        # backward scratch
+        self.dkv = e(K * N * T, L * 2 * d)
+        self.g_f32_a = e(R, d, dt=f32)
+        self.g_f32_b = e(R, d, dt=f32)
+        self.g_bf_a = e(R, d)
+        self.g_bf_b = e(R, d)
+        self.g_qkv = e(R, 3 * d)
+        self.g_ff = e(R, dims.qf_ffn)
+        self.g_h1 = e(R, dims.qf_ffn)
+        self.g_out_bf = e(N * Q, dims.d_llm)
+        self.g_mix = e(N * Q, d, dt=f32)
+        self.g_mixn = e(N * Q, d, dt=f32)
+        self.g_x = e(R, d, dt=f32)
+        # gradient buffers (fp32, fused like the packed weights)
+        z = lambda *s: torch.zeros(*s, dtype=f32, device=device)  # noqa: E731
+        self.grads = dict(layer_weights=z(Q, K), prompts=z(K * Q, d), kv_w=z(L * 2 * d, d), kv_b=z(L * 2 * d),
+                          proj_ln_w=z(d), proj_ln_b=z(d), proj_w=z(dims.d_llm, d), proj_b=z(dims.d_llm))
+        self.lgrads = [dict(s_qkv_w=z(3 * d, d), s_qkv_b=z(3 * d), s_o_w=z(d, d), s_o_b=z(d), s_ln_w=z(d), s_ln_b=z(d),
+                            c_q_w=z(d, d), c_q_b=z(d), c_o_w=z(d, d), c_o_b=z(d), c_ln_w=z(d), c_ln_b=z(d),
+                            f1_w=z(dims.qf_ffn, d), f1_b=z(dims.qf_ffn), f2_w=z(d, dims.qf_ffn), f2_b=z(d),
+                            f_ln_w=z(d), f_ln_b=z(d)) for _ in range(L)]
+
+    def zero_grads(self):
+        for t in self.grads.values():
+            t.zero_()
+        for g in self.lgrads:
+            for t in g.values():
+                t.zero_()
+
+
+def connector_forward_train(con, dims: PathDims, ws, st: TrainState, out_f32):
+    N, d, T, Q = ws.N, dims.d_model, dims.max_pos, dims.prompt_size
+    K, H = len(dims.tap_layers), dims.n_heads
+    B = K * N
+    scale = dims.head_dim ** -0.5
+    ops.gemm(ws.taps.view(K * N * T, d), con.kv_w, con.kv_b, out_bf16=ws.kv)
+    x_f32, x_bf = st.layers[0]["x_f32"], st.layers[0]["x_bf"]
+    x_f32.view(K, N, Q, d).copy_(con.prompts.view(K, 1, Q, d).expand(K, N, Q, d))
+    x_bf.copy_(x_f32)
+    for l, (L, S) in enumerate(zip(con.layers, st.layers)):
+        ops.gemm(S["x_bf"], L["s_qkv_w"], L["s_qkv_b"], out_bf16=S["qkv"])
+        ops.attention(S["qkv"][:, :d], S["qkv"][:, d:2 * d], S["qkv"][:, 2 * d:], S["ao_s"], B, H, Q, Q, scale, lse=S["lse_s"])
+        ops.gemm(S["ao_s"], L["s_o_w"], L["s_o_b"], out_f32=S["t1"], resid=S["x_f32"])
+        ops.layernorm(S["t1"], L["s_ln_w"], L["s_ln_b"], 1e-12, out_bf16=S["a_bf"], out_f32=S["a_f32"])
+        ops.gemm(S["a_bf"], L["c_q_w"], L["c_q_b"], out_bf16=S["q_c"])
+        kc = l * 2 * d
+        ops.attention(S["q_c"], ws.kv[:, kc:kc + d], ws.kv[:, kc + d:kc + 2 * d], S["ao_c"], B, H, Q, T, scale, lse=S["lse_c"])
+        ops.gemm(S["ao_c"], L["c_o_w"], L["c_o_b"], out_f32=S["t2"], resid=S["a_f32"])
+        ops.layernorm(S["t2"], L["c_ln_w"], L["c_ln_b"], 1e-12, out_bf16=S["c_bf"], out_f32=S["c_f32"])
+        ops.gemm(S["c_bf"], L["f1_w"], L["f1_b"], out_bf16=S["h1"])          # pre-activation kept for the backward
+        ops.gelu_fwd(S["h1"], S["f"])
+        ops.gemm(S["f"], L["f2_w"], L["f2_b"], out_f32=S["t3"], resid=S["c_f32"])
+        nxt = st.layers[l + 1] if l + 1 < len(st.layers) else None
+        ops.layernorm(S["t3"], L["f_ln_w"], L["f_ln_b"], 1e-12,
+                      out_bf16=nxt["x_bf"] if nxt else st.x_out_bf, out_f32=nxt["x_f32"] if nxt else st.x_out)
+    ops.layer_mix(st.x_out.view(K, N * Q, d), con.layer_weights, N, Q, st.mix)
+    ops.layernorm(st.mix, con.proj_ln_w, con.proj_ln_b, 1e-5, out_bf16=st.mix_bf)
+    ops.gemm(st.mix_bf, con.proj_w, con.proj_b, out_f32=out_f32)
+    return out_f32
+
+
+def connector_backward(con, conT: ConnectorTPack, dims: PathDims, ws, st: TrainState, grad_out):
+    """grad_out fp32 [N*Q, d_llm] -> fills st.grads / st.lgrads (+=; call st.zero_grads() first)."""
+    N, d, T, Q = ws.N, dims.d_model, dims.max_pos, dims.prompt_size
+    K, H = len(dims.tap_layers), dims.n_heads
+    B, R = K * N, K * N * Q
+    scale = dims.head_dim ** -0.5
+    G = st.grads
+    # ---- proj: out = LN(mix) Wp^T + bp ----
+    ops.cast_bf16(grad_out, st.g_out_bf)
+    ops.gemm_wgrad(st.g_out_bf, st.mix_bf, G["proj_w"])
+    ops.colsum(grad_out, G["proj_b"])
+    ops.gemm(st.g_out_bf, conT.proj, None, out_f32=st.g_mixn)                       # d(LN out)
+    ops.layernorm_bwd(st.g_mixn, st.mix, con.proj_ln_w, 1e-5, G["proj_ln_w"], G["proj_ln_b"], dx_f32=st.g_mix)
+    # ---- layer mix ----
+    ops.layer_mix_bwd(st.g_mix, st.x_out.view(K, N * Q, d), con.layer_weights, N, Q, st.g_x.view(K, N * Q, d), G["layer_weights"])
+    dx = st.g_x                                                                      # grad wrt the layer output x' (fp32)
+    for l in range(len(con.layers) - 1, -1, -1):
+        L, LT, S, g = con.layers[l], conT.layers[l], st.layers[l], st.lgrads[l]
+        # x' = LN(t3)
+        ops.layernorm_bwd(dx, S["t3"], L["f_ln_w"], 1e-12, g["f_ln_w"], g["f_ln_b"], dx_f32=st.g_f32_a, dx_bf16=st.g_bf_a)
+        # t3 = f W2^T + b2 + c
+        ops.gemm_wgrad(st.g_bf_a, S["f"], g["f2_w"])
+        ops.colsum(st.g_f32_a, g["f2_b"])
+        ops.gemm(st.g_bf_a, LT["f2"], None, out_bf16=st.g_ff)                       # df
+        ops.gelu_bwd(st.g_ff, S["h1"], st.g_h1)                                     # dh1
+        # h1 = c W1^T + b1
+        ops.gemm_wgrad(st.g_h1, S["c_bf"], g["f1_w"])
+        ops.colsum(st.g_h1, g["f1_b"])
+        ops.gemm(st.g_h1, LT["f1"], None, out_f32=st.g_f32_b, resid=st.g_f32_a)     # dc = dt3 + dh1 W1
+        # c = LN(t2)
+        ops.layernorm_bwd(st.g_f32_b, S["t2"], L["c_ln_w"], 1e-12, g["c_ln_w"], g["c_ln_b"], dx_f32=st.g_f32_a, dx_bf16=st.g_bf_a)
+        # t2 = ao_c Wco^T + b + a
+        ops.gemm_wgrad(st.g_bf_a, S["ao_c"], g["c_o_w"])
+        ops.colsum(st.g_f32_a, g["c_o_b"])
+        ops.gemm(st.g_bf_a, LT["c_o"], None, out_bf16=st.g_bf_b)                    # d(ao_c)
+        kc = l * 2 * d
+        ops.attention_bwd(S["q_c"], ws.kv[:, kc:kc + d], ws.kv[:, kc + d:kc + 2 * d], S["ao_c"], st.g_bf_b, S["lse_c"],
+                          st.g_qkv[:, :d], st.dkv[:, kc:kc + d], st.dkv[:, kc + d:kc + 2 * d], B, H, Q, T, scale)
+        dq_c = st.g_qkv[:, :d]
+        # q_c = a Wq^T + bq
+        ops.gemm_wgrad(dq_c, S["a_bf"], g["c_q_w"])
+        ops.colsum(dq_c, g["c_q_b"])
+        ops.gemm(dq_c, LT["c_q"], None, out_f32=st.g_f32_b, resid=st.g_f32_a)        # da = dt2 + dq_c Wq
+        # a = LN(t1)
+        ops.layernorm_bwd(st.g_f32_b, S["t1"], L["s_ln_w"], 1e-12, g["s_ln_w"], g["s_ln_b"], dx_f32=st.g_f32_a, dx_bf16=st.g_bf_a)
+        # t1 = ao_s Wso^T + b + x
+        ops.gemm_wgrad(st.g_bf_a, S["ao_s"], g["s_o_w"])
+        ops.colsum(st.g_f32_a, g["s_o_b"])
+        ops.gemm(st.g_bf_a, LT["s_o"], None, out_bf16=st.g_bf_b)                    # d(ao_s)
+        ops.attention_bwd(S["qkv"][:, :d], S["qkv"][:, d:2 * d], S["qkv"][:, 2 * d:], S["ao_s"], st.g_bf_b, S["lse_s"],
+                          st.g_qkv[:, :d], st.g_qkv[:, d:2 * d], st.g_qkv[:, 2 * d:], B, H, Q, Q, scale)
+        # qkv = x Wqkv^T + b
+        ops.gemm_wgrad(st.g_qkv, S["x_bf"], g["s_qkv_w"])
+        ops.colsum(st.g_qkv, g["s_qkv_b"])
+        ops.gemm(st.g_qkv, LT["s_qkv"], None, out_f32=st.g_x, resid=st.g_f32_a)      # dx = dt1 + dqkv Wqkv
+        dx = st.g_x
+    # ---- learned prompts: x0[k, n] = layer_prompts[k] for every clip n ----
+    for k in range(K):
+        ops.colsum(dx.view(K, N, Q * d)[k], G["prompts"].view(K, Q * d)[k])
+    # ---- cross-attention K/V projections of all layers: one weight-gradient GEMM over all taps' rows ----
+    ops.gemm_wgrad(st.dkv, ws.taps.view(K * N * T, d), G["kv_w"])
+    ops.colsum(st.dkv, G["kv_b"])
+
+
+def param_order(connector) -> List[str]:
+    return [n for n, _ in connector.named_parameters()]
+
+
+def grads_by_name(st: TrainState, dims: PathDims) -> Dict[str, torch.Tensor]:
+    d, Q = dims.d_model, dims.prompt_size
+    G = st.grads
+    out = {"layer_weights": G["layer_weights"], "proj.0.weight": G["proj_ln_w"], "proj.0.bias": G["proj_ln_b"],
+           "proj.1.weight": G["proj_w"], "proj.1.bias": G["proj_b"]}
+    for k in range(len(dims.tap_layers)):
+        out[f"layer_prompts.{k}"] = G["prompts"][k * Q:(k + 1) * Q].view(1, Q, d)
+    for l, g in enumerate(st.lgrads):
+        p = f"qformer.layer.{l}."
+        for i, nm in enumerate(("query", "key", "value")):
+            out[p + f"attention.self.{nm}.weight"] = g["s_qkv_w"][i * d:(i + 1) * d]
+            out[p + f"attention.self.{nm}.bias"] = g["s_qkv_b"][i * d:(i + 1) * d]
+        out[p + "attention.output.dense.weight"], out[p + "attention.output.dense.bias"] = g["s_o_w"], g["s_o_b"]
+        out[p + "attention.output.LayerNorm.weight"], out[p + "attention.output.LayerNorm.bias"] = g["s_ln_w"], g["s_ln_b"]
+        out[p + "crossattention.self.query.weight"], out[p + "crossattention.self.query.bias"] = g["c_q_w"], g["c_q_b"]
+        kc = l * 2 * d
+        out[p + "crossattention.self.key.weight"] = G["kv_w"][kc:kc + d]
+        out[p + "crossattention.self.key.bias"] = G["kv_b"][kc:kc + d]
+        out[p + "crossattention.self.value.weight"] = G["kv_w"][kc + d:kc + 2 * d]
+        out[p + "crossattention.self.value.bias"] = G["kv_b"][kc + d:kc + 2 * d]
+        out[p + "crossattention.output.dense.weight"], out[p + "crossattention.output.dense.bias"] = g["c_o_w"], g["c_o_b"]
+        out[p + "crossattention.output.LayerNorm.weight"], out[p + "crossattention.output.LayerNorm.bias"] = g["c_ln_w"], g["c_ln_b"]
+        out[p + "intermediate.dense.weight"], out[p + "intermediate.dense.bias"] = g["f1_w"], g["f1_b"]
+        out[p + "output.dense.weight"], out[p + "output.dense.bias"] = g["f2_w"], g["f2_b"]
+        out[p + "output.LayerNorm.weight"], out[p + "output.LayerNorm.bias"] = g["f_ln_w"], g["f_ln_b"]
+    return out
+
+
+class _ConnectorFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, perception, N, *params):
+        enc, con = perception._packs()
+        ws = perception._workspace(N)
+        st = perception._train_state(N)
+        out = torch.empty(N * perception.dims.prompt_size, perception.dims.d_llm, dtype=torch.float32, device=ws.h.device)
+        connector_forward_train(con, perception.dims, ws, st, out)
+        ctx.perception, ctx.N = perception, N
+        return out.view(N, perception.dims.prompt_size, perception.dims.d_llm)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        p, N = ctx.perception, ctx.N
+        _, con = p._packs()
+        conT = p._t_pack()
+        ws, st = p._workspace(N), p._train_state(N)
+        st.zero_grads()
+        g = grad_out.to(torch.float32).contiguous().view(N * p.dims.prompt_size, p.dims.d_llm)
+        connector_backward(con, conT, p.dims, ws, st, g)
+        by_name = grads_by_name(st, p.dims)
+        grads = []
+        for name, prm in p.connector.named_parameters():
+            grads.append(by_name[name].to(prm.dtype).reshape(prm.shape).clone() if prm.requires_grad else None)
+        return (None, None, *grads)
+
+
+def connector_training_forward(perception, input_features):
+    """Frozen encoder forward (no graph) + differentiable connector."""
+    N = input_features.size(0)
+    with torch.no_grad():
+        enc, _ = perception._packs()
+        ws = perception._workspace(N)
+        engine.encoder_forward(enc, perception.dims, ws, perception.mel_time_major(input_features))
+    params = [prm for _, prm in perception.connector.named_parameters()]
+    return _ConnectorFn.apply(perception, N, *params)

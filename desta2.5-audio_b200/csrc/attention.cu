@@ -29,6 +29,7 @@ struct AttnArgs {
   int Tq, Tk;
   float scale_log2;    // scale * log2(e)
   int q_rows, kv_rows; // TMA box rows actually loaded (min(128, T))
+  float* lse;          // optional [batch, heads, Tq]: log2-domain log-sum-exp of the scaled scores (for the backward)
 };
 
 __global__ void __launch_bounds__(AT_THREADS, 2)
@@ -206,6 +207,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tcgen05_fence_after();
     const float inv = 1.0f / l_run;
     const int row = q0 + r;
+    if (a.lse && row < a.Tq) a.lse[((size_t)batch * gridDim.y + head) * a.Tq + row] = m_run * c + log2f(l_run);
     __nv_bfloat16* orow = a.out + ((size_t)batch * a.Tq + row) * a.ldo + head * AT_HD;
 #pragma unroll 1
     for (int ch = 0; ch < 2; ++ch) {
@@ -245,7 +247,7 @@ static int make_qkv_tmap(CUtensorMap* m, const void* base, int heads, int T, int
 using namespace desta;
 
 extern "C" int desta_attention(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo,
-                               int batch, int heads, int Tq, int Tk, float scale, void* stream) {
+                               int batch, int heads, int Tq, int Tk, float scale, float* lse, void* stream) {
   if (!q || !k || !v || !out) { set_error("desta_attention: null pointer"); return DESTA_ERR_ARG; }
   if (batch <= 0 || heads <= 0 || Tq <= 0 || Tk <= 0) { set_error("desta_attention: bad shape"); return DESTA_ERR_ARG; }
   if ((ldq % 8) || (ldk % 8) || (ldv % 8) || (ldo % 8) || ldq < heads * 64 || ldk < heads * 64 || ldv < heads * 64 || ldo < heads * 64) {
@@ -257,6 +259,7 @@ extern "C" int desta_attention(const void* q, int ldq, const void* k, int ldk, c
   AttnArgs a;
   a.out = (__nv_bfloat16*)out; a.ldo = ldo; a.Tq = Tq; a.Tk = Tk;
   a.scale_log2 = scale * 1.4426950408889634f;
+  a.lse = lse;
   a.q_rows = Tq < AT_BQ ? Tq : AT_BQ;
   a.kv_rows = Tk < AT_BKV ? Tk : AT_BKV;
   CUtensorMap tmQ, tmK, tmV;

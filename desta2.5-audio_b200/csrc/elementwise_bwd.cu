@@ -1,0 +1,290 @@
+// Memory-bound pieces of the connector backward (autograd of LayerNorm / GELU / bias / layer mix in
+// $TF/models/bert/modeling_bert.py:294-298, 339-356 and desta/models/modeling_desta25.py:600-606).
+#include "common.cuh"
+#include "desta_b200.h"
+
+namespace desta {
+
+int num_sms();
+
+// ---- LayerNorm backward.  One warp per row (row kept in registers), statistics recomputed from the saved input.
+//      dx = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat));  dgamma += sum_rows dy*xhat;  dbeta += sum_rows dy.
+//      Per-warp partial dgamma/dbeta live in registers across the rows a warp owns, then shared -> global atomics. ----
+template <int MAXV>
+__global__ void __launch_bounds__(256)
+layernorm_bwd_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ x, int ldx,
+                     const float* __restrict__ gamma, float eps, int M, int D, float* __restrict__ dx_f32, int ld_f32,
+                     __nv_bfloat16* __restrict__ dx_bf16, int ld_bf16, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  extern __shared__ float s_red[];   // [2][D]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int nv = D >> 2;
+  for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) s_red[i] = 0.f;
+  __syncthreads();
+  float4 ag[MAXV], ab[MAXV];
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) { ag[i] = make_float4(0, 0, 0, 0); ab[i] = make_float4(0, 0, 0, 0); }
+  for (int row = blockIdx.x * nwarp + warp; row < M; row += gridDim.x * nwarp) {
+    const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * ldx);
+    const float4* dr = reinterpret_cast<const float4*>(dy + (size_t)row * lddy);
+    float4 xv[MAXV], dv[MAXV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int idx = lane + 32 * i;
+      if (idx < nv) { xv[i] = xr[idx]; dv[i] = dr[idx]; s += (xv[i].x + xv[i].y) + (xv[i].z + xv[i].w); }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / (float)D;
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int idx = lane + 32 * i;
+      if (idx < nv) {
+        const float a = xv[i].x - mean, b = xv[i].y - mean, c = xv[i].z - mean, d = xv[i].w - mean;
+        ss += (a * a + b * b) + (c * c + d * d);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float rstd = rsqrtf(ss / (float)D + eps);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int idx = lane + 32 * i;
+      if (idx < nv) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + idx);
+        // xhat into xv, g*dy into a temp; accumulate dgamma / dbeta partials
+        xv[i].x = (xv[i].x - mean) * rstd; xv[i].y = (xv[i].y - mean) * rstd;
+        xv[i].z = (xv[i].z - mean) * rstd; xv[i].w = (xv[i].w - mean) * rstd;
+        ag[i].x += dv[i].x * xv[i].x; ag[i].y += dv[i].y * xv[i].y; ag[i].z += dv[i].z * xv[i].z; ag[i].w += dv[i].w * xv[i].w;
+        ab[i].x += dv[i].x; ab[i].y += dv[i].y; ab[i].z += dv[i].z; ab[i].w += dv[i].w;
+        dv[i].x *= g.x; dv[i].y *= g.y; dv[i].z *= g.z; dv[i].w *= g.w;
+        s1 += (dv[i].x + dv[i].y) + (dv[i].z + dv[i].w);
+        s2 += (dv[i].x * xv[i].x + dv[i].y * xv[i].y) + (dv[i].z * xv[i].z + dv[i].w * xv[i].w);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+    const float m1 = s1 / (float)D, m2 = s2 / (float)D;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int idx = lane + 32 * i;
+      if (idx < nv) {
+        float4 r;
+        r.x = rstd * (dv[i].x - m1 - xv[i].x * m2); r.y = rstd * (dv[i].y - m1 - xv[i].y * m2);
+        r.z = rstd * (dv[i].z - m1 - xv[i].z * m2); r.w = rstd * (dv[i].w - m1 - xv[i].w * m2);
+        if (dx_f32) reinterpret_cast<float4*>(dx_f32 + (size_t)row * ld_f32)[idx] = r;
+        if (dx_bf16) {
+          uint2 u; u.x = pack_bf16(r.x, r.y); u.y = pack_bf16(r.z, r.w);
+          reinterpret_cast<uint2*>(dx_bf16 + (size_t)row * ld_bf16)[idx] = u;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int idx = lane + 32 * i;
+    if (idx < nv) {
+      atomicAdd(&s_red[4 * idx + 0], ag[i].x); atomicAdd(&s_red[4 * idx + 1], ag[i].y);
+      atomicAdd(&s_red[4 * idx + 2], ag[i].z); atomicAdd(&s_red[4 * idx + 3], ag[i].w);
+      atomicAdd(&s_red[D + 4 * idx + 0], ab[i].x); atomicAdd(&s_red[D + 4 * idx + 1], ab[i].y);
+      atomicAdd(&s_red[D + 4 * idx + 2], ab[i].z); atomicAdd(&s_red[D + 4 * idx + 3], ab[i].w);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < D; i += blockDim.x) {
+    atomicAdd(dgamma + i, s_red[i]);
+    atomicAdd(dbeta + i, s_red[D + i]);
+  }
+}
+
+// ---- erf-GELU forward on a saved pre-activation, and its backward:  d/dh [0.5 h (1 + erf(h/sqrt2))] ----
+__global__ void __launch_bounds__(256)
+gelu_fwd_kernel(const uint4* __restrict__ h, uint4* __restrict__ y, size_t n8) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+    uint4 v = h[i];
+    __nv_bfloat162* b = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float2 f = __bfloat1622float2(b[t]);
+      b[t] = __floats2bfloat162_rn(gelu_erf(f.x), gelu_erf(f.y));
+    }
+    y[i] = v;
+  }
+}
+__device__ __forceinline__ float gelu_grad(float h) {
+  const float cdf = 0.5f * (1.0f + erff(h * 0.70710678118654752f));
+  const float pdf = 0.39894228040143268f * __expf(-0.5f * h * h);
+  return cdf + h * pdf;
+}
+__global__ void __launch_bounds__(256)
+gelu_bwd_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ h, uint4* __restrict__ dh, size_t n8) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+    uint4 g = dy[i];
+    const uint4 hv = h[i];
+    __nv_bfloat162* gb = reinterpret_cast<__nv_bfloat162*>(&g);
+    const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&hv);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float2 gf = __bfloat1622float2(gb[t]), hf = __bfloat1622float2(hb[t]);
+      gb[t] = __floats2bfloat162_rn(gf.x * gelu_grad(hf.x), gf.y * gelu_grad(hf.y));
+    }
+    dh[i] = g;
+  }
+}
+
+// ---- column sums (bias gradients): out[j] += sum_m x[m, j].  Block = 32 columns x 8 row-lanes, grid-stride over rows. ----
+template <typename T>
+__global__ void __launch_bounds__(256)
+colsum_kernel(const T* __restrict__ x, int ld, int M, int N, float* __restrict__ out, int rows_per_block) {
+  __shared__ float s[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + tx;
+  const int r0 = blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
+  float acc = 0.f;
+  if (col < N)
+    for (int r = r0 + ty; r < r1; r += 8) acc += (float)x[(size_t)r * ld + col];
+  s[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && col < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += s[i][tx];
+    atomicAdd(out + col, t);
+  }
+}
+
+// ---- layer mix backward: dx[k,r,:] = w[q,k] * dm[r,:];  dlw[q,k] = w[q,k] * (g[q,k] - sum_k' w[q,k'] g[q,k']),
+//      g[q,k] = sum_{n,d} dm[n,q,d] * x[k,n,q,d].  One block per query index q. ----
+__global__ void __launch_bounds__(256)
+layer_mix_bwd_kernel(const float* __restrict__ dm, const float* __restrict__ x, const float* __restrict__ lw, int taps, int N,
+                     int Q, int D, float* __restrict__ dx, float* __restrict__ dlw) {
+  __shared__ float s_w[16], s_g[16][8];
+  const int q = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    float mx = -INFINITY, den = 0.f;
+    for (int k = 0; k < taps; ++k) mx = fmaxf(mx, lw[q * taps + k]);
+    for (int k = 0; k < taps; ++k) den += expf(lw[q * taps + k] - mx);
+    for (int k = 0; k < taps; ++k) s_w[k] = expf(lw[q * taps + k] - mx) / den;
+  }
+  __syncthreads();
+  float g[16];
+  for (int k = 0; k < taps; ++k) g[k] = 0.f;
+  const size_t tap_stride = (size_t)N * Q * D;
+  for (int n = 0; n < N; ++n) {
+    const size_t row = ((size_t)n * Q + q) * D;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+      const float v = dm[row + d];
+      for (int k = 0; k < taps; ++k) {
+        g[k] = fmaf(v, x[k * tap_stride + row + d], g[k]);
+        dx[k * tap_stride + row + d] = s_w[k] * v;
+      }
+    }
+  }
+  for (int k = 0; k < taps; ++k) {
+    float t = g[k];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0) s_g[k][warp] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float gk[16], dot = 0.f;
+    for (int k = 0; k < taps; ++k) {
+      float t = 0.f;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_g[k][w];
+      gk[k] = t;
+      dot += s_w[k] * t;
+    }
+    for (int k = 0; k < taps; ++k) dlw[q * taps + k] += s_w[k] * (gk[k] - dot);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+cast_f32_bf16_kernel(const float4* __restrict__ x, uint2* __restrict__ y, size_t n4) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = x[i];
+    uint2 u; u.x = pack_bf16(v.x, v.y); u.y = pack_bf16(v.z, v.w);
+    y[i] = u;
+  }
+}
+
+static int ew_grid(size_t n) {
+  size_t b = (n + 255) / 256;
+  const size_t cap = (size_t)num_sms() * 16;
+  return (int)(b > cap ? cap : (b ? b : 1));
+}
+
+}  // namespace desta
+
+using namespace desta;
+
+extern "C" int desta_layernorm_bwd(const float* dy, int lddy, const float* x, int ldx, const float* gamma, float eps, int M,
+                                   int D, float* dx_f32, int ld_f32, void* dx_bf16, int ld_bf16, float* dgamma, float* dbeta,
+                                   void* stream) {
+  if (!dy || !x || !gamma || !dgamma || !dbeta || (!dx_f32 && !dx_bf16)) { set_error("desta_layernorm_bwd: null pointer"); return DESTA_ERR_ARG; }
+  if (M <= 0) return DESTA_OK;
+  if (D <= 0 || (D % 4) || D > 2048 || (lddy % 4) || (ldx % 4) || (dx_f32 && (ld_f32 % 4)) || (dx_bf16 && (ld_bf16 % 4))) {
+    set_error("desta_layernorm_bwd: D must be a multiple of 4 and <= 2048 (D=%d)", D);
+    return DESTA_ERR_ARG;
+  }
+  int grid = (M + 7) / 8;
+  const int cap = num_sms() * 4;
+  if (grid > cap) grid = cap;
+  const size_t sm = 2 * (size_t)D * 4;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (D <= 512)
+    layernorm_bwd_kernel<4><<<grid, 256, sm, s>>>(dy, lddy, x, ldx, gamma, eps, M, D, dx_f32, ld_f32, (__nv_bfloat16*)dx_bf16, ld_bf16, dgamma, dbeta);
+  else if (D <= 1280)
+    layernorm_bwd_kernel<10><<<grid, 256, sm, s>>>(dy, lddy, x, ldx, gamma, eps, M, D, dx_f32, ld_f32, (__nv_bfloat16*)dx_bf16, ld_bf16, dgamma, dbeta);
+  else
+    layernorm_bwd_kernel<16><<<grid, 256, sm, s>>>(dy, lddy, x, ldx, gamma, eps, M, D, dx_f32, ld_f32, (__nv_bfloat16*)dx_bf16, ld_bf16, dgamma, dbeta);
+  return check_launch("layernorm_bwd_kernel");
+}
+
+extern "C" int desta_gelu_fwd(const void* h, void* y, size_t n, void* stream) {
+  if (!h || !y || (n % 8)) { set_error("desta_gelu_fwd: null pointer or n %% 8 != 0"); return DESTA_ERR_ARG; }
+  if (!n) return DESTA_OK;
+  gelu_fwd_kernel<<<ew_grid(n / 8), 256, 0, (cudaStream_t)stream>>>((const uint4*)h, (uint4*)y, n / 8);
+  return check_launch("gelu_fwd_kernel");
+}
+
+extern "C" int desta_gelu_bwd(const void* dy, const void* h, void* dh, size_t n, void* stream) {
+  if (!dy || !h || !dh || (n % 8)) { set_error("desta_gelu_bwd: null pointer or n %% 8 != 0"); return DESTA_ERR_ARG; }
+  if (!n) return DESTA_OK;
+  gelu_bwd_kernel<<<ew_grid(n / 8), 256, 0, (cudaStream_t)stream>>>((const uint4*)dy, (const uint4*)h, (uint4*)dh, n / 8);
+  return check_launch("gelu_bwd_kernel");
+}
+
+extern "C" int desta_colsum(const void* x, int dtype, int ld, int M, int N, float* out, void* stream) {
+  if (!x || !out) { set_error("desta_colsum: null pointer"); return DESTA_ERR_ARG; }
+  if (M <= 0 || N <= 0) return DESTA_OK;
+  int row_blocks = (num_sms() * 8) / ((N + 31) / 32);
+  if (row_blocks < 1) row_blocks = 1;
+  int rows_per_block = (M + row_blocks - 1) / row_blocks;
+  if (rows_per_block < 64) rows_per_block = 64;
+  row_blocks = (M + rows_per_block - 1) / rows_per_block;
+  if (row_blocks > 65535) { rows_per_block = (M + 65534) / 65535; row_blocks = (M + rows_per_block - 1) / rows_per_block; }
+  const dim3 grid((N + 31) / 32, row_blocks);
+  if (dtype == 0) colsum_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x, ld, M, N, out, rows_per_block);
+  else colsum_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, ld, M, N, out, rows_per_block);
+  return check_launch("colsum_kernel");
+}
+
+extern "C" int desta_layer_mix_bwd(const float* dm, const float* x, const float* layer_weights, int taps, int N, int Q, int D,
+                                   float* dx, float* dlw, void* stream) {
+  if (!dm || !x || !layer_weights || !dx || !dlw) { set_error("desta_layer_mix_bwd: null pointer"); return DESTA_ERR_ARG; }
+  if (taps > 16) { set_error("desta_layer_mix_bwd: at most 16 taps"); return DESTA_ERR_ARG; }
+  if (N <= 0) return DESTA_OK;
+  layer_mix_bwd_kernel<<<Q, 256, 0, (cudaStream_t)stream>>>(dm, x, layer_weights, taps, N, Q, D, dx, dlw);
+  return check_launch("layer_mix_bwd_kernel");
+}
+
+extern "C" int desta_cast_f32_bf16(const float* x, void* y, size_t n, void* stream) {
+  if (!x || !y || (n % 4)) { set_error("desta_cast_f32_bf16: null pointer or n %% 4 != 0"); return DESTA_ERR_ARG; }
+  if (!n) return DESTA_OK;
+  cast_f32_bf16_kernel<<<ew_grid(n / 4), 256, 0, (cudaStream_t)stream>>>((const float4*)x, (uint2*)y, n / 4);
+  return check_launch("cast_f32_bf16_kernel");
+}

@@ -8,6 +8,13 @@
 //   (modeling_whisper.py:404-406, modeling_bert.py:339-342, modeling_desta25.py:563-564), + row-periodic fp32 table
 //   (embed_positions add, modeling_desta25.py:566-570), + fp32 residual (modeling_whisper.py:400,408),
 //   fp32 and/or bf16 stores (bf16 copy = the tap hand-off, modeling_desta25.py:585-595).
+//
+// MODE_WGRAD (connector backward, autograd of $TF/models/bert/modeling_bert.py Linear layers):
+//   C[Nout,Kin] += dY[Mred,Nout]^T · X[Mred,Kin] — both operands are read as they lie in memory (reduction dim = rows),
+//   i.e. MN-major UMMA operands: TMA boxes of 64 rows x 64 columns land as 128-byte-swizzled atoms, LBO = 8 KB between
+//   the 64-column atoms, SBO = 1 KB between 8-row groups.  Optional split-K over the reduction with fp32 atomics.
+#include <string.h>
+
 #include "common.cuh"
 #include "desta_b200.h"
 
@@ -30,10 +37,16 @@ struct GemmArgs {
   const float* pos; int pos_rows;
   float scale; int scale_cols;
   int gelu;
+  int splits;      // split-K factor (MODE_WGRAD); > 1 => fp32 atomic accumulation into out_f32
+  int atomic;
 };
 
+constexpr int MODE_TN = 0, MODE_WGRAD = 1;
+constexpr int ATOM_BYTES = 64 * 128;   // one 64-row x 64-column bf16 box
+
+template <int MODE>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -45,8 +58,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = (g.M + BM - 1) / BM, n_tiles = (g.N + BN - 1) / BN;
-  const int num_tiles = m_tiles * n_tiles;
-  const int k_blocks = (g.K + BK - 1) / BK;
+  const int num_tiles = m_tiles * n_tiles * g.splits;          // work items = (tile, k-split)
+  const int k_blocks_total = (g.K + BK - 1) / BK;
+  const int kb_per = (k_blocks_total + g.splits - 1) / g.splits;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -66,39 +80,61 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int item = blockIdx.x; item < num_tiles; item += gridDim.x) {
+        const int tile = item / g.splits, split = item - tile * g.splits;
         const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
-        for (int kb = 0; kb < k_blocks; ++kb) {
+        const int kb0 = split * kb_per, kb1 = min(k_blocks_total, kb0 + kb_per);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
           uint8_t* sa = smem + stage * STAGE_BYTES;
-          tma_load_2d(sa, &tmA, &full[stage], kb * BK, m_blk * BM);
-          tma_load_2d(sa + A_STAGE_BYTES, &tmB, &full[stage], kb * BK, n_blk * BN);
+          if (MODE == MODE_TN) {
+            tma_load_2d(sa, &tmA, &full[stage], kb * BK, m_blk * BM);
+            tma_load_2d(sa + A_STAGE_BYTES, &tmB, &full[stage], kb * BK, n_blk * BN);
+          } else {
+#pragma unroll
+            for (int a = 0; a < BM / 64; ++a) tma_load_2d(sa + a * ATOM_BYTES, &tmA, &full[stage], m_blk * BM + a * 64, kb * BK);
+#pragma unroll
+            for (int a = 0; a < BN / 64; ++a)
+              tma_load_2d(sa + A_STAGE_BYTES + a * ATOM_BYTES, &tmB, &full[stage], n_blk * BN + a * 64, kb * BK);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, MODE == MODE_WGRAD, MODE == MODE_WGRAD);
       int stage = 0; uint32_t phase = 0;
       int local = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+      for (int item = blockIdx.x; item < num_tiles; item += gridDim.x, ++local) {
+        const int split = item % g.splits;
+        const int kb0 = split * kb_per, kb1 = min(k_blocks_total, kb0 + kb_per);
         const int as = local & 1;
         const uint32_t acc_phase = (local >> 1) & 1;
         mbar_wait(&acc_empty[as], acc_phase ^ 1);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
-        for (int kb = 0; kb < k_blocks; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full[stage], phase);
           tcgen05_fence_after();
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-          const uint64_t adesc = umma_desc_sw128(sa, 16, 1024);
-          const uint64_t bdesc = umma_desc_sw128(sa + A_STAGE_BYTES, 16, 1024);
+          if (MODE == MODE_TN) {
+            const uint64_t adesc = umma_desc_sw128(sa, 16, 1024);
+            const uint64_t bdesc = umma_desc_sw128(sa + A_STAGE_BYTES, 16, 1024);
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            // advance 16 bf16 = 32 B along K inside the 128-byte swizzle atom: +2 in the (addr>>4) field
-            umma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              // advance 16 bf16 = 32 B along K inside the 128-byte swizzle atom: +2 in the (addr>>4) field
+              umma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb0 || k) ? 1u : 0u);
+            }
+          } else {
+            const uint64_t adesc = umma_desc_sw128(sa, ATOM_BYTES, 1024);
+            const uint64_t bdesc = umma_desc_sw128(sa + A_STAGE_BYTES, ATOM_BYTES, 1024);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              // 16 reduction rows = two 8-row groups = 2048 B
+              umma_bf16_ss(d_tmem, adesc + 128 * k, bdesc + 128 * k, idesc, (kb > kb0 || k) ? 1u : 0u);
+            }
           }
           umma_commit(&empty[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -110,7 +146,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int half = (warp - EPI_WARP0) >> 2;  // column half handled by this warp
     int local = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+    for (int item = blockIdx.x; item < num_tiles; item += gridDim.x, ++local) {
+      const int tile = item / g.splits;
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
       const int as = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
@@ -183,7 +220,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int j = 0; j < 32; ++j) if (col0 + j < g.N) f[j] += r[j];
           }
         }
-        if (g.out_f32) {
+        if (g.out_f32 && g.atomic) {
+          float* o = g.out_f32 + (size_t)row * g.ld_f32 + col0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) if (col0 + j < g.N) atomicAdd(o + j, f[j]);
+        } else if (g.out_f32) {
           float* o = g.out_f32 + (size_t)row * g.ld_f32 + col0;
           if (full_cols) {
 #pragma unroll
@@ -235,6 +276,22 @@ int num_sms() {
 
 using namespace desta;
 
+static int launch_gemm(int mode, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<MODE_TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_bf16_kernel<MODE_WGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
+    if (e != cudaSuccess) { set_error("gemm smem attribute: %s", cudaGetErrorString(e)); return DESTA_ERR_CUDA; }
+    attr_set = true;
+  }
+  const int m_tiles = (g.M + BM - 1) / BM, n_tiles = (g.N + BN - 1) / BN;
+  const int items = m_tiles * n_tiles * g.splits;
+  const int grid = items < num_sms() ? items : num_sms();
+  if (mode == MODE_TN) gemm_bf16_kernel<MODE_TN><<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(tmA, tmB, g);
+  else gemm_bf16_kernel<MODE_WGRAD><<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(tmA, tmB, g);
+  return check_launch("gemm_bf16_kernel");
+}
+
 extern "C" int desta_gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int K,
                                const desta_gemm_epilogue* ep, void* stream) {
   if (!A || !W || !ep) { set_error("desta_gemm_bf16: null pointer"); return DESTA_ERR_ARG; }
@@ -258,15 +315,40 @@ extern "C" int desta_gemm_bf16(const void* A, int lda, const void* W, int ldw, i
   g.bias = ep->bias; g.resid = ep->resid; g.ld_resid = ep->ld_resid;
   g.pos = ep->pos; g.pos_rows = ep->pos_rows > 0 ? ep->pos_rows : 1;
   g.scale = ep->scale; g.scale_cols = ep->scale_cols; g.gelu = ep->gelu;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
-    if (e != cudaSuccess) { set_error("gemm smem attribute: %s", cudaGetErrorString(e)); return DESTA_ERR_CUDA; }
-    attr_set = true;
+  g.splits = 1; g.atomic = 0;
+  return launch_gemm(MODE_TN, tmA, tmB, g, (cudaStream_t)stream);
+}
+
+extern "C" int desta_gemm_bf16_wgrad(const void* dY, int ldy, const void* X, int ldx, int Mred, int Nout, int Kin,
+                                     float* dW, int ldw, void* stream) {
+  if (!dY || !X || !dW) { set_error("desta_gemm_bf16_wgrad: null pointer"); return DESTA_ERR_ARG; }
+  if (Mred <= 0 || Nout <= 0 || Kin <= 0) { set_error("desta_gemm_bf16_wgrad: bad shape"); return DESTA_ERR_ARG; }
+  if ((ldy % 8) || (ldx % 8) || ldy < Nout || ldx < Kin || (ldw % 4)) {
+    set_error("desta_gemm_bf16_wgrad: leading dims must cover the row and keep 16-byte alignment");
+    return DESTA_ERR_ARG;
   }
-  const int m_tiles = (M + BM - 1) / BM, n_tiles = (N + BN - 1) / BN;
-  const int tiles = m_tiles * n_tiles;
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_bf16_tn_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, (cudaStream_t)stream>>>(tmA, tmB, g);
-  return check_launch("gemm_bf16_tn_kernel");
+  CUtensorMap tmA, tmB;
+  // operands are loaded as 64-row x 64-column boxes, exactly as they lie in memory (reduction dim = rows)
+  if (make_tmap_2d_bf16(&tmA, dY, (uint64_t)Mred, (uint64_t)Nout, (uint64_t)ldy, 64, 64)) return DESTA_ERR_CUDA;
+  if (make_tmap_2d_bf16(&tmB, X, (uint64_t)Mred, (uint64_t)Kin, (uint64_t)ldx, 64, 64)) return DESTA_ERR_CUDA;
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.M = Nout; g.N = Kin; g.K = Mred;
+  g.out_f32 = dW; g.ld_f32 = ldw;
+  g.pos_rows = 1; g.scale = 1.f;
+  const int tiles = ((Nout + BM - 1) / BM) * ((Kin + BN - 1) / BN);
+  const int kblocks = (Mred + BK - 1) / BK;
+  int splits = 1;
+  if (tiles < num_sms()) {                       // small outputs: spread the long reduction over the idle SMs
+    splits = num_sms() / tiles;
+    const int max_splits = kblocks / 8 > 0 ? kblocks / 8 : 1;    // keep >= 8 k-blocks per split
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+  }
+  const int kb_per = (kblocks + splits - 1) / splits;
+  splits = (kblocks + kb_per - 1) / kb_per;      // no empty split
+  g.splits = splits;
+  if (splits > 1) g.atomic = 1;                  // dW += partial (fp32 atomics)
+  else { g.resid = dW; g.ld_resid = ldw; }       // dW += acc (plain read-modify-write, one writer per element)
+  return launch_gemm(MODE_WGRAD, tmA, tmB, g, (cudaStream_t)stream);
 }

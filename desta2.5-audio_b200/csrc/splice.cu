@@ -66,6 +66,24 @@ splice_rows_kernel(const int64_t* __restrict__ input_ids, const uint4* __restric
   }
 }
 
+__global__ void __launch_bounds__(256)
+splice_bwd_kernel(const uint4* __restrict__ grad_out, const desta_splice_desc* __restrict__ descs, int Q, int S, int d8,
+                  float4* __restrict__ dfeats) {
+  const int c = blockIdx.y;
+  const desta_splice_desc dd = descs[c];
+  for (int j = blockIdx.x; j < Q; j += gridDim.x) {
+    const uint4* src = grad_out + ((size_t)dd.prompt * S + dd.start + j) * d8;
+    float4* dst = dfeats + ((size_t)c * Q + j) * d8 * 2;
+    for (int i = threadIdx.x; i < d8; i += blockDim.x) {
+      const uint4 u = __ldg(src + i);
+      const __nv_bfloat162* b = reinterpret_cast<const __nv_bfloat162*>(&u);
+      const float2 f0 = __bfloat1622float2(b[0]), f1 = __bfloat1622float2(b[1]), f2 = __bfloat1622float2(b[2]), f3 = __bfloat1622float2(b[3]);
+      dst[2 * i] = make_float4(f0.x, f0.y, f1.x, f1.y);
+      dst[2 * i + 1] = make_float4(f2.x, f2.y, f3.x, f3.y);
+    }
+  }
+}
+
 int num_sms();
 
 }  // namespace desta
@@ -104,4 +122,14 @@ extern "C" int desta_splice(const int64_t* input_ids, const void* table, int64_t
     splice_rows_kernel<false><<<grid, 256, 0, s>>>(input_ids, (const uint4*)table, vocab, descs_dev, trans_ids, audio_feats, Q,
                                                    d / 8, row_map, rows, (uint4*)out);
   return check_launch("splice kernels");
+}
+
+extern "C" int desta_splice_bwd(const void* grad_out, const desta_splice_desc* descs_dev, int n_desc, int Q, int S, int d,
+                                float* dfeats, void* stream) {
+  if (!grad_out || !descs_dev || !dfeats) { set_error("desta_splice_bwd: null pointer"); return DESTA_ERR_ARG; }
+  if (n_desc <= 0) return DESTA_OK;
+  if (d % 8) { set_error("desta_splice_bwd: hidden size must be a multiple of 8"); return DESTA_ERR_ARG; }
+  splice_bwd_kernel<<<dim3(Q < 64 ? Q : 64, n_desc), 256, 0, (cudaStream_t)stream>>>((const uint4*)grad_out, descs_dev, Q, S, d / 8,
+                                                                                   (float4*)dfeats);
+  return check_launch("splice_bwd_kernel");
 }

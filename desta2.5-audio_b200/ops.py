@@ -110,7 +110,7 @@ def layernorm(x, gamma, beta, eps, *, out_bf16=None, out_f32=None):
                                     _p(out_f32), out_f32.stride(0) if out_f32 is not None else 0, _stream()), "desta_layernorm")
 
 
-def attention(q, k, v, out, batch, heads, Tq, Tk, scale):
+def attention(q, k, v, out, batch, heads, Tq, Tk, scale, lse=None):
     """q/k/v/out: 2-D bf16 views [batch*T, >= heads*64] (row stride = leading dim; may be slices of a fused buffer)."""
     for t in (q, k, v, out):
         _cuda(t, torch.bfloat16)
@@ -118,7 +118,97 @@ def attention(q, k, v, out, batch, heads, Tq, Tk, scale):
     assert q.shape[0] == batch * Tq and k.shape[0] == batch * Tk and v.shape[0] == batch * Tk and out.shape[0] == batch * Tq
     with _op("attention", 1, 4.0 * batch * heads * Tq * Tk * 64):
         check(lib().desta_attention(_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(out), out.stride(0),
-                                    batch, heads, Tq, Tk, float(scale), _stream()), "desta_attention")
+                                    batch, heads, Tq, Tk, float(scale), _p(lse), _stream()), "desta_attention")
+
+
+def attention_bwd(q, k, v, o, dout, lse, dq, dk, dv, batch, heads, Tq, Tk, scale):
+    for t in (q, k, v, o, dout, dq, dk, dv):
+        _cuda(t, torch.bfloat16)
+        assert t.stride(1) == 1
+    _cuda(lse, torch.float32)
+    with _op("attention_bwd", 1, 10.0 * batch * heads * Tq * Tk * 64):
+        check(lib().desta_attention_bwd(_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(o), o.stride(0),
+                                        _p(dout), dout.stride(0), _p(lse), _p(dq), dq.stride(0), _p(dk), dk.stride(0),
+                                        _p(dv), dv.stride(0), batch, heads, Tq, Tk, float(scale), _stream()), "desta_attention_bwd")
+
+
+def gemm_wgrad(dy, x, dw):
+    """dw[Nout,Kin] (fp32, +=) from dy[M,Nout], x[M,Kin] (bf16, rows = reduction dim)."""
+    _cuda(dy, torch.bfloat16), _cuda(x, torch.bfloat16), _cuda(dw, torch.float32)
+    M, Nout = dy.shape
+    M2, Kin = x.shape
+    assert M == M2 and dw.shape == (Nout, Kin) and dy.stride(1) == 1 and x.stride(1) == 1 and dw.stride(1) == 1
+    with _op("gemm_wgrad", 1, 2.0 * M * Nout * Kin):
+        check(lib().desta_gemm_bf16_wgrad(_p(dy), dy.stride(0), _p(x), x.stride(0), M, Nout, Kin, _p(dw), dw.stride(0), _stream()),
+              "desta_gemm_bf16_wgrad")
+
+
+def layernorm_bwd(dy, x, gamma, eps, dgamma, dbeta, *, dx_f32=None, dx_bf16=None):
+    _cuda(dy, torch.float32), _cuda(x, torch.float32)
+    M, D = x.shape
+    with _op("layernorm_bwd", 1, M * D * 12, "byte"):
+        check(lib().desta_layernorm_bwd(_p(dy), dy.stride(0), _p(x), x.stride(0), _p(gamma), float(eps), M, D,
+                                        _p(dx_f32), dx_f32.stride(0) if dx_f32 is not None else 0,
+                                        _p(dx_bf16), dx_bf16.stride(0) if dx_bf16 is not None else 0,
+                                        _p(dgamma), _p(dbeta), _stream()), "desta_layernorm_bwd")
+
+
+def gelu_fwd(h, y):
+    _cuda(h, torch.bfloat16), _cuda(y, torch.bfloat16)
+    assert h.is_contiguous() and y.is_contiguous()
+    with _op("gelu", 1, h.numel() * 4, "byte"):
+        check(lib().desta_gelu_fwd(_p(h), _p(y), h.numel(), _stream()), "desta_gelu_fwd")
+
+
+def gelu_bwd(dy, h, dh):
+    for t in (dy, h, dh):
+        _cuda(t, torch.bfloat16)
+        assert t.is_contiguous()
+    with _op("gelu", 1, h.numel() * 6, "byte"):
+        check(lib().desta_gelu_bwd(_p(dy), _p(h), _p(dh), h.numel(), _stream()), "desta_gelu_bwd")
+
+
+def colsum(x, out):
+    """out[j] += sum_m x[m, j]; x fp32 or bf16 2-D (row stride = leading dim)."""
+    assert x.is_cuda and x.stride(1) == 1 and x.dtype in (torch.float32, torch.bfloat16)
+    _cuda(out, torch.float32)
+    M, N = x.shape
+    assert out.numel() == N
+    with _op("colsum", 1, x.numel() * x.element_size(), "byte"):
+        check(lib().desta_colsum(_p(x), 0 if x.dtype == torch.float32 else 1, x.stride(0), M, N, _p(out), _stream()), "desta_colsum")
+
+
+def layer_mix_bwd(dm, x, layer_weights, N, Q, dx, dlw):
+    taps, rows, D = x.shape
+    for t in (dm, x, layer_weights, dx, dlw):
+        _cuda(t, torch.float32)
+        assert t.is_contiguous()
+    with _op("layer_mix", 1, (2 * x.numel() + dm.numel()) * 4, "byte"):
+        check(lib().desta_layer_mix_bwd(_p(dm), _p(x), _p(layer_weights), taps, N, Q, D, _p(dx), _p(dlw), _stream()), "desta_layer_mix_bwd")
+
+
+def cast_bf16(x, y):
+    _cuda(x, torch.float32), _cuda(y, torch.bfloat16)
+    assert x.is_contiguous() and y.is_contiguous() and x.numel() == y.numel()
+    with _op("cast", 1, x.numel() * 6, "byte"):
+        check(lib().desta_cast_f32_bf16(_p(x), _p(y), x.numel(), _stream()), "desta_cast_f32_bf16")
+
+
+def splice_descs_device(descs, device):
+    n = len(descs)
+    host = (SpliceDesc * max(n, 1))()
+    for i, (p_, s_, t_, o_) in enumerate(descs):
+        host[i] = SpliceDesc(int(p_), int(s_), int(t_), int(o_))
+    return host, torch.frombuffer(bytearray(bytes(host)), dtype=torch.int32).to(device)
+
+
+def splice_bwd(grad_out, descs, Q, dfeats):
+    """dfeats [n,Q,d] fp32 <- rows of grad_out [B,S,d] bf16 under each clip's audio span."""
+    _cuda(grad_out, torch.bfloat16), _cuda(dfeats, torch.float32)
+    B, S, d = grad_out.shape
+    _, dev = splice_descs_device(descs, grad_out.device)
+    with _op("splice", 1, dfeats.numel() * 6, "byte"):
+        check(lib().desta_splice_bwd(_p(grad_out.contiguous()), _p(dev), len(descs), Q, S, d, _p(dfeats), _stream()), "desta_splice_bwd")
 
 
 def im2col_k3(x, N, T_in, C, stride, cols):

@@ -33,7 +33,10 @@ class WhisperPerceptionB200(nn.Module):
         self._enc_pack = None
         self._con_pack = None
         self._con_versions = None
+        self._t_pack_obj = None
+        self._t_versions = None
         self._ws = {}
+        self._train = {}
 
     # ---- reference-compatible constructor: wrap an existing reference WhisperPerception ----
     @classmethod
@@ -62,6 +65,23 @@ class WhisperPerceptionB200(nn.Module):
         if key not in self._ws:
             self._ws = {key: Workspace(self.dims, N, dev)}        # keep one batch size resident
         return self._ws[key]
+
+    def _train_state(self, N):
+        from .autograd import TrainState
+        dev = self._device()
+        key = (N, str(dev))
+        if key not in self._train:
+            self._train = {key: TrainState(self.dims, N, dev)}
+        return self._train[key]
+
+    def _t_pack(self):
+        from .autograd import ConnectorTPack
+        versions = tuple(p._version for p in self.connector.parameters())
+        if self._t_pack_obj is None or versions != self._t_versions:
+            sd = {"connector." + k: v for k, v in self.connector.state_dict().items()}
+            self._t_pack_obj = ConnectorTPack(sd, self.dims, self._device())
+            self._t_versions = versions
+        return self._t_pack_obj
 
     def mel_time_major(self, input_features: torch.Tensor) -> torch.Tensor:
         dev = self._device()

@@ -44,12 +44,14 @@ class _SpliceFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_out):
-        g = torch.zeros(ctx.shape, dtype=ctx.dtype, device=grad_out.device)
+        g = torch.empty(ctx.shape, dtype=torch.float32, device=grad_out.device)
+        ops.splice_bwd(grad_out.to(torch.bfloat16), list(ctx.descs), ctx.Q, g)
         live = _last_writer(ctx.descs, ctx.Q)
-        for i, (b, s, _t, _o) in enumerate(ctx.descs):
-            if live[i]:
-                g[i] = grad_out[b, s:s + ctx.Q].to(ctx.dtype)
-        return g, None, None, None, None, None
+        if not all(live):
+            for i, ok in enumerate(live):
+                if not ok:
+                    g[i].zero_()
+        return g.to(ctx.dtype), None, None, None, None, None
 
 
 def _last_writer(descs, Q):

@@ -65,7 +65,7 @@ int desta_layernorm(const float* x, int ldx, const float* gamma, const float* be
  * Replaces WhisperAttention (modeling_whisper.py:284-358, scale 1 because q is pre-scaled) and the eager
  * Bert self/cross attention (modeling_bert.py:168-207, 234-284, scale head_dim^-1/2). */
 int desta_attention(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo,
-                    int batch, int heads, int Tq, int Tk, float scale, void* stream);
+                    int batch, int heads, int Tq, int Tk, float scale, float* lse /* optional [batch,heads,Tq] */, void* stream);
 
 /* im2col for the conv stem (modeling_desta25.py:563-564): Conv1d(k=3,pad=1,stride s) as GEMM rows.
  * x time-major bf16 [N, T_in, C] -> cols bf16 [N*T_out, 3*C] with column index = tap*C + c  (T_out = T_in/stride). */
@@ -75,6 +75,27 @@ int desta_im2col_k3(const void* x, int N, int T_in, int C, int stride, void* col
  * x fp32 [taps, N*Q, D] -> out fp32 [N*Q, D]. */
 int desta_layer_mix(const float* x, const float* layer_weights, int taps, int N, int Q, int D, float* out, void* stream);
 
+/* ---- (3b) connector backward (row a6: the autograd graph of modeling_desta25.py:587-606 over
+ *      $TF/models/bert/modeling_bert.py:168-207,234-298,330-356; taps need no gradient, encoder frozen :1451-1453). ---- */
+/* dW[Nout,Kin] += dY[Mred,Nout]^T X[Mred,Kin]  (bf16 operands read in place, fp32 accumulate; split-K with atomics). */
+int desta_gemm_bf16_wgrad(const void* dY, int ldy, const void* X, int ldx, int Mred, int Nout, int Kin, float* dW, int ldw,
+                          void* stream);
+/* Attention backward (Tq <= 128): dq/dk/dv bf16 with the same row layout as q/k/v; lse from desta_attention. */
+int desta_attention_bwd(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, const void* o, int ldo,
+                        const void* dout, int lddo, const float* lse, void* dq, int lddq, void* dk, int lddk, void* dv,
+                        int lddv, int batch, int heads, int Tq, int Tk, float scale, void* stream);
+/* LayerNorm backward from the saved fp32 input; dgamma/dbeta are accumulated (+=). */
+int desta_layernorm_bwd(const float* dy, int lddy, const float* x, int ldx, const float* gamma, float eps, int M, int D,
+                        float* dx_f32, int ld_f32, void* dx_bf16, int ld_bf16, float* dgamma, float* dbeta, void* stream);
+/* erf-GELU on a saved bf16 pre-activation, and its backward dh = dy * gelu'(h) (all bf16, n elements). */
+int desta_gelu_fwd(const void* h, void* y, size_t n, void* stream);
+int desta_gelu_bwd(const void* dy, const void* h, void* dh, size_t n, void* stream);
+/* out[j] += sum_m x[m,j]  (bias gradients; dtype 0 = fp32, 1 = bf16). */
+int desta_colsum(const void* x, int dtype, int ld, int M, int N, float* out, void* stream);
+/* Backward of desta_layer_mix: dx [taps,N*Q,D] (written), dlw [Q,taps] (+=). */
+int desta_layer_mix_bwd(const float* dm, const float* x, const float* layer_weights, int taps, int N, int Q, int D, float* dx,
+                        float* dlw, void* stream);
+int desta_cast_f32_bf16(const float* x, void* y, size_t n, void* stream);
 /* ---- (4) splice: replaces the gathers + per-audio scatter loop of
  *      DeSTA25AudioModel._prepare_inputs_for_llm (modeling_desta25.py:940-1050; gathers :975-982,1009; loop :1014-1045).
  *      out[b,s,:] = table[input_ids[b,s]] for text rows; rows [start, start+Q) of prompt b <- bf16_rne(audio_feats[i]);
@@ -90,6 +111,9 @@ typedef struct desta_splice_desc {
 int desta_splice(const int64_t* input_ids, const void* table, int64_t vocab, const desta_splice_desc* descs_dev,
                  const desta_splice_desc* descs_host, int n_desc, const int64_t* trans_ids, const void* audio_feats,
                  int feat_dtype, int Q, void* out, int B, int S, int d, int32_t* row_map, void* stream);
+/* Gradient of the splice w.r.t. the audio features: dfeats[i] = grad_out[prompt_i, start_i : start_i + Q] (bf16 -> fp32). */
+int desta_splice_bwd(const void* grad_out, const desta_splice_desc* descs_dev, int n_desc, int Q, int S, int d, float* dfeats,
+                     void* stream);
 
 #ifdef __cplusplus
 }

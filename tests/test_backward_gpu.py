@@ -1,0 +1,174 @@
+"""Connector backward (scope row a6): kernel-level parity vs torch autograd (fp32) and whole-connector gradients vs the
+oracle's autograd + the reference-generated golden gradients.  Gradient tolerance (written here, bf16 operands with
+fp32 accumulation): max|delta|/max|ref| <= 5e-2 and cosine >= 0.995 per tensor."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from desta_b200 import ops
+
+from test_path_gpu import KINDS, _cos, _rel, build_perception  # noqa: E402
+
+
+@pytest.mark.parametrize("M,Nout,Kin", [(64, 128, 256), (512, 128, 256), (4096, 1280, 1280), (16384, 384, 3072),
+                                        (6000, 512, 128), (1000, 200, 72)])
+def test_gemm_wgrad(M, Nout, Kin):
+    g = torch.Generator(device="cuda").manual_seed(M + Nout)
+    dy = torch.randn(M, Nout, device="cuda", generator=g).to(torch.bfloat16)
+    x = torch.randn(M, Kin, device="cuda", generator=g).to(torch.bfloat16)
+    dw = torch.randn(Nout, Kin, device="cuda", generator=g)
+    ref = dw + dy.float().t() @ x.float()
+    ops.gemm_wgrad(dy, x, dw)
+    assert _rel(dw, ref) < 1e-4
+
+
+def test_gemm_wgrad_strided_operands():
+    M, d = 3000, 256
+    buf = torch.randn(M, 4 * d, device="cuda").to(torch.bfloat16)
+    x = torch.randn(M, 128, device="cuda").to(torch.bfloat16)
+    dw = torch.zeros(d, 128, device="cuda")
+    ops.gemm_wgrad(buf[:, d:2 * d], x, dw)
+    assert _rel(dw, buf[:, d:2 * d].float().t() @ x.float()) < 1e-4
+
+
+@pytest.mark.parametrize("B,H,Tq,Tk,scale", [(2, 2, 64, 64, 0.125), (3, 2, 64, 1500, 0.125), (1, 1, 128, 256, 0.2),
+                                             (2, 6, 64, 300, 0.125)])
+def test_attention_bwd(B, H, Tq, Tk, scale):
+    g = torch.Generator(device="cuda").manual_seed(Tk)
+    d = H * 64
+    q = torch.randn(B * Tq, d, device="cuda", generator=g).to(torch.bfloat16)
+    k = torch.randn(B * Tk, d, device="cuda", generator=g).to(torch.bfloat16)
+    v = torch.randn(B * Tk, d, device="cuda", generator=g).to(torch.bfloat16)
+    do = torch.randn(B * Tq, d, device="cuda", generator=g).to(torch.bfloat16)
+    o = torch.empty_like(q)
+    lse = torch.empty(B * H * Tq, device="cuda")
+    ops.attention(q, k, v, o, B, H, Tq, Tk, scale, lse=lse)
+    dq, dk, dv = torch.zeros_like(q), torch.zeros_like(k), torch.zeros_like(v)
+    ops.attention_bwd(q, k, v, o, do, lse, dq, dk, dv, B, H, Tq, Tk, scale)
+    qf, kf, vf = (t.float().requires_grad_(True) for t in (q, k, v))
+    qh = qf.reshape(B, Tq, H, 64).transpose(1, 2)
+    kh = kf.reshape(B, Tk, H, 64).transpose(1, 2)
+    vh = vf.reshape(B, Tk, H, 64).transpose(1, 2)
+    s = qh @ kh.transpose(-1, -2) * scale
+    ref = (torch.softmax(s, -1) @ vh).transpose(1, 2).reshape(B * Tq, d)
+    lse_ref = (torch.logsumexp(s, -1) * 1.4426950408889634).reshape(-1)
+    assert (lse - lse_ref).abs().max().item() < 2e-2
+    ref.backward(do.float())
+    for name, a, b in (("dq", dq, qf.grad), ("dk", dk, kf.grad), ("dv", dv, vf.grad)):
+        assert _rel(a, b) < 3e-2 and _cos(a, b) > 0.999, f"{name}: rel {_rel(a, b)} cos {_cos(a, b)}"
+
+
+@pytest.mark.parametrize("M,D,eps", [(1000, 1280, 1e-12), (333, 128, 1e-5), (64, 384, 1e-12)])
+def test_layernorm_bwd(M, D, eps):
+    x = (torch.randn(M, D, device="cuda") * 2 + 0.5).requires_grad_(True)
+    gamma = torch.randn(D, device="cuda", requires_grad=True)
+    beta = torch.randn(D, device="cuda", requires_grad=True)
+    dy = torch.randn(M, D, device="cuda")
+    torch.nn.functional.layer_norm(x, (D,), gamma, beta, eps).backward(dy)
+    dx = torch.empty(M, D, device="cuda")
+    dxb = torch.empty(M, D, device="cuda", dtype=torch.bfloat16)
+    dg, db = torch.zeros(D, device="cuda"), torch.zeros(D, device="cuda")
+    ops.layernorm_bwd(dy, x.detach(), gamma.detach(), eps, dg, db, dx_f32=dx, dx_bf16=dxb)
+    assert _rel(dx, x.grad) < 1e-4 and _rel(dg, gamma.grad) < 1e-4 and _rel(db, beta.grad) < 1e-4
+    assert torch.equal(dxb, dx.to(torch.bfloat16))
+
+
+def test_gelu_colsum_mix_cast_splice_bwd():
+    h = (torch.randn(512, 3072, device="cuda") * 2).to(torch.bfloat16)
+    y = torch.empty_like(h)
+    ops.gelu_fwd(h, y)
+    assert _rel(y, torch.nn.functional.gelu(h.float())) < 6e-3
+    dy = torch.randn(512, 3072, device="cuda").to(torch.bfloat16)
+    dh = torch.empty_like(h)
+    ops.gelu_bwd(dy, h, dh)
+    hf = h.float().requires_grad_(True)
+    torch.nn.functional.gelu(hf).backward(dy.float())
+    assert _rel(dh, hf.grad) < 6e-3
+    # colsum (+= semantics), fp32 and strided bf16
+    out = torch.ones(3072, device="cuda")
+    ops.colsum(dy, out)
+    assert _rel(out, 1 + dy.float().sum(0)) < 1e-4
+    xf = torch.randn(100000, 96, device="cuda")
+    out = torch.zeros(64, device="cuda")
+    ops.colsum(xf[:, 16:80], out)
+    assert _rel(out, xf[:, 16:80].sum(0)) < 1e-4
+    # layer mix backward
+    taps, N, Q, D = 4, 3, 64, 256
+    x = torch.randn(taps, N * Q, D, device="cuda", requires_grad=True)
+    lw = torch.randn(Q, taps, device="cuda", requires_grad=True)
+    dm = torch.randn(N * Q, D, device="cuda")
+    w = torch.softmax(lw, -1)
+    m = (x.view(taps, N, Q, D).permute(1, 2, 0, 3) * w[None, :, :, None]).sum(2).reshape(N * Q, D)
+    m.backward(dm)
+    dx = torch.empty(taps, N * Q, D, device="cuda")
+    dlw = torch.zeros(Q, taps, device="cuda")
+    ops.layer_mix_bwd(dm, x.detach(), lw.detach(), N, Q, dx, dlw)
+    assert _rel(dx, x.grad) < 1e-5 and _rel(dlw, lw.grad) < 1e-4
+    # cast
+    a = torch.randn(4096, device="cuda")
+    b = torch.empty(4096, device="cuda", dtype=torch.bfloat16)
+    ops.cast_bf16(a, b)
+    assert torch.equal(b, a.to(torch.bfloat16))
+    # splice backward
+    go = torch.randn(2, 200, 128, device="cuda").to(torch.bfloat16)
+    descs = [(0, 5, 0, 0), (1, 100, 3, 0), (0, 90, 0, 3)]
+    df = torch.empty(3, 64, 128, device="cuda")
+    ops.splice_bwd(go, descs, 64, df)
+    for i, (b_, s_, _, _) in enumerate(descs):
+        assert torch.equal(df[i], go[b_, s_:s_ + 64].float())
+
+
+@pytest.mark.parametrize("name,n_clips", [("micro", 3), ("debug", 2)])
+def test_connector_gradients_vs_oracle(name, n_clips, golden_dir):
+    from oracle import encoder as o_enc, logmel as o_mel, qformer as o_qf
+    from oracle.configs import CONFIGS
+    from oracle.synth import synth_waves
+    from oracle.weights import make_weights
+    cfg = CONFIGS[name]
+    W = make_weights(cfg, seed=11, with_table=False)
+    waves = synth_waves(seed=7, kinds=KINDS)[:n_clips]
+    mel = torch.from_numpy(o_mel.logmel(waves, cfg.n_mels))
+    gout = torch.randn(n_clips, cfg.prompt_size, cfg.d_llm, generator=torch.Generator().manual_seed(5))
+    with torch.no_grad():
+        taps = o_enc.encoder_taps(W, cfg, mel)
+    Wg = {k: (v.clone().requires_grad_(True) if k.startswith("perception.connector.") else v) for k, v in W.items()}
+    out_ref = o_qf.connector(Wg, cfg, taps)
+    (out_ref * gout).sum().backward()
+
+    p = build_perception(cfg, W).train()
+    for prm in p.whisper.parameters():
+        prm.requires_grad_(False)
+    wave = torch.from_numpy(np.stack([o_mel.pad_or_truncate(w) for w in waves])).cuda()
+    feats, _ = p(input_features=wave)
+    assert feats.requires_grad
+    assert _rel(feats, out_ref) <= 2e-2
+    (feats * gout.cuda()).sum().backward()
+    worst = (0.0, "")
+    n = 0
+    for pname, prm in p.connector.named_parameters():
+        ref = Wg["perception.connector." + pname].grad
+        assert prm.grad is not None, pname
+        rel, cos = _rel(prm.grad, ref), _cos(prm.grad, ref)
+        worst = max(worst, (rel, pname))
+        assert rel <= 5e-2 and cos >= 0.995, f"{pname}: rel {rel:.4f} cos {cos:.5f}"
+        n += 1
+    assert n == sum(k.startswith("perception.connector.") for k in W)
+    print(f"worst gradient rel err {worst}")
+    if name == "micro":   # golden gradients produced by the reference's own autograd
+        gold = np.load(os.path.join(golden_dir, "micro_path.npz"))
+        sd = dict(p.connector.named_parameters())
+        assert _rel(sd["layer_weights"].grad, torch.from_numpy(gold["grad_layer_weights"])) <= 5e-2
+        assert _rel(sd["proj.1.bias"].grad, torch.from_numpy(gold["grad_proj_bias"])) <= 5e-2
+        assert _rel(sd["qformer.layer.0.crossattention.self.query.weight"].grad[::8, ::8], torch.from_numpy(gold["grad_q0"])) <= 5e-2
+        assert _rel(sd["qformer.layer.1.crossattention.self.key.weight"].grad[::8, ::8], torch.from_numpy(gold["grad_k1"])) <= 5e-2
+    # a second step after an in-place parameter update must see the new weights (pack refresh)
+    with torch.no_grad():
+        for prm in p.connector.parameters():
+            prm.add_(0.01 * torch.randn_like(prm))
+    feats2, _ = p(input_features=wave)
+    assert (feats2 - feats).abs().max().item() > 0
