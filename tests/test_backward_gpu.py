@@ -150,13 +150,22 @@ def test_connector_gradients_vs_oracle(name, n_clips, golden_dir):
     (feats * gout.cuda()).sum().backward()
     worst = (0.0, "")
     n = 0
+    gmax = max(Wg["perception.connector." + pn].grad.abs().max().item() for pn, _ in p.connector.named_parameters())
+    bad = []
     for pname, prm in p.connector.named_parameters():
         ref = Wg["perception.connector." + pname].grad
         assert prm.grad is not None, pname
+        n += 1
+        if ref.abs().max().item() < 1e-6 * gmax:
+            # analytically zero gradient (softmax is invariant to a key bias): only noise on both sides
+            if prm.grad.abs().max().item() > 2e-3 * gmax:
+                bad.append(f"{pname}: |grad| {prm.grad.abs().max().item():.3e} but the reference gradient is zero")
+            continue
         rel, cos = _rel(prm.grad, ref), _cos(prm.grad, ref)
         worst = max(worst, (rel, pname))
-        assert rel <= 5e-2 and cos >= 0.995, f"{pname}: rel {rel:.4f} cos {cos:.5f}"
-        n += 1
+        if not (rel <= 5e-2 and cos >= 0.995):
+            bad.append(f"{pname}: rel {rel:.4f} cos {cos:.5f}")
+    assert not bad, "\n".join(bad)
     assert n == sum(k.startswith("perception.connector.") for k in W)
     print(f"worst gradient rel err {worst}")
     if name == "micro":   # golden gradients produced by the reference's own autograd
