@@ -137,19 +137,27 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     for (int j = 0; j < n_kv; ++j) {
       mbar_wait(s_full, j & 1);
       tcgen05_fence_after();
-      const int kv_valid = a.Tk - j * AT_BKV;          // columns >= kv_valid are padding
-      // pass 1: block row max
+      const int kv_valid = a.Tk - j * AT_BKV;          // columns >= kv_valid are padding (last block only)
+      const bool masked = kv_valid < AT_BKV;
+      // pass 1: block row max (3-input max; key masking only in the ragged last block)
       float m_blk = -INFINITY;
 #pragma unroll 1
       for (int ch = 0; ch < 4; ++ch) {
         uint32_t v[32];
         tmem_ld_32x32(tmem_S + lane_off + ch * 32, v);
         tmem_wait_ld();
+        if (masked) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float s = (ch * 32 + i < kv_valid) ? __uint_as_float(v[i]) : -INFINITY;
-          m_blk = fmaxf(m_blk, s);
+          for (int i = 0; i < 32; ++i)
+            if (ch * 32 + i >= kv_valid) v[i] = 0xff800000u;   // -inf
         }
+        float m0 = m_blk, m1 = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          m0 = max3(m0, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+          m1 = max3(m1, __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+        }
+        m_blk = fmaxf(m0, m1);
       }
       const float m_new = fmaxf(m_run, m_blk);
       const bool need = (m_new - m_run) * c > 8.0f;    // also true on the first block (m_run = -inf)
@@ -175,18 +183,24 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       // pass 2: p = exp2(c*s - c*m_run), row sum, bf16 P into the swizzled A-operand layout
       const float mc = m_run * c;
-      float l_blk = 0.f;
+      float l0 = 0.f, l1 = 0.f;
 #pragma unroll 1
       for (int ch = 0; ch < 4; ++ch) {
         uint32_t v[32];
         tmem_ld_32x32(tmem_S + lane_off + ch * 32, v);
         tmem_wait_ld();
+        if (masked) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (ch * 32 + i >= kv_valid) v[i] = 0xff800000u;   // exp2(-inf) = 0
+        }
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          float p0 = (ch * 32 + i < kv_valid) ? fast_exp2(fmaf(__uint_as_float(v[i]), c, -mc)) : 0.f;
-          float p1 = (ch * 32 + i + 1 < kv_valid) ? fast_exp2(fmaf(__uint_as_float(v[i + 1]), c, -mc)) : 0.f;
-          l_blk += p0 + p1;
+          const float p0 = fast_exp2(fmaf(__uint_as_float(v[i]), c, -mc));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(v[i + 1]), c, -mc));
+          l0 += p0;
+          l1 += p1;
           pk[i >> 1] = pack_bf16(p0, p1);
         }
         // 32 columns = 4 chunks of 16 B; column chunk index inside the 64-column atom: (ch & 1) * 4 + q
@@ -197,6 +211,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           *reinterpret_cast<uint4*>(atom + chunk * 16) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
         }
       }
+      const float l_blk = l0 + l1;
       l_run += l_blk;
       fence_proxy_async_smem();       // generic-proxy smem writes -> visible to the tensor core (async proxy)
       tcgen05_fence_before();         // orders this thread's TMEM loads/stores before the MMA warp's next MMAs

@@ -13,6 +13,7 @@
 //   C[Nout,Kin] += dY[Mred,Nout]^T · X[Mred,Kin] — both operands are read as they lie in memory (reduction dim = rows),
 //   i.e. MN-major UMMA operands: TMA boxes of 64 rows x 64 columns land as 128-byte-swizzled atoms, LBO = 8 KB between
 //   the 64-column atoms, SBO = 1 KB between 8-row groups.  Optional split-K over the reduction with fp32 atomics.
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -261,6 +262,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
+int launch_gemm_2cta(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const desta_gemm_epilogue* ep,
+                     cudaStream_t stream);
+
 static int g_num_sms = 0;
 int num_sms() {
   if (g_num_sms == 0) {
@@ -305,6 +309,9 @@ extern "C" int desta_gemm_bf16(const void* A, int lda, const void* W, int ldw, i
     set_error("desta_gemm_bf16: output/residual leading dims must keep 16-byte row alignment");
     return DESTA_ERR_ARG;
   }
+  static int force_1cta = -1;
+  if (force_1cta < 0) { const char* e = getenv("DESTA_GEMM_1CTA"); force_1cta = (e && e[0] == '1') ? 1 : 0; }
+  if (!force_1cta && M > 128) return launch_gemm_2cta(A, lda, W, ldw, M, N, K, ep, (cudaStream_t)stream);
   CUtensorMap tmA, tmB;
   if (make_tmap_2d_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM, BK)) return DESTA_ERR_CUDA;
   if (make_tmap_2d_bf16(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, BN, BK)) return DESTA_ERR_CUDA;

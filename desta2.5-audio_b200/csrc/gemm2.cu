@@ -1,0 +1,335 @@
+// 2-CTA (cta_group::2) persistent tcgen05 GEMM:  C[M,N] = epilogue( A[M,K] · W[N,K]^T ), bf16 in, fp32 accumulate.
+//
+// A CTA pair (thread-block cluster of 2, one TPC) owns a 256 x 256 output tile: each CTA stages its own 128 rows of A
+// and HALF of the W tile (128 of the 256 N-rows) per k-block, and the leader CTA issues UMMA 256x256x16 — the tensor
+// cores of both SMs read the two B halves from both shared memories, which halves the shared-memory traffic per FLOP
+// compared with the 1-CTA kernel in gemm.cu (ncu showed that one pinned at ~75 % tensor-pipe by smem bandwidth).
+//   per CTA: 5-stage ring of (16 KB A + 16 KB B), 2 x 256 TMEM columns (epilogue of tile i overlaps MMAs of tile i+1),
+//   warp 0 TMA producer (2SM loads signal the leader's mbarrier), warp 1 MMA issuer (leader only), warp 2 TMEM alloc,
+//   warps 4..11 epilogue.
+// Epilogue: same fused ops as gemm.cu; bf16 outputs leave through shared-memory staging + TMA bulk stores
+// (32x32 boxes per warp, SWIZZLE_64B) instead of scattered 16-byte row stores through the LSU.
+#include "common.cuh"
+#include "desta_b200.h"
+
+namespace desta {
+
+namespace g2 {
+constexpr int BM = 128, BN = 256, BNH = 128, BK = 64, STAGES = 5, UMMA_K = 16;
+constexpr int A_BYTES = BM * BK * 2, B_BYTES = BNH * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;   // 32 KB
+constexpr int STAGING_PER_WARP = 2 * 4096;
+constexpr int EPI_WARP0 = 4, EPI_WARPS = 8, THREADS = 384;
+constexpr int SMEM = STAGES * STAGE_BYTES + EPI_WARPS * STAGING_PER_WARP + 1024 + 256;
+}  // namespace g2
+
+struct Gemm2Args {
+  int M, N, K;
+  float* out_f32; int ld_f32;
+  int has_bf16;            // bf16 output through tmC
+  const float* bias;
+  const float* resid; int ld_resid;
+  const float* pos; int pos_rows;
+  float scale; int scale_cols;
+  int gelu;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}\n"
+      ::"r"(smem_u32(bar)), "r"(cta)
+      : "memory");
+}
+// 2SM TMA load: data lands in THIS CTA's smem, transaction bytes are counted on the LEADER CTA's mbarrier
+__device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  const uint32_t leader_bar = smem_u32(bar) & 0xFEFFFFFFu;
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(m), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_ss_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                  uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (once all previously issued MMAs completed) on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(m), "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2::THREADS, 1)
+gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                         const __grid_constant__ CUtensorMap tmC, const Gemm2Args g) {
+  using namespace g2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* staging = smem + STAGES * STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + EPI_WARPS * STAGING_PER_WARP);
+  uint64_t* full = bars;                        // [STAGES] used in the leader: 2 producer arrivals + tx bytes of both CTAs
+  uint64_t* empty = bars + STAGES;              // [STAGES] per CTA, arrived by the leader's multicast commit
+  uint64_t* acc_full = bars + 2 * STAGES;       // [2] per CTA (multicast commit)
+  uint64_t* acc_empty = bars + 2 * STAGES + 2;  // [2] used in the leader: epilogue warps of both CTAs
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int m_tiles = (g.M + 2 * BM - 1) / (2 * BM), n_tiles = (g.N + BN - 1) / BN;
+  const int num_tiles = m_tiles * n_tiles;
+  const int k_blocks = (g.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    if (g.has_bf16) tma_prefetch_desc(&tmC);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 2); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 2 * EPI_WARPS); }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();          // peer barriers initialised / TMEM allocated in both CTAs
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += n_pairs) {
+        const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+        const int row_a = m_blk * 2 * BM + (int)rank * BM;
+        const int row_b = n_blk * BN + (int)rank * BNH;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          tma_load_2d_2sm(sa, &tmA, &full[stage], kb * BK, row_a);
+          tma_load_2d_2sm(sa + A_BYTES, &tmB, &full[stage], kb * BK, row_b);
+          if (leader) mbar_arrive_expect_tx(&full[stage], 2 * STAGE_BYTES);
+          else mbar_arrive_cluster(&full[stage], 0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN, 0, 0);
+      int stage = 0; uint32_t phase = 0;
+      int local = 0;
+      for (int tile = pair; tile < num_tiles; tile += n_pairs, ++local) {
+        const int as = local & 1;
+        const uint32_t acc_phase = (local >> 1) & 1;
+        mbar_wait(&acc_empty[as], acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint64_t adesc = umma_desc_sw128(sa, 16, 1024);
+          const uint64_t bdesc = umma_desc_sw128(sa + A_BYTES, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) umma_bf16_ss_2cta(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          umma_commit_2cta(&empty[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2cta(&acc_full[as]);
+      }
+    }
+  } else if (warp >= EPI_WARP0) {
+    const int q = warp & 3;
+    const int half = (warp - EPI_WARP0) >> 2;
+    uint8_t* stg = staging + (warp - EPI_WARP0) * STAGING_PER_WARP;
+    int local = 0;
+    int nstore = 0;
+    for (int tile = pair; tile < num_tiles; tile += n_pairs, ++local) {
+      const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+      const int as = local & 1;
+      const uint32_t acc_phase = (local >> 1) & 1;
+      mbar_wait(&acc_full[as], acc_phase);
+      tcgen05_fence_after();
+      const int row0 = m_blk * 2 * BM + (int)rank * BM + q * 32;
+      const int row = row0 + lane;
+      const bool row_ok = row < g.M;
+      const uint32_t taddr0 = tmem_base + as * BN + half * 128 + ((uint32_t)(q * 32) << 16);
+      const float* pos_row = g.pos ? g.pos + (size_t)(row % g.pos_rows) * g.N : nullptr;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        __syncwarp();
+        tmem_ld_32x32(taddr0 + c * 32, v);
+        tmem_wait_ld();
+        if (c == 3) {
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(&acc_empty[as], 0);
+        }
+        const int col0 = n_blk * BN + half * 128 + c * 32;
+        if (col0 >= g.N) continue;
+        const bool full_cols = (col0 + 32 <= g.N);
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (g.bias) {
+          if (full_cols) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + col0 + j));
+              f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (col0 + j < g.N) f[j] += __ldg(g.bias + col0 + j);
+          }
+        }
+        if (col0 < g.scale_cols) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) if (col0 + j < g.scale_cols) f[j] *= g.scale;
+        }
+        if (g.gelu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+        }
+        if (row_ok) {
+          if (pos_row) {
+            if (full_cols) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(pos_row + col0 + j));
+                f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (col0 + j < g.N) f[j] += __ldg(pos_row + col0 + j);
+            }
+          }
+          if (g.resid) {
+            const float* r = g.resid + (size_t)row * g.ld_resid + col0;
+            if (full_cols) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 b = *reinterpret_cast<const float4*>(r + j);
+                f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (col0 + j < g.N) f[j] += r[j];
+            }
+          }
+          if (g.out_f32) {
+            float* o = g.out_f32 + (size_t)row * g.ld_f32 + col0;
+            if (full_cols) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (col0 + j < g.N) o[j] = f[j];
+            }
+          }
+        }
+        if (g.has_bf16) {
+          // stage 32 rows x 32 bf16 (64-byte rows, SWIZZLE_64B) and hand the box to the TMA (clips at M / N itself)
+          uint8_t* buf = stg + (nstore & 1) * 4096;
+          if (lane == 0) bulk_wait_read<1>();          // the store that used this buffer two chunks ago has read it
+          __syncwarp();
+          uint8_t* rowp = buf + lane * 64;
+          const int sw = (lane >> 1) & 3;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 u;
+            u.x = pack_bf16(f[8 * j], f[8 * j + 1]); u.y = pack_bf16(f[8 * j + 2], f[8 * j + 3]);
+            u.z = pack_bf16(f[8 * j + 4], f[8 * j + 5]); u.w = pack_bf16(f[8 * j + 6], f[8 * j + 7]);
+            *reinterpret_cast<uint4*>(rowp + ((j ^ sw) << 4)) = u;
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (row0 < g.M) tma_store_2d(&tmC, buf, col0, row0);
+            bulk_commit();
+          }
+          ++nstore;
+        }
+      }
+    }
+    if (g.has_bf16 && lane == 0) bulk_wait_all();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();          // nobody exits (or frees TMEM) while the peer may still touch this CTA's smem / barriers
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+  }
+}
+
+int num_sms();
+
+int launch_gemm_2cta(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const desta_gemm_epilogue* ep,
+                     cudaStream_t stream) {
+  using namespace g2;
+  CUtensorMap tmA, tmB, tmC;
+  if (make_tmap_2d_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM, BK)) return DESTA_ERR_CUDA;
+  if (make_tmap_2d_bf16(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, BNH, BK)) return DESTA_ERR_CUDA;
+  if (ep->out_bf16) {
+    uint64_t dims[2] = {(uint64_t)N, (uint64_t)M};
+    uint64_t strides[2] = {0, (uint64_t)ep->ld_bf16 * 2};
+    uint32_t box[2] = {32, 32};
+    if (make_tmap(&tmC, ep->out_bf16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B))
+      return DESTA_ERR_CUDA;
+  } else {
+    tmC = tmA;
+  }
+  Gemm2Args g;
+  g.M = M; g.N = N; g.K = K;
+  g.out_f32 = ep->out_f32; g.ld_f32 = ep->ld_f32;
+  g.has_bf16 = ep->out_bf16 != nullptr;
+  g.bias = ep->bias; g.resid = ep->resid; g.ld_resid = ep->ld_resid;
+  g.pos = ep->pos; g.pos_rows = ep->pos_rows > 0 ? ep->pos_rows : 1;
+  g.scale = ep->scale; g.scale_cols = ep->scale_cols; g.gelu = ep->gelu;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e != cudaSuccess) { set_error("gemm 2cta smem attribute: %s", cudaGetErrorString(e)); return DESTA_ERR_CUDA; }
+    attr_set = true;
+  }
+  const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);
+  int pairs = num_sms() / 2;
+  if (tiles < pairs) pairs = tiles;
+  gemm_bf16_tn_2cta_kernel<<<2 * pairs, THREADS, SMEM, stream>>>(tmA, tmB, tmC, g);
+  return check_launch("gemm_bf16_tn_2cta_kernel");
+}
+
+}  // namespace desta

@@ -1,0 +1,79 @@
+"""Kernel micro-benchmarks on one B200 (CUDA events, L2-exceeding working sets). Usage: python tools/kbench.py [gemm] [attn] [mel] [splice]"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import __graft_entry__  # noqa: E402
+
+__graft_entry__.build()
+from desta_b200 import ops  # noqa: E402
+
+
+def timeit(fn, iters=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def bench_gemm():
+    M = 96000
+    for name, N, K, kw in [("qkv", 3840, 1280, dict(scale=0.125, scale_cols=1280)), ("out_proj+res", 1280, 1280, dict(resid=True)),
+                           ("fc1+gelu", 5120, 1280, dict(gelu=True)), ("fc2+res", 1280, 5120, dict(resid=True)),
+                           ("kvproj", 15360, 1280, {}), ("conv2", 1280, 3840, dict(gelu=True)), ("qf_small", 1280, 1280, dict(M=16384))]:
+        m = kw.pop("M", M)
+        a = torch.randn(m, K, device="cuda").to(torch.bfloat16)
+        w = (torch.randn(N, K, device="cuda") * 0.02).to(torch.bfloat16)
+        b = torch.randn(N, device="cuda")
+        if kw.pop("resid", False):
+            h = torch.randn(m, N, device="cuda")
+            fn = lambda: ops.gemm(a, w, b, out_f32=h, resid=h)  # noqa: E731
+        else:
+            o = torch.empty(m, N, device="cuda", dtype=torch.bfloat16)
+            fn = lambda: ops.gemm(a, w, b, out_bf16=o, **kw)  # noqa: E731
+        ms = timeit(fn)
+        print(f"gemm {name:14s} M={m} N={N} K={K}: {ms:.3f} ms  {2.0 * m * N * K / ms / 1e9:.0f} TFLOP/s", flush=True)
+        del a, w
+
+
+def bench_attn():
+    for name, B, H, Tq, Tk, scale in [("encoder", 64, 20, 1500, 1500, 1.0), ("qf_cross", 256, 20, 64, 1500, 0.125), ("qf_self", 256, 20, 64, 64, 0.125)]:
+        d = H * 64
+        qkv = torch.randn(B * max(Tq, Tk), 3 * d, device="cuda").to(torch.bfloat16)
+        out = torch.empty(B * Tq, d, device="cuda", dtype=torch.bfloat16)
+        fn = lambda: ops.attention(qkv[:B * Tq, :d], qkv[:B * Tk, d:2 * d], qkv[:B * Tk, 2 * d:], out, B, H, Tq, Tk, scale)  # noqa: E731
+        ms = timeit(fn)
+        print(f"attn {name:9s} B={B} H={H} Tq={Tq} Tk={Tk}: {ms:.3f} ms  {4.0 * B * H * Tq * Tk * 64 / ms / 1e9:.0f} TFLOP/s", flush=True)
+
+
+def bench_mel():
+    for N in (64, 256):
+        wave = torch.clamp(0.1 * torch.randn(N, 480000, device="cuda"), -1, 1)
+        ms = timeit(lambda: ops.logmel(wave, 128, want_bf16_tm=True))
+        print(f"logmel N={N}: {ms:.3f} ms  {N * (480000 * 4 + 128 * 3000 * 4) / ms / 1e6:.0f} GB/s (algorithmic in+out)", flush=True)
+
+
+def bench_splice():
+    for B, S, d, V in ((64, 128, 4096, 128256), (256, 512, 4096, 128256)):
+        table = (torch.randn(V, d, device="cuda") * 0.02).to(torch.bfloat16)
+        ids = torch.randint(0, V, (B, S), device="cuda")
+        feats = torch.randn(B, 64, d, device="cuda")
+        descs = [(i, 20, 0, 0) for i in range(B)]
+        out = torch.empty(B, S, d, device="cuda", dtype=torch.bfloat16)
+        ms = timeit(lambda: ops.splice(ids, table, descs, None, feats, 64, out=out))
+        nbytes = B * S * 8 + (B * S - B * 64) * d * 2 + B * 64 * d * 4 + B * S * d * 2
+        print(f"splice B={B} S={S} d={d}: {ms:.4f} ms  {nbytes / ms / 1e6:.0f} GB/s", flush=True)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["gemm", "attn", "mel", "splice"]
+    for w in which:
+        {"gemm": bench_gemm, "attn": bench_attn, "mel": bench_mel, "splice": bench_splice}[w]()
