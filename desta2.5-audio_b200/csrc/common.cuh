@@ -54,10 +54,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred P;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, P;\n\t}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)      // suspend-time hint: sleep in hardware, do not spin
       : "memory");
   return ok != 0;
 }
@@ -192,6 +192,38 @@ __device__ __forceinline__ float gelu_erf(float x) {
   const float e = 1.0f - p * t * __expf(-z * z);   // erf(|x|/sqrt2)
   const float erfv = copysignf(e, x);
   return 0.5f * x * (1.0f + erfv);
+}
+
+// erf-GELU for 32 accumulator values at once, MUFU-free and written stage-by-stage so that the 32 independent
+// Horner chains interleave (the per-element form above serialises on the MUFU scoreboard inside a GEMM epilogue).
+// erf(z) ~ z * P(z^2) on |z| <= 3 (minimax fit, |err| < 9e-5; erf(3) = 1 - 2.2e-5), z = x / sqrt(2) clamped:
+// |GELU error| < 2.6e-4 absolute, far below the bf16 rounding of the stored value.
+__device__ __forceinline__ void gelu_erf_x32(float (&f)[32]) {
+  float z2[32], p[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const float z = fminf(fmaxf(f[j] * 0.70710678118654752f, -3.0f), 3.0f);
+    z2[j] = z * z;
+    p[j] = fmaf(-4.055365537e-07f, z2[j], 1.715984945e-05f);
+  }
+#pragma unroll
+  for (int j = 0; j < 32; ++j) p[j] = fmaf(p[j], z2[j], -3.145955852e-04f);
+#pragma unroll
+  for (int j = 0; j < 32; ++j) p[j] = fmaf(p[j], z2[j], 3.318711650e-03f);
+#pragma unroll
+  for (int j = 0; j < 32; ++j) p[j] = fmaf(p[j], z2[j], -2.268580161e-02f);
+#pragma unroll
+  for (int j = 0; j < 32; ++j) p[j] = fmaf(p[j], z2[j], 1.077178270e-01f);
+#pragma unroll
+  for (int j = 0; j < 32; ++j) p[j] = fmaf(p[j], z2[j], -3.732313812e-01f);
+#pragma unroll
+  for (int j = 0; j < 32; ++j) p[j] = fmaf(p[j], z2[j], 1.127895713e+00f);
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const float z = fminf(fmaxf(f[j] * 0.70710678118654752f, -3.0f), 3.0f);
+    const float hx = 0.5f * f[j];
+    f[j] = fmaf(hx, p[j] * z, hx);
+  }
 }
 
 __device__ __forceinline__ float fast_exp2(float x) {

@@ -191,10 +191,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int j = 0; j < 32; ++j) if (col0 + j < g.scale_cols) f[j] *= g.scale;
         }
-        if (g.gelu) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
-        }
+        if (g.gelu) gelu_erf_x32(f);
         if (row_ok) {
         if (pos_row) {
           if (full_cols) {

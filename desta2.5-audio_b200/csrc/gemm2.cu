@@ -19,7 +19,7 @@ constexpr int BM = 128, BN = 256, BNH = 128, BK = 64, STAGES = 5, UMMA_K = 16;
 constexpr int A_BYTES = BM * BK * 2, B_BYTES = BNH * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;   // 32 KB
 constexpr int STAGING_PER_WARP = 2 * 4096;
 constexpr int EPI_WARP0 = 4, EPI_WARPS = 8, THREADS = 384;
-constexpr int SMEM = STAGES * STAGE_BYTES + EPI_WARPS * STAGING_PER_WARP + 1024 + 256;
+constexpr int SMEM = STAGES * STAGE_BYTES + EPI_WARPS * STAGING_PER_WARP + 1024 + 256 + EPI_WARPS * 512;
 }  // namespace g2
 
 struct Gemm2Args {
@@ -97,6 +97,7 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   uint64_t* acc_full = bars + 2 * STAGES;       // [2] per CTA (multicast commit)
   uint64_t* acc_empty = bars + 2 * STAGES + 2;  // [2] used in the leader: epilogue warps of both CTAs
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  float* bias_all = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [EPI_WARPS][128]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -179,6 +180,20 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
       const int as = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
+      float* bias_s = bias_all + (warp - EPI_WARP0) * 128;
+      if (g.bias) {       // this warp's 128 bias values, fetched while the MMAs of the tile are still running
+        const int cb = n_blk * BN + half * 128 + lane * 4;
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (cb + 3 < g.N) b4 = __ldg(reinterpret_cast<const float4*>(g.bias + cb));
+        else {
+          if (cb < g.N) b4.x = __ldg(g.bias + cb);
+          if (cb + 1 < g.N) b4.y = __ldg(g.bias + cb + 1);
+          if (cb + 2 < g.N) b4.z = __ldg(g.bias + cb + 2);
+        }
+        __syncwarp();
+        reinterpret_cast<float4*>(bias_s)[lane] = b4;
+        __syncwarp();
+      }
       mbar_wait(&acc_full[as], acc_phase);
       tcgen05_fence_after();
       const int row0 = m_blk * 2 * BM + (int)rank * BM + q * 32;
@@ -204,25 +219,17 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
         if (g.bias) {
-          if (full_cols) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + col0 + j));
-              f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) if (col0 + j < g.N) f[j] += __ldg(g.bias + col0 + j);
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b = reinterpret_cast<const float4*>(bias_s + c * 32)[j >> 2];   // broadcast read
+            f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
           }
         }
         if (col0 < g.scale_cols) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) if (col0 + j < g.scale_cols) f[j] *= g.scale;
         }
-        if (g.gelu) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
-        }
+        if (g.gelu) gelu_erf_x32(f);
         if (row_ok) {
           if (pos_row) {
             if (full_cols) {
