@@ -3,34 +3,76 @@
 // pre-scaled) and the eager Bert self / cross attention of the Q-Former ($TF/models/bert/modeling_bert.py:168-207,
 // 234-284; 64 queries x 64 or 1500 keys, scale 1/8).
 //
-// One CTA = 128 query rows of one (batch, head); two CTAs are co-resident per SM (112 KB smem, 256 TMEM columns each)
-// so one CTA's softmax overlaps the other's MMAs.
-//   warp 0   : TMA producer  (Q once; K/V blocks of 128 keys through a 2-stage mbarrier ring, SWIZZLE_128B)
-//   warp 1   : TMEM allocator + MMA issuer: S = Q K^T (UMMA 128x128x16, both operands K-major),
+// One CTA = 128 query rows of one (batch, head); two CTAs are co-resident per SM (112 KB smem, 256 TMEM columns each).
+// Keys are processed in blocks of 64 with DOUBLE-BUFFERED scores (S) and probabilities (P): the MMA warp computes
+// S_{j+2} = Q K_{j+2}^T while the softmax warps are still exponentiating block j, so the softmax warps — which are the
+// bottleneck at head_dim 64 (MUFU ex2 throughput) — never wait on the tensor core.
+//   warp 0   : TMA producer  (Q once; K/V blocks of 64 keys through a 4-stage mbarrier ring, SWIZZLE_128B)
+//   warp 1   : TMEM allocator + MMA issuer: S = Q K^T (UMMA 128x64x16, both operands K-major),
 //              O += P V (UMMA 128x64x16, A = P from shared memory K-major, B = V MN-major as it lies in memory)
-//   warps 2-5: softmax, one query row per thread (TMEM lane == row): running max / sum in fp32, exp2 with the scale
-//              folded in, lazy rescale of the O accumulator in TMEM (only when the max grows by > 2^8), P written as
-//              bf16 into the 128B-swizzled A-operand layout, final 1/l normalisation and 128-byte row stores.
+//   warps 2-5: softmax, one query row per thread (TMEM lane == row).  ONE TMEM pass per block: exponentials are taken
+//              against the running max of the previous blocks while the block max is gathered in the same pass; only
+//              when a row's max grows by more than 2^8 is the reference raised (O and l rescaled in TMEM) and the block
+//              redone.  P is written as bf16 into the 128B-swizzled A-operand layout; final 1/l and 128-byte row stores.
 #include "common.cuh"
 #include "desta_b200.h"
 
 namespace desta {
 
-constexpr int AT_BQ = 128, AT_BKV = 128, AT_HD = 64, AT_STAGES = 2;
+constexpr int AT_BQ = 128, AT_BKV = 64, AT_HD = 64, AT_STAGES = 4;
 constexpr int AT_Q_BYTES = AT_BQ * AT_HD * 2;      // 16 KB
-constexpr int AT_KV_BYTES = AT_BKV * AT_HD * 2;    // 16 KB (K) + 16 KB (V) per stage
-constexpr int AT_P_BYTES = AT_BQ * AT_BKV * 2;     // 32 KB
-constexpr int AT_SMEM = AT_Q_BYTES + AT_STAGES * 2 * AT_KV_BYTES + AT_P_BYTES + 128;   // 114,816 B -> 2 CTAs / SM
+constexpr int AT_KV_BYTES = AT_BKV * AT_HD * 2;    // 8 KB (K) + 8 KB (V) per stage
+constexpr int AT_P_BYTES = AT_BQ * AT_BKV * 2;     // 16 KB, double-buffered
+constexpr int AT_SMEM = AT_Q_BYTES + AT_STAGES * 2 * AT_KV_BYTES + 2 * AT_P_BYTES + 128;   // 114,816 B -> 2 CTAs / SM
 constexpr int AT_THREADS = 192;
-constexpr int AT_TMEM_COLS = 256;                  // S: [0,128)  O: [128,192)
+constexpr int AT_TMEM_COLS = 256;                  // S0: [0,64)  S1: [64,128)  O: [128,192)
 
 struct AttnArgs {
   __nv_bfloat16* out; int ldo;
   int Tq, Tk;
   float scale_log2;    // scale * log2(e)
-  int q_rows, kv_rows; // TMA box rows actually loaded (min(128, T))
+  int q_rows, kv_rows; // TMA box rows actually loaded (min(tile, T))
   float* lse;          // optional [batch, heads, Tq]: log2-domain log-sum-exp of the scaled scores (for the backward)
 };
+
+// One softmax pass over a 128 x 64 score block held in TMEM: p = exp2(c*s - mc) written as bf16 into the swizzled
+// A-operand tile, row sum and row max returned.  Key masking only in the ragged last block.
+__device__ __forceinline__ void softmax_pass(uint32_t tS, uint8_t* prow, int rx, float c, float mc, int kv_valid, float& l_blk,
+                                             float& m_blk) {
+  const bool masked = kv_valid < AT_BKV;
+  float l0 = 0.f, l1 = 0.f, m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll 1
+  for (int ch = 0; ch < 2; ++ch) {
+    uint32_t v[32];
+    tmem_ld_32x32(tS + ch * 32, v);
+    tmem_wait_ld();
+    if (masked) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (ch * 32 + i >= kv_valid) v[i] = 0xff800000u;   // -inf: exp2 -> 0, ignored by max
+    }
+    uint32_t pk[16];
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      const float s0 = __uint_as_float(v[i]), s1 = __uint_as_float(v[i + 1]), s2 = __uint_as_float(v[i + 2]), s3 = __uint_as_float(v[i + 3]);
+      m0 = max3(m0, s0, s1);
+      m1 = max3(m1, s2, s3);
+      const float p0 = fast_exp2(fmaf(s0, c, -mc)), p1 = fast_exp2(fmaf(s1, c, -mc));
+      const float p2 = fast_exp2(fmaf(s2, c, -mc)), p3 = fast_exp2(fmaf(s3, c, -mc));
+      l0 += p0 + p1;
+      l1 += p2 + p3;
+      pk[i >> 1] = pack_bf16(p0, p1);
+      pk[(i >> 1) + 1] = pack_bf16(p2, p3);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int chunk = (ch * 4 + q) ^ rx;
+      *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+    }
+  }
+  l_blk = l0 + l1;
+  m_blk = fmaxf(m0, m1);
+}
 
 __global__ void __launch_bounds__(AT_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -38,16 +80,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   extern __shared__ __align__(1024) uint8_t smem[];   // SWIZZLE_128B tiles need 1024-byte alignment
   if (smem_u32(smem) & 1023) __trap();
   uint8_t* sQ = smem;
-  uint8_t* sKV = sQ + AT_Q_BYTES;                       // stage s: K at s*32K, V at s*32K + 16K
-  uint8_t* sP = sKV + AT_STAGES * 2 * AT_KV_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + AT_P_BYTES);
+  uint8_t* sKV = sQ + AT_Q_BYTES;                       // stage s: K at s*16K, V at s*16K + 8K
+  uint8_t* sP = sKV + AT_STAGES * 2 * AT_KV_BYTES;      // two P tiles of 16 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * AT_P_BYTES);
   uint64_t* q_full = bars;            // 1
-  uint64_t* kv_full = bars + 1;       // [2]
-  uint64_t* kv_empty = bars + 3;      // [2]
-  uint64_t* s_full = bars + 5;
-  uint64_t* p_ready = bars + 6;
-  uint64_t* pv_done = bars + 7;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* kv_full = bars + 1;       // [4]
+  uint64_t* kv_empty = bars + 5;      // [4]
+  uint64_t* s_full = bars + 9;        // [2]
+  uint64_t* p_ready = bars + 11;      // [2]
+  uint64_t* pv_done = bars + 13;      // [2]: PV_j commits to pv_done[j & 1] (two barriers: a waiter is never 2 phases behind)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * AT_BQ, head = blockIdx.y, batch = blockIdx.z;
@@ -62,7 +104,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
     mbar_init(q_full, 1);
     for (int i = 0; i < AT_STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
-    mbar_init(s_full, 1); mbar_init(p_ready, 128); mbar_init(pv_done, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 128); }
+    mbar_init(&pv_done[0], 1); mbar_init(&pv_done[1], 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<AT_TMEM_COLS>(tmem_slot);
@@ -70,15 +113,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;
+  const uint32_t tmem_O = tmem_base + 128;
 
   if (warp == 0) {
     if (lane == 0) {
       mbar_arrive_expect_tx(q_full, a.q_rows * AT_HD * 2);
       tma_load_3d(sQ, &tmQ, q_full, head * AT_HD, q0, batch);
       for (int j = 0; j < n_kv; ++j) {
-        const int st = j & 1;
-        mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
+        const int st = j % AT_STAGES;
+        mbar_wait(&kv_empty[st], ((j / AT_STAGES) & 1) ^ 1);
         mbar_arrive_expect_tx(&kv_full[st], 2 * a.kv_rows * AT_HD * 2);
         tma_load_3d(sKV + st * 2 * AT_KV_BYTES, &tmK, &kv_full[st], head * AT_HD, j * AT_BKV, batch);
         tma_load_3d(sKV + st * 2 * AT_KV_BYTES + AT_KV_BYTES, &tmV, &kv_full[st], head * AT_HD, j * AT_BKV, batch);
@@ -89,40 +132,33 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       constexpr uint32_t idesc_qk = umma_idesc_bf16(AT_BQ, AT_BKV, 0, 0);
       constexpr uint32_t idesc_pv = umma_idesc_bf16(AT_BQ, AT_HD, 0, 1);   // B (= V) is MN-major
       const uint64_t qdesc = umma_desc_sw128(smem_u32(sQ), 16, 1024);
-      const uint64_t pdesc = umma_desc_sw128(smem_u32(sP), 16, 1024);
-      mbar_wait(q_full, 0);
-      mbar_wait(&kv_full[0], 0);
-      tcgen05_fence_after();
-      {
-        const uint64_t kdesc = umma_desc_sw128(smem_u32(sKV), 16, 1024);
-#pragma unroll
-        for (int k = 0; k < AT_HD / 16; ++k) umma_bf16_ss(tmem_S, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, k != 0);
-        umma_commit(s_full);
-      }
-      for (int j = 0; j < n_kv; ++j) {
-        const int st = j & 1;
-        mbar_wait(p_ready, j & 1);           // P_j in smem, S_j consumed, O rescaled if needed
+      // S_j = Q K_j^T into S buffer (j & 1); issued two blocks ahead of the softmax
+      auto issue_qk = [&](int j) {
+        const int st = j % AT_STAGES;
+        mbar_wait(&kv_full[st], (j / AT_STAGES) & 1);
         tcgen05_fence_after();
-        // V stage: 128 key rows x 128 B (64 head-dim values) -> MN-major B operand, 8-row groups 1024 B apart
+        const uint64_t kdesc = umma_desc_sw128(smem_u32(sKV + st * 2 * AT_KV_BYTES), 16, 1024);
+#pragma unroll
+        for (int k = 0; k < AT_HD / 16; ++k)
+          umma_bf16_ss(tmem_base + (j & 1) * AT_BKV, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, k != 0);
+        umma_commit(&s_full[j & 1]);
+      };
+      mbar_wait(q_full, 0);
+      issue_qk(0);
+      if (n_kv > 1) issue_qk(1);
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j % AT_STAGES;
+        mbar_wait(&p_ready[j & 1], (j >> 1) & 1);   // P_j in smem, S_j consumed, O rescaled if needed
+        tcgen05_fence_after();
+        // V stage: 64 key rows x 128 B (64 head-dim values) -> MN-major B operand, 8-row groups 1024 B apart
         const uint64_t vdesc = umma_desc_sw128(smem_u32(sKV + st * 2 * AT_KV_BYTES + AT_KV_BYTES), 1024, 1024);
+        const uint64_t pdesc = umma_desc_sw128(smem_u32(sP + (j & 1) * AT_P_BYTES), 16, 1024);
 #pragma unroll
-        for (int k = 0; k < AT_BKV / 16; ++k) {
-          // A = P[:, 16k .. 16k+16): atom (k / 4) of 16 KB, 32 B per step inside the 128-byte swizzle row
-          const uint64_t pd = pdesc + (uint64_t)((k >> 2) * (AT_BQ * 128 / 16) + (k & 3) * 2);
-          const uint64_t vd = vdesc + (uint64_t)(k * (16 * 128 / 16));
-          umma_bf16_ss(tmem_O, pd, vd, idesc_pv, (j | k) != 0);
-        }
+        for (int k = 0; k < AT_BKV / 16; ++k)
+          umma_bf16_ss(tmem_O, pdesc + 2 * k, vdesc + (uint64_t)(k * 128), idesc_pv, (j | k) != 0);
         umma_commit(&kv_empty[st]);
-        umma_commit(pv_done);
-        if (j + 1 < n_kv) {
-          const int sn = (j + 1) & 1;
-          mbar_wait(&kv_full[sn], ((j + 1) >> 1) & 1);
-          tcgen05_fence_after();
-          const uint64_t kdesc = umma_desc_sw128(smem_u32(sKV + sn * 2 * AT_KV_BYTES), 16, 1024);
-#pragma unroll
-          for (int k = 0; k < AT_HD / 16; ++k) umma_bf16_ss(tmem_S, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, k != 0);
-          umma_commit(s_full);
-        }
+        umma_commit(&pv_done[j & 1]);
+        if (j + 2 < n_kv) issue_qk(j + 2);          // S buffer (j & 1) is free again
       }
     }
   } else {
@@ -132,39 +168,37 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     const float c = a.scale_log2;
     float m_run = -INFINITY, l_run = 0.f;
-    uint8_t* prow = sP + r * 128;
     const int rx = r & 7;
     for (int j = 0; j < n_kv; ++j) {
-      mbar_wait(s_full, j & 1);
+      const uint32_t tS = tmem_base + (j & 1) * AT_BKV + lane_off;
+      uint8_t* prow = sP + (j & 1) * AT_P_BYTES + r * 128;
+      mbar_wait(&s_full[j & 1], (j >> 1) & 1);        // (implies PV_{j-2} finished: the P buffer is free)
       tcgen05_fence_after();
-      const int kv_valid = a.Tk - j * AT_BKV;          // columns >= kv_valid are padding (last block only)
-      const bool masked = kv_valid < AT_BKV;
-      // pass 1: block row max (3-input max; key masking only in the ragged last block)
-      float m_blk = -INFINITY;
+      const int kv_valid = a.Tk - j * AT_BKV;
+      if (j == 0) {
+        // first block: no reference max yet -> plain max pass
+        float m0 = -INFINITY;
 #pragma unroll 1
-      for (int ch = 0; ch < 4; ++ch) {
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_S + lane_off + ch * 32, v);
-        tmem_wait_ld();
-        if (masked) {
+        for (int ch = 0; ch < 2; ++ch) {
+          uint32_t v[32];
+          tmem_ld_32x32(tS + ch * 32, v);
+          tmem_wait_ld();
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (ch * 32 + i >= kv_valid) v[i] = 0xff800000u;   // -inf
+          for (int i = 0; i < 32; i += 2)
+            m0 = max3(m0, (ch * 32 + i < kv_valid) ? __uint_as_float(v[i]) : -INFINITY,
+                      (ch * 32 + i + 1 < kv_valid) ? __uint_as_float(v[i + 1]) : -INFINITY);
         }
-        float m0 = m_blk, m1 = -INFINITY;
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          m0 = max3(m0, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
-          m1 = max3(m1, __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
-        }
-        m_blk = fmaxf(m0, m1);
+        m_run = m0;
       }
-      const float m_new = fmaxf(m_run, m_blk);
-      const bool need = (m_new - m_run) * c > 8.0f;    // also true on the first block (m_run = -inf)
+      // exp pass against the running max of the PREVIOUS blocks; the block max comes out of the same pass
+      float l_blk, m_blk;
+      softmax_pass(tS, prow, rx, c, m_run * c, kv_valid, l_blk, m_blk);
+      const bool need = (m_blk - m_run) * c > 8.0f;    // exponent headroom exceeded somewhere in this row
       if (__any_sync(0xffffffffu, need)) {
+        // rare: raise the reference max, rescale O and l, redo the block's exponentials
+        const float m_new = fmaxf(m_run, m_blk);
         if (j > 0) {
-          // PV_{j-1} was issued before QK_j, so it has completed; wait anyway (cheap) before touching O
-          mbar_wait(pv_done, (j - 1) & 1);
+          mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);   // PV_{j-1} must have landed in O
           tcgen05_fence_after();
           const float f = exp2f((m_run - m_new) * c);
           l_run *= f;
@@ -180,45 +214,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           tmem_wait_st();
         }
         m_run = m_new;
+        softmax_pass(tS, prow, rx, c, m_run * c, kv_valid, l_blk, m_blk);
       }
-      // pass 2: p = exp2(c*s - c*m_run), row sum, bf16 P into the swizzled A-operand layout
-      const float mc = m_run * c;
-      float l0 = 0.f, l1 = 0.f;
-#pragma unroll 1
-      for (int ch = 0; ch < 4; ++ch) {
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_S + lane_off + ch * 32, v);
-        tmem_wait_ld();
-        if (masked) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (ch * 32 + i >= kv_valid) v[i] = 0xff800000u;   // exp2(-inf) = 0
-        }
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const float p0 = fast_exp2(fmaf(__uint_as_float(v[i]), c, -mc));
-          const float p1 = fast_exp2(fmaf(__uint_as_float(v[i + 1]), c, -mc));
-          l0 += p0;
-          l1 += p1;
-          pk[i >> 1] = pack_bf16(p0, p1);
-        }
-        // 32 columns = 4 chunks of 16 B; column chunk index inside the 64-column atom: (ch & 1) * 4 + q
-        uint8_t* atom = prow + (ch >> 1) * (AT_BQ * 128);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int chunk = ((ch & 1) * 4 + q) ^ rx;
-          *reinterpret_cast<uint4*>(atom + chunk * 16) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-        }
-      }
-      const float l_blk = l0 + l1;
       l_run += l_blk;
       fence_proxy_async_smem();       // generic-proxy smem writes -> visible to the tensor core (async proxy)
       tcgen05_fence_before();         // orders this thread's TMEM loads/stores before the MMA warp's next MMAs
-      mbar_arrive(p_ready);
+      mbar_arrive(&p_ready[j & 1]);
     }
     // ---- epilogue: O / l -> bf16, one 128-byte row per thread ----
-    mbar_wait(pv_done, (n_kv - 1) & 1);
+    mbar_wait(&pv_done[(n_kv - 1) & 1], ((n_kv - 1) >> 1) & 1);
     tcgen05_fence_after();
     const float inv = 1.0f / l_run;
     const int row = q0 + r;

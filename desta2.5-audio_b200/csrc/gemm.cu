@@ -86,7 +86,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
         const int kb0 = split * kb_per, kb1 = min(k_blocks_total, kb0 + kb_per);
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_wait_sleep(&empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
           uint8_t* sa = smem + stage * STAGE_BYTES;
           if (MODE == MODE_TN) {
@@ -152,7 +152,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
       const int as = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
-      mbar_wait(&acc_full[as], acc_phase);
+      mbar_wait_sleep(&acc_full[as], acc_phase);
       tcgen05_fence_after();
       const int row = m_blk * BM + q * 32 + lane;
       const bool row_ok = row < g.M;

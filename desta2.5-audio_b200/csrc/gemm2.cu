@@ -17,7 +17,7 @@ namespace desta {
 namespace g2 {
 constexpr int BM = 128, BN = 256, BNH = 128, BK = 64, STAGES = 5, UMMA_K = 16;
 constexpr int A_BYTES = BM * BK * 2, B_BYTES = BNH * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;   // 32 KB
-constexpr int STAGING_PER_WARP = 2 * 4096;
+constexpr int STAGING_PER_WARP = 2 * 2048;   // two 32x32 bf16 boxes per epilogue warp
 constexpr int EPI_WARP0 = 4, EPI_WARPS = 8, THREADS = 384;
 constexpr int SMEM = STAGES * STAGE_BYTES + EPI_WARPS * STAGING_PER_WARP + 1024 + 256 + EPI_WARPS * 512;
 }  // namespace g2
@@ -135,7 +135,7 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         const int row_a = m_blk * 2 * BM + (int)rank * BM;
         const int row_b = n_blk * BN + (int)rank * BNH;
         for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_wait_sleep(&empty[stage], phase ^ 1);
           uint8_t* sa = smem + stage * STAGE_BYTES;
           tma_load_2d_2sm(sa, &tmA, &full[stage], kb * BK, row_a);
           tma_load_2d_2sm(sa + A_BYTES, &tmB, &full[stage], kb * BK, row_b);
@@ -194,7 +194,7 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         reinterpret_cast<float4*>(bias_s)[lane] = b4;
         __syncwarp();
       }
-      mbar_wait(&acc_full[as], acc_phase);
+      mbar_wait_sleep(&acc_full[as], acc_phase);
       tcgen05_fence_after();
       const int row0 = m_blk * 2 * BM + (int)rank * BM + q * 32;
       const int row = row0 + lane;
@@ -269,7 +269,7 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         }
         if (g.has_bf16) {
           // stage 32 rows x 32 bf16 (64-byte rows, SWIZZLE_64B) and hand the box to the TMA (clips at M / N itself)
-          uint8_t* buf = stg + (nstore & 1) * 4096;
+          uint8_t* buf = stg + (nstore & 1) * 2048;
           if (lane == 0) bulk_wait_read<1>();          // the store that used this buffer two chunks ago has read it
           __syncwarp();
           uint8_t* rowp = buf + lane * 64;

@@ -56,7 +56,8 @@ def test_gemm_epilogues():
     # gelu + pos
     ops.gemm(a, w, bias, out_f32=out, gelu=True, pos=pos)
     ref = torch.nn.functional.gelu(acc) + pos.repeat(2, 1)
-    assert _rel(out, ref) < 2e-5
+    # the epilogue's erf-GELU is a MUFU-free polynomial: |abs err| < 2.6e-4, below bf16 output rounding
+    assert (out - ref).abs().max().item() < 5e-4
     # residual, fp32 + bf16 copy, in-place on the residual buffer
     buf = resid.clone()
     tap = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
