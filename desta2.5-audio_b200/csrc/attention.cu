@@ -36,25 +36,28 @@ struct AttnArgs {
 };
 
 // One softmax pass over a 128 x 64 score block held in TMEM: p = exp2(c*s - mc) written as bf16 into the swizzled
-// A-operand tile, row sum and row max returned.  Key masking only in the ragged last block.
+// A-operand tile, row sum and row max returned.  MASKED (ragged last key block only) selects -inf for padded keys
+// with predicated selects - no per-element branches.
+template <bool MASKED>
 __device__ __forceinline__ void softmax_pass(uint32_t tS, uint8_t* prow, int rx, float c, float mc, int kv_valid, float& l_blk,
                                              float& m_blk) {
-  const bool masked = kv_valid < AT_BKV;
   float l0 = 0.f, l1 = 0.f, m0 = -INFINITY, m1 = -INFINITY;
-#pragma unroll 1
+#pragma unroll
   for (int ch = 0; ch < 2; ++ch) {
     uint32_t v[32];
     tmem_ld_32x32(tS + ch * 32, v);
     tmem_wait_ld();
-    if (masked) {
-#pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (ch * 32 + i >= kv_valid) v[i] = 0xff800000u;   // -inf: exp2 -> 0, ignored by max
-    }
     uint32_t pk[16];
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
-      const float s0 = __uint_as_float(v[i]), s1 = __uint_as_float(v[i + 1]), s2 = __uint_as_float(v[i + 2]), s3 = __uint_as_float(v[i + 3]);
+      float s0 = __uint_as_float(v[i]), s1 = __uint_as_float(v[i + 1]), s2 = __uint_as_float(v[i + 2]), s3 = __uint_as_float(v[i + 3]);
+      if (MASKED) {
+        const int col = ch * 32 + i;
+        s0 = col < kv_valid ? s0 : -INFINITY;
+        s1 = col + 1 < kv_valid ? s1 : -INFINITY;
+        s2 = col + 2 < kv_valid ? s2 : -INFINITY;
+        s3 = col + 3 < kv_valid ? s3 : -INFINITY;
+      }
       m0 = max3(m0, s0, s1);
       m1 = max3(m1, s2, s3);
       const float p0 = fast_exp2(fmaf(s0, c, -mc)), p1 = fast_exp2(fmaf(s1, c, -mc));
@@ -121,7 +124,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tma_load_3d(sQ, &tmQ, q_full, head * AT_HD, q0, batch);
       for (int j = 0; j < n_kv; ++j) {
         const int st = j % AT_STAGES;
-        mbar_wait(&kv_empty[st], ((j / AT_STAGES) & 1) ^ 1);
+        mbar_wait_sleep(&kv_empty[st], ((j / AT_STAGES) & 1) ^ 1);
         mbar_arrive_expect_tx(&kv_full[st], 2 * a.kv_rows * AT_HD * 2);
         tma_load_3d(sKV + st * 2 * AT_KV_BYTES, &tmK, &kv_full[st], head * AT_HD, j * AT_BKV, batch);
         tma_load_3d(sKV + st * 2 * AT_KV_BYTES + AT_KV_BYTES, &tmV, &kv_full[st], head * AT_HD, j * AT_BKV, batch);
@@ -135,7 +138,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       // S_j = Q K_j^T into S buffer (j & 1); issued two blocks ahead of the softmax
       auto issue_qk = [&](int j) {
         const int st = j % AT_STAGES;
-        mbar_wait(&kv_full[st], (j / AT_STAGES) & 1);
+        mbar_wait_sleep(&kv_full[st], (j / AT_STAGES) & 1);
         tcgen05_fence_after();
         const uint64_t kdesc = umma_desc_sw128(smem_u32(sKV + st * 2 * AT_KV_BYTES), 16, 1024);
 #pragma unroll
@@ -148,7 +151,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if (n_kv > 1) issue_qk(1);
       for (int j = 0; j < n_kv; ++j) {
         const int st = j % AT_STAGES;
-        mbar_wait(&p_ready[j & 1], (j >> 1) & 1);   // P_j in smem, S_j consumed, O rescaled if needed
+        mbar_wait_sleep(&p_ready[j & 1], (j >> 1) & 1);   // P_j in smem, S_j consumed, O rescaled if needed
         tcgen05_fence_after();
         // V stage: 64 key rows x 128 B (64 head-dim values) -> MN-major B operand, 8-row groups 1024 B apart
         const uint64_t vdesc = umma_desc_sw128(smem_u32(sKV + st * 2 * AT_KV_BYTES + AT_KV_BYTES), 1024, 1024);
@@ -192,7 +195,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       // exp pass against the running max of the PREVIOUS blocks; the block max comes out of the same pass
       float l_blk, m_blk;
-      softmax_pass(tS, prow, rx, c, m_run * c, kv_valid, l_blk, m_blk);
+      if (kv_valid >= AT_BKV) softmax_pass<false>(tS, prow, rx, c, m_run * c, kv_valid, l_blk, m_blk);
+      else softmax_pass<true>(tS, prow, rx, c, m_run * c, kv_valid, l_blk, m_blk);
       const bool need = (m_blk - m_run) * c > 8.0f;    // exponent headroom exceeded somewhere in this row
       if (__any_sync(0xffffffffu, need)) {
         // rare: raise the reference max, rescale O and l, redo the block's exponentials
@@ -214,7 +218,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           tmem_wait_st();
         }
         m_run = m_new;
-        softmax_pass(tS, prow, rx, c, m_run * c, kv_valid, l_blk, m_blk);
+        softmax_pass<true>(tS, prow, rx, c, m_run * c, kv_valid, l_blk, m_blk);
       }
       l_run += l_blk;
       fence_proxy_async_smem();       // generic-proxy smem writes -> visible to the tensor core (async proxy)
