@@ -15,17 +15,23 @@
 namespace desta {
 
 namespace g2 {
-constexpr int BM = 128, BN = 256, BNH = 128, BK = 64, STAGES = 5, UMMA_K = 16;
+constexpr int BM = 128, BN = 256, BNH = 128, BK = 64, UMMA_K = 16;
 constexpr int A_BYTES = BM * BK * 2, B_BYTES = BNH * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;   // 32 KB
-constexpr int STAGING_PER_WARP = 2 * 2048;   // two 32x32 bf16 boxes per epilogue warp
 constexpr int EPI_WARP0 = 4, EPI_WARPS = 8, THREADS = 384;
-constexpr int SMEM = STAGES * STAGE_BYTES + EPI_WARPS * STAGING_PER_WARP + 1024 + 256 + EPI_WARPS * 512;
+// two epilogue flavours: bf16 outputs (two 2 KB boxes per warp, 5 pipeline stages) and fp32 outputs with optional
+// fp32 residual (two 4 KB boxes per warp, loaded AND stored by TMA; 4 pipeline stages)
+constexpr int EPI_BF16 = 0, EPI_F32 = 1;
+__host__ __device__ constexpr int stages_of(int mode) { return mode == EPI_BF16 ? 5 : 4; }
+__host__ __device__ constexpr int staging_of(int mode) { return mode == EPI_BF16 ? 2 * 2048 : 2 * 4096; }
+constexpr int BAR_BYTES = 512;
+__host__ __device__ constexpr int smem_of(int mode) { return stages_of(mode) * STAGE_BYTES + EPI_WARPS * staging_of(mode) + 1024 + BAR_BYTES + EPI_WARPS * 512; }
 }  // namespace g2
 
 struct Gemm2Args {
   int M, N, K;
   float* out_f32; int ld_f32;
-  int has_bf16;            // bf16 output through tmC
+  __nv_bfloat16* out_bf16; int ld_bf16;   // EPI_F32 only: optional direct bf16 copy (tap hand-off)
+  int has_bf16;            // EPI_BF16: bf16 output through tmC
   const float* bias;
   const float* resid; int ld_resid;
   const float* pos; int pos_rows;
@@ -79,15 +85,24 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* s
                ::"l"(m), "r"(smem_u32(src)), "r"(c0), "r"(c1)
                : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_plain(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2::THREADS, 1)
 gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                         const __grid_constant__ CUtensorMap tmC, const Gemm2Args g) {
+                         const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const Gemm2Args g) {
   using namespace g2;
+  constexpr int STAGES = stages_of(MODE);
+  constexpr int STAGING_PER_WARP = staging_of(MODE);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* staging = smem + STAGES * STAGE_BYTES;
@@ -96,8 +111,9 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   uint64_t* empty = bars + STAGES;              // [STAGES] per CTA, arrived by the leader's multicast commit
   uint64_t* acc_full = bars + 2 * STAGES;       // [2] per CTA (multicast commit)
   uint64_t* acc_empty = bars + 2 * STAGES + 2;  // [2] used in the leader: epilogue warps of both CTAs
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-  float* bias_all = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [EPI_WARPS][128]
+  uint64_t* rbar = bars + 2 * STAGES + 4;       // [EPI_WARPS][2] residual boxes landed (EPI_F32)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rbar + 2 * EPI_WARPS);
+  float* bias_all = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + BAR_BYTES);   // [EPI_WARPS][128]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -110,11 +126,13 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    if (g.has_bf16) tma_prefetch_desc(&tmC);
+    tma_prefetch_desc(&tmC);
+    if (MODE == EPI_F32 && g.resid) tma_prefetch_desc(&tmR);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 2); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 2 * EPI_WARPS); }
+    for (int i = 0; i < 2 * EPI_WARPS; ++i) mbar_init(&rbar[i], 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -171,18 +189,25 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       }
     }
   } else if (warp >= EPI_WARP0) {
+    const int ew = warp - EPI_WARP0;
     const int q = warp & 3;
-    const int half = (warp - EPI_WARP0) >> 2;
-    uint8_t* stg = staging + (warp - EPI_WARP0) * STAGING_PER_WARP;
+    const int half = ew >> 2;
+    uint8_t* stg = staging + ew * STAGING_PER_WARP;
+    uint64_t* my_rbar = rbar + 2 * ew;
     int local = 0;
-    int nstore = 0;
+    uint32_t nchunk = 0;           // staged boxes issued so far by this warp (buffer = nchunk & 1)
+    const bool use_resid = (MODE == EPI_F32) && g.resid != nullptr;
     for (int tile = pair; tile < num_tiles; tile += n_pairs, ++local) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
       const int as = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
-      float* bias_s = bias_all + (warp - EPI_WARP0) * 128;
+      const int row0 = m_blk * 2 * BM + (int)rank * BM + q * 32;
+      const int row = row0 + lane;
+      const bool row_ok = row < g.M;
+      const int colbase = n_blk * BN + half * 128;
+      float* bias_s = bias_all + ew * 128;
       if (g.bias) {       // this warp's 128 bias values, fetched while the MMAs of the tile are still running
-        const int cb = n_blk * BN + half * 128 + lane * 4;
+        const int cb = colbase + lane * 4;
         float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (cb + 3 < g.N) b4 = __ldg(reinterpret_cast<const float4*>(g.bias + cb));
         else {
@@ -194,11 +219,14 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         reinterpret_cast<float4*>(bias_s)[lane] = b4;
         __syncwarp();
       }
+      if (use_resid && lane == 0 && colbase < g.N && row0 < g.M) {
+        // residual box of chunk 0 (the buffer's previous store was issued >= 2 chunks ago)
+        bulk_wait_read<1>();
+        mbar_arrive_expect_tx(&my_rbar[nchunk & 1], 4096);
+        tma_load_2d_plain(stg + (nchunk & 1) * 4096, &tmR, &my_rbar[nchunk & 1], colbase, row0);
+      }
       mbar_wait_sleep(&acc_full[as], acc_phase);
       tcgen05_fence_after();
-      const int row0 = m_blk * 2 * BM + (int)rank * BM + q * 32;
-      const int row = row0 + lane;
-      const bool row_ok = row < g.M;
       const uint32_t taddr0 = tmem_base + as * BN + half * 128 + ((uint32_t)(q * 32) << 16);
       const float* pos_row = g.pos ? g.pos + (size_t)(row % g.pos_rows) * g.N : nullptr;
 #pragma unroll 1
@@ -212,8 +240,8 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(&acc_empty[as], 0);
         }
-        const int col0 = n_blk * BN + half * 128 + c * 32;
-        if (col0 >= g.N) continue;
+        const int col0 = colbase + c * 32;
+        if (col0 >= g.N || row0 >= g.M) continue;     // warp-uniform
         const bool full_cols = (col0 + 32 <= g.N);
         float f[32];
 #pragma unroll
@@ -230,46 +258,21 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           for (int j = 0; j < 32; ++j) if (col0 + j < g.scale_cols) f[j] *= g.scale;
         }
         if (g.gelu) gelu_erf_x32(f);
-        if (row_ok) {
-          if (pos_row) {
-            if (full_cols) {
+        if (pos_row && row_ok) {
+          if (full_cols) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(pos_row + col0 + j));
-                f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) if (col0 + j < g.N) f[j] += __ldg(pos_row + col0 + j);
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(pos_row + col0 + j));
+              f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
             }
-          }
-          if (g.resid) {
-            const float* r = g.resid + (size_t)row * g.ld_resid + col0;
-            if (full_cols) {
+          } else {
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 b = *reinterpret_cast<const float4*>(r + j);
-                f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) if (col0 + j < g.N) f[j] += r[j];
-            }
-          }
-          if (g.out_f32) {
-            float* o = g.out_f32 + (size_t)row * g.ld_f32 + col0;
-            if (full_cols) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) if (col0 + j < g.N) o[j] = f[j];
-            }
+            for (int j = 0; j < 32; ++j) if (col0 + j < g.N) f[j] += __ldg(pos_row + col0 + j);
           }
         }
-        if (g.has_bf16) {
+        if (MODE == EPI_BF16) {
           // stage 32 rows x 32 bf16 (64-byte rows, SWIZZLE_64B) and hand the box to the TMA (clips at M / N itself)
-          uint8_t* buf = stg + (nstore & 1) * 2048;
+          uint8_t* buf = stg + (nchunk & 1) * 2048;
           if (lane == 0) bulk_wait_read<1>();          // the store that used this buffer two chunks ago has read it
           __syncwarp();
           uint8_t* rowp = buf + lane * 64;
@@ -284,14 +287,64 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            if (row0 < g.M) tma_store_2d(&tmC, buf, col0, row0);
+            tma_store_2d(&tmC, buf, col0, row0);
             bulk_commit();
           }
-          ++nstore;
+          ++nchunk;
+        } else {
+          // fp32: 32 rows x 32 floats (128-byte rows, SWIZZLE_128B).  The residual box was TMA-loaded into this very
+          // buffer; add in place, then TMA-store.  The next chunk's residual is requested before the math.
+          uint8_t* buf = stg + (nchunk & 1) * 4096;
+          const bool more = (c < 3) && (col0 + 32 < g.N);
+          if (use_resid) {
+            if (lane == 0 && more) {
+              bulk_wait_read<0>();                      // the other buffer's store (previous chunk) has been read
+              mbar_arrive_expect_tx(&my_rbar[(nchunk + 1) & 1], 4096);
+              tma_load_2d_plain(stg + ((nchunk + 1) & 1) * 4096, &tmR, &my_rbar[(nchunk + 1) & 1], col0 + 32, row0);
+            }
+            mbar_wait(&my_rbar[nchunk & 1], (nchunk >> 1) & 1);
+          } else {
+            if (lane == 0) bulk_wait_read<1>();
+            __syncwarp();
+          }
+          float4* rowp = reinterpret_cast<float4*>(buf + lane * 128);
+          const int sw = lane & 7;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 o4 = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            if (use_resid) {
+              const float4 r4 = rowp[j ^ sw];
+              o4.x += r4.x; o4.y += r4.y; o4.z += r4.z; o4.w += r4.w;
+            }
+            rowp[j ^ sw] = o4;
+            f[4 * j] = o4.x; f[4 * j + 1] = o4.y; f[4 * j + 2] = o4.z; f[4 * j + 3] = o4.w;
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmC, buf, col0, row0);
+            bulk_commit();
+          }
+          ++nchunk;
+          if (g.out_bf16 && row_ok) {                  // tap hand-off: direct bf16 copy (4 of 32 fc2 launches)
+            __nv_bfloat16* o = g.out_bf16 + (size_t)row * g.ld_bf16 + col0;
+            if (full_cols) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                uint4 u;
+                u.x = pack_bf16(f[j], f[j + 1]); u.y = pack_bf16(f[j + 2], f[j + 3]);
+                u.z = pack_bf16(f[j + 4], f[j + 5]); u.w = pack_bf16(f[j + 6], f[j + 7]);
+                *reinterpret_cast<uint4*>(o + j) = u;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (col0 + j < g.N) o[j] = __float2bfloat16_rn(f[j]);
+            }
+          }
         }
       }
     }
-    if (g.has_bf16 && lane == 0) bulk_wait_all();
+    if (lane == 0) bulk_wait_all();
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -304,38 +357,53 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 
 int num_sms();
 
+static int make_f32_box_map(CUtensorMap* m, const float* base, int M, int N, int ld) {
+  uint64_t dims[2] = {(uint64_t)N, (uint64_t)M};
+  uint64_t strides[2] = {0, (uint64_t)ld * 4};
+  uint32_t box[2] = {32, 32};
+  return make_tmap(m, base, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
 int launch_gemm_2cta(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const desta_gemm_epilogue* ep,
                      cudaStream_t stream) {
   using namespace g2;
-  CUtensorMap tmA, tmB, tmC;
+  CUtensorMap tmA, tmB, tmC, tmR;
   if (make_tmap_2d_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM, BK)) return DESTA_ERR_CUDA;
   if (make_tmap_2d_bf16(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, BNH, BK)) return DESTA_ERR_CUDA;
-  if (ep->out_bf16) {
+  const int mode = ep->out_f32 ? EPI_F32 : EPI_BF16;
+  Gemm2Args g;
+  g.M = M; g.N = N; g.K = K;
+  g.out_f32 = ep->out_f32; g.ld_f32 = ep->ld_f32;
+  g.out_bf16 = nullptr; g.ld_bf16 = 0; g.has_bf16 = 0;
+  if (mode == EPI_BF16) {
     uint64_t dims[2] = {(uint64_t)N, (uint64_t)M};
     uint64_t strides[2] = {0, (uint64_t)ep->ld_bf16 * 2};
     uint32_t box[2] = {32, 32};
     if (make_tmap(&tmC, ep->out_bf16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B))
       return DESTA_ERR_CUDA;
+    tmR = tmC;
+    g.has_bf16 = 1;
   } else {
-    tmC = tmA;
+    if (make_f32_box_map(&tmC, ep->out_f32, M, N, ep->ld_f32)) return DESTA_ERR_CUDA;
+    if (ep->resid) { if (make_f32_box_map(&tmR, ep->resid, M, N, ep->ld_resid)) return DESTA_ERR_CUDA; }
+    else tmR = tmC;
+    g.out_bf16 = (__nv_bfloat16*)ep->out_bf16; g.ld_bf16 = ep->ld_bf16;
   }
-  Gemm2Args g;
-  g.M = M; g.N = N; g.K = K;
-  g.out_f32 = ep->out_f32; g.ld_f32 = ep->ld_f32;
-  g.has_bf16 = ep->out_bf16 != nullptr;
   g.bias = ep->bias; g.resid = ep->resid; g.ld_resid = ep->ld_resid;
   g.pos = ep->pos; g.pos_rows = ep->pos_rows > 0 ? ep->pos_rows : 1;
   g.scale = ep->scale; g.scale_cols = ep->scale_cols; g.gelu = ep->gelu;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_2cta_kernel<EPI_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_of(EPI_BF16));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_bf16_tn_2cta_kernel<EPI_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_of(EPI_F32));
     if (e != cudaSuccess) { set_error("gemm 2cta smem attribute: %s", cudaGetErrorString(e)); return DESTA_ERR_CUDA; }
     attr_set = true;
   }
   const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);
   int pairs = num_sms() / 2;
   if (tiles < pairs) pairs = tiles;
-  gemm_bf16_tn_2cta_kernel<<<2 * pairs, THREADS, SMEM, stream>>>(tmA, tmB, tmC, g);
+  if (mode == EPI_BF16) gemm_bf16_tn_2cta_kernel<EPI_BF16><<<2 * pairs, THREADS, smem_of(EPI_BF16), stream>>>(tmA, tmB, tmC, tmR, g);
+  else gemm_bf16_tn_2cta_kernel<EPI_F32><<<2 * pairs, THREADS, smem_of(EPI_F32), stream>>>(tmA, tmB, tmC, tmR, g);
   return check_launch("gemm_bf16_tn_2cta_kernel");
 }
 

@@ -2,9 +2,7 @@
 // Replaces the gathers + N-iteration Python scatter loop of DeSTA25AudioModel._prepare_inputs_for_llm
 // (ref: desta/models/modeling_desta25.py:940-1050; embed_tokens gathers :975-982,1009; scatter loop :1014-1045).
 //
-// Pass 1 (tiny): row_map[b*S+s] = -1 (text row), then descs applied IN ORDER by one thread block so that later clips
-//   overwrite earlier ones exactly like the reference's loop:  code = (clip << 1 | 0) * ... see encode below.
-// Pass 2 (HBM-bound): one warp per output row; 16-byte vector loads from the embedding table / audio features,
+// HBM-bound: one warp per output row; 16-byte vector loads from the embedding table / audio features,
 //   fp32 -> bf16 round-to-nearest-even for audio rows (the implicit cast of the slice assignment at :1040-1041),
 //   transcript / text rows copied bit-for-bit.
 #include "common.cuh"
@@ -12,51 +10,49 @@
 
 namespace desta {
 
-// row_map encoding: -1 = text row (gather table[input_ids]); >= 0: (clip << 16 | j) with j < Q -> audio row j of clip,
-// j >= Q -> transcript token j-Q of clip.  (clips < 32768, Q + T_i < 65536: checked on the host.)
-__global__ void splice_map_kernel(const desta_splice_desc* __restrict__ descs, int n_desc, int Q, int S, int total,
-                                  int32_t* __restrict__ row_map) {
-  for (int i = threadIdx.x; i < total; i += blockDim.x) row_map[i] = -1;
-  __syncthreads();
-  for (int c = 0; c < n_desc; ++c) {       // in loop order: later clips win
-    const desta_splice_desc d = descs[c];
-    const int len = Q + d.n_trans;
-    for (int j = threadIdx.x; j < len; j += blockDim.x) row_map[d.prompt * S + d.start + j] = (c << 16) | j;
-    __syncthreads();
-  }
-}
-
+// Each warp owns output rows; the 32 lanes scan the clip descriptors (staged in shared memory) to find the LAST clip
+// whose span [start, start + Q + T_i) covers the row - "later clips win", exactly the reference's loop order - so no
+// row-map pass and no scratch buffer are needed: ONE launch.
 template <bool FEAT_F32>
 __global__ void __launch_bounds__(256)
 splice_rows_kernel(const int64_t* __restrict__ input_ids, const uint4* __restrict__ table, int64_t vocab,
-                   const desta_splice_desc* __restrict__ descs, const int64_t* __restrict__ trans_ids,
-                   const void* __restrict__ feats, int Q, int d8, const int32_t* __restrict__ row_map, int rows,
-                   uint4* __restrict__ out) {
+                   const desta_splice_desc* __restrict__ descs, int n_desc, const int64_t* __restrict__ trans_ids,
+                   const void* __restrict__ feats, int Q, int S, int d8, int rows, uint4* __restrict__ out) {
+  extern __shared__ desta_splice_desc s_desc[];
+  for (int i = threadIdx.x; i < n_desc; i += blockDim.x) s_desc[i] = descs[i];
+  __syncthreads();
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < rows; row += gridDim.x * warps_per_block) {
-    const int code = row_map[row];
+    const int b = row / S, pos = row - b * S;
+    int hit = -1;
+    for (int c = lane; c < n_desc; c += 32) {
+      const desta_splice_desc dd = s_desc[c];
+      if (dd.prompt == b && pos >= dd.start && pos < dd.start + Q + dd.n_trans) hit = c;   // ascending c: last one wins
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) hit = max(hit, __shfl_xor_sync(0xffffffffu, hit, o));
     uint4* o = out + (size_t)row * d8;
     const uint4* src = nullptr;
-    if (code < 0) {
+    if (hit < 0) {
       int64_t id = input_ids[row];
       id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
       src = table + (size_t)id * d8;
     } else {
-      const int c = code >> 16, j = code & 0xFFFF;
+      const int j = pos - s_desc[hit].start;
       if (j >= Q) {
-        int64_t id = trans_ids[descs[c].trans_off + (j - Q)];
+        int64_t id = trans_ids[s_desc[hit].trans_off + (j - Q)];
         id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
         src = table + (size_t)id * d8;
       } else if (!FEAT_F32) {
-        src = reinterpret_cast<const uint4*>(feats) + ((size_t)c * Q + j) * d8;
+        src = reinterpret_cast<const uint4*>(feats) + ((size_t)hit * Q + j) * d8;
       } else {
-        const float4* f = reinterpret_cast<const float4*>(feats) + ((size_t)c * Q + j) * d8 * 2;
+        const float4* f = reinterpret_cast<const float4*>(feats) + ((size_t)hit * Q + j) * d8 * 2;
         for (int i = lane; i < d8; i += 32) {
-          const float4 a = f[2 * i], b = f[2 * i + 1];
+          const float4 a = f[2 * i], bb = f[2 * i + 1];
           uint4 u;
           u.x = pack_bf16(a.x, a.y); u.y = pack_bf16(a.z, a.w);
-          u.z = pack_bf16(b.x, b.y); u.w = pack_bf16(b.z, b.w);
+          u.z = pack_bf16(bb.x, bb.y); u.w = pack_bf16(bb.z, bb.w);
           o[i] = u;
         }
         continue;
@@ -94,7 +90,7 @@ extern "C" int desta_splice(const int64_t* input_ids, const void* table, int64_t
                             const desta_splice_desc* descs_host, int n_desc, const int64_t* trans_ids,
                             const void* audio_feats, int feat_dtype, int Q, void* out, int B, int S, int d,
                             int32_t* row_map, void* stream) {
-  if (!input_ids || !table || !out || !row_map) { set_error("desta_splice: null pointer"); return DESTA_ERR_ARG; }
+  if (!input_ids || !table || !out) { set_error("desta_splice: null pointer"); return DESTA_ERR_ARG; }
   if (B <= 0 || S <= 0) return DESTA_OK;
   if (d % 8) { set_error("desta_splice: hidden size must be a multiple of 8 (got %d)", d); return DESTA_ERR_ARG; }
   if (n_desc > 0 && (!descs_dev || !descs_host || !audio_feats)) { set_error("desta_splice: null descs/feats"); return DESTA_ERR_ARG; }
@@ -111,16 +107,22 @@ extern "C" int desta_splice(const int64_t* input_ids, const void* table, int64_t
   }
   cudaStream_t s = (cudaStream_t)stream;
   const int rows = B * S;
-  splice_map_kernel<<<1, 1024, 0, s>>>(descs_dev, n_desc, Q, S, rows, row_map);
+  (void)row_map;
   int grid = (rows + 7) / 8;
   const int cap = num_sms() * 8;
   if (grid > cap) grid = cap;
+  const size_t sm = (size_t)(n_desc > 0 ? n_desc : 1) * sizeof(desta_splice_desc);
+  if (sm > 200 * 1024) { set_error("desta_splice: too many clips for one launch (%d)", n_desc); return DESTA_ERR_ARG; }
+  if (sm > 48 * 1024) {
+    cudaFuncSetAttribute(splice_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    cudaFuncSetAttribute(splice_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  }
   if (feat_dtype == 0)
-    splice_rows_kernel<true><<<grid, 256, 0, s>>>(input_ids, (const uint4*)table, vocab, descs_dev, trans_ids, audio_feats, Q,
-                                                  d / 8, row_map, rows, (uint4*)out);
+    splice_rows_kernel<true><<<grid, 256, sm, s>>>(input_ids, (const uint4*)table, vocab, descs_dev, n_desc, trans_ids, audio_feats, Q,
+                                                   S, d / 8, rows, (uint4*)out);
   else
-    splice_rows_kernel<false><<<grid, 256, 0, s>>>(input_ids, (const uint4*)table, vocab, descs_dev, trans_ids, audio_feats, Q,
-                                                   d / 8, row_map, rows, (uint4*)out);
+    splice_rows_kernel<false><<<grid, 256, sm, s>>>(input_ids, (const uint4*)table, vocab, descs_dev, n_desc, trans_ids, audio_feats, Q,
+                                                    S, d / 8, rows, (uint4*)out);
   return check_launch("splice kernels");
 }
 

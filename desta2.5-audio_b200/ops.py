@@ -270,7 +270,6 @@ def splice(input_ids, table, descs, trans_ids, feats, Q, out=None):
     dev = torch.frombuffer(bytearray(bytes(host)), dtype=torch.int32).to(input_ids.device, non_blocking=False)
     if out is None:
         out = torch.empty(B, S, d, dtype=torch.bfloat16, device=input_ids.device)
-    row_map = torch.empty(B * S, dtype=torch.int32, device=input_ids.device)
     feat_dtype = 0
     if feats is not None:
         assert feats.is_contiguous() and feats.shape[-1] == d
@@ -279,7 +278,7 @@ def splice(input_ids, table, descs, trans_ids, feats, Q, out=None):
     fb = 4 if feat_dtype == 0 else 2
     n_audio_rows = n * Q
     nbytes = B * S * 8 + (B * S - n_audio_rows) * d * 2 + n_audio_rows * d * fb + B * S * d * 2
-    with _op("splice", 2, nbytes, "byte"):
+    with _op("splice", 1, nbytes, "byte"):
         check(lib().desta_splice(_p(input_ids.contiguous()), _p(table), V, _p(dev), host, n, _p(trans_ids), _p(feats), feat_dtype,
-                                 Q, _p(out), B, S, d, _p(row_map), _stream()), "desta_splice")
+                                 Q, _p(out), B, S, d, None, _stream()), "desta_splice")
     return out

@@ -106,7 +106,7 @@ typedef struct desta_splice_desc {
   int32_t n_trans;     /* T_i */
   int32_t trans_off;   /* offset into trans_ids */
 } desta_splice_desc;
-/* row_map [B*S] int32 scratch (device).  feat_dtype: 0 = fp32, 1 = bf16.  Returns DESTA_ERR_SHAPE if a span
+/* row_map: unused (may be NULL; kept for ABI stability).  feat_dtype: 0 = fp32, 1 = bf16.  Returns DESTA_ERR_SHAPE if a span
  * leaves [0,S) (the reference raises at :1041); descs are validated on the host copy `descs_host`. */
 int desta_splice(const int64_t* input_ids, const void* table, int64_t vocab, const desta_splice_desc* descs_dev,
                  const desta_splice_desc* descs_host, int n_desc, const int64_t* trans_ids, const void* audio_feats,
