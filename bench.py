@@ -187,14 +187,39 @@ def run_ours(args):
     trans = [torch.zeros(1, 0, dtype=torch.int64) for _ in range(n)]     # empty transcripts (simple_dataset.py:668)
     out_host = torch.empty(n, SEQ_LEN, w["d_llm"], dtype=torch.bfloat16).pin_memory()
 
+    train = args.mode == "train"
+    bucket = None
+    if train:
+        from desta_b200.dist import GradBucket
+        perception.train()
+        grad_emb = (0.01 * torch.randn(n, SEQ_LEN, w["d_llm"], device=dev, generator=g)).to(torch.bfloat16)
+        if world > 1:
+            bucket = GradBucket(list(perception.connector.parameters()))
+
+    def train_step(ii, wv):
+        # frozen encoder forward + Q-Former forward/backward; the LLM's gradient w.r.t. inputs_embeds is synthetic
+        for prm in perception.connector.parameters():
+            prm.grad = None
+        emb = prepare_inputs_for_llm(table, perception, ii, None, wv, trans, positions)
+        emb.backward(grad_emb)
+        if bucket is not None:
+            bucket.allreduce()      # same exchange as the reference's DDP: one averaged all-reduce of connector grads
+        return emb
+
     def step_resident():
+        if train:
+            return train_step(ids_dev, wave_dev)
         with torch.no_grad():
             return prepare_inputs_for_llm(table, perception, ids_dev, None, wave_dev, trans, positions)
 
     def step_e2e():
+        wv = wave_host.to(dev, non_blocking=True)
+        ii = ids_host.to(dev, non_blocking=True)
+        if train:
+            emb = train_step(ii, wv)
+            out_host.copy_(emb.detach(), non_blocking=True)
+            return emb
         with torch.no_grad():
-            wv = wave_host.to(dev, non_blocking=True)
-            ii = ids_host.to(dev, non_blocking=True)
             emb = prepare_inputs_for_llm(table, perception, ii, None, wv, trans, positions)
             out_host.copy_(emb, non_blocking=True)
         return emb
@@ -241,27 +266,34 @@ def run_ours(args):
     fam = {k: {"ms": round(v["ms"], 3), "share": round(v["ms"] / total_ms, 4), "calls": v["calls"],
                "achieved": round(v["work"] / (v["ms"] * 1e-3) / (1e12 if v["unit"] == "flop" else 1e9), 1),
                "unit": "TFLOP/s" if v["unit"] == "flop" else "GB/s"} for k, v in prof.items()}
-    gm = prof["gemm"]
+    gm = {"work": sum(prof[k]["work"] for k in ("gemm", "gemm_wgrad") if k in prof),
+          "ms": sum(prof[k]["ms"] for k in ("gemm", "gemm_wgrad") if k in prof)}
     gemm_tflops = gm["work"] / (gm["ms"] * 1e-3) / 1e12
     step_s = ms * 1e-3 / args.steps
     value = 30.0 * n * world / step_s
     e2e_value = 30.0 * n * world / (ms_e2e * 1e-3 / args.steps)
     flops_clip = fwd_flops_per_clip(w)
+    if train:   # + connector backward = 2 x forward minus the K/V data-gradient (taps need no grad), SURVEY.md §8d
+        d_, T_, K_, L_ = w["d_model"], 1500, len(w["tap_layers"]), w["qf_layers"]
+        kv = K_ * L_ * 2 * T_ * d_ * 2 * d_
+        enc_only = fwd_flops_per_clip(dict(w, qf_layers=0)) - 2 * w["prompt_size"] * d_ * w["d_llm"]
+        con = flops_clip - enc_only
+        flops_clip = flops_clip + 2 * con - kv
     line = {
-        "metric": "audio-sec/sec waveform->LLM embeds", "value": value, "unit": "audio-s/s", "n_gpus": world,
+        "metric": "audio-sec/sec waveform->LLM embeds" if not train else "audio-sec/sec training step (frozen encoder fwd + Q-Former fwd/bwd)", "value": value, "unit": "audio-s/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": step_s * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"{args.workload}: whisper-large-v3 encoder + Qformer6L -> Llama-3.1-8B embeds, 30 s clips",
-                   "clips_per_gpu": n, "seq_len": SEQ_LEN, "l2": "working set >> 126 MB L2 (no flush needed)",
+                   "mode": args.mode, "clips_per_gpu": n, "seq_len": SEQ_LEN, "l2": "working set >> 126 MB L2 (no flush needed)",
                    "parallelism": f"clips sharded over {world} GPU(s), no data-path collective"},
         "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": wave_host.numel() * 4 + ids_host.numel() * 8,
                 "d2h_bytes_per_step": out_host.numel() * 2, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "gemm_bf16_tn_kernel (all GEMM launches of one step)",
+        "roofline": {"bound": "tensor", "kernel": "gemm_bf16_tn_2cta_kernel (all GEMM launches of one step)",
                      "achieved": round(gemm_tflops, 1), "peak": tf_sust, "unit": "TFLOP/s",
                      "frac": round(gemm_tflops / tf_sust, 4), "traffic": None, "peak_kind": f"{peak_kind} sustained bf16",
-                     "share_of_step": fam["gemm"]["share"]},
+                     "share_of_step": round(gm["ms"] / total_ms, 4)},
         "step_tensor_frac": round(flops_clip * n / step_s / 1e12 / tf_sust, 4),
         "kernels": fam,
     }
@@ -283,6 +315,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="large_v3_llama", choices=sorted(WORKLOADS))
     ap.add_argument("--clips", type=int, default=64, help="clips per GPU per step")
+    ap.add_argument("--mode", default="forward", choices=["forward", "train"],
+                    help="forward = BASELINE.json configs[1] (default); train = configs[4] step (connector fwd+bwd, grad all-reduce)")
     ap.add_argument("--cpu-clips", type=int, default=2, help="clips in the bounded cpu_baseline sample")
     ap.add_argument("--ref-clips", type=int, default=2, help="clips per step of the --impl reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
