@@ -4,10 +4,14 @@
 // as called at desta/models/modeling_desta25.py:1570 and desta/trainer/data/simple_dataset.py:239-243.
 //
 // Kernel 1 (logmel_fft_kernel): one CTA = 32 consecutive frames of one clip (8 warps x 4 frames).  The 5360 samples the
-//   tile touches are staged once in shared memory with coalesced loads (frames overlap 60 %), each warp runs four
-//   400-point real FFTs at a time in fp32 as a 200-point complex FFT (radix 8 x 5 x 5, in-place in a per-warp scratch)
-//   plus the real-input post-pass, applies the sparse triangular mel filters, takes log10 and stores the raw tile
-//   [mel][32 frames] with 128-byte coalesced rows; the clip maximum is reduced warp -> block -> one atomicMax.
+//   tile touches are staged once in shared memory with coalesced loads (frames overlap 60 %; 16 floats of padding per
+//   hop keep the four frames of a warp on different banks).  Each 400-point real FFT runs as a 200-point complex FFT
+//   held ENTIRELY IN REGISTERS by 8 threads: thread t owns z[8m + t] (25 values), does the 25-point DFT (radix 5 x 5,
+//   compile-time twiddles) in registers, and the radix-8 step across the 8 threads is three shuffle butterfly stages
+//   (decimation in frequency, outputs land bit-reversed over the lanes).  The real-input post-pass fetches the mirror
+//   bin with one more shuffle, the power spectrum goes through a small conflict-free shared buffer to the sparse
+//   triangular mel filters (one lane = one mel bin for the warp's 4 frames -> 16-byte stores), log10, and the clip
+//   maximum is reduced warp -> block -> one atomicMax.
 // Kernel 2 (logmel_finish_kernel): max(L, clip_max - 8), (x + 4) / 4 in place (reads that hit L2 right after kernel 1),
 //   optional bf16 time-major copy [N, 3000, n_mels] that feeds the conv-stem GEMM.
 #include <math.h>
@@ -118,24 +122,40 @@ __device__ __forceinline__ float unorder_f32(unsigned u) {
   return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
 }
 
-__global__ void __launch_bounds__(MEL_WARPS * 32)
+constexpr int MEL_HOP_PAD = MEL_HOP + 16;                       // padded hop in the staged wave (bank spreading)
+constexpr int MEL_WAVE_PAD = MEL_WAVE + 16 * (MEL_WAVE / MEL_HOP + 1);
+constexpr int MEL_PSTRIDE = 216;                                // per-frame stride of the power buffer (conflict-free)
+
+// W25^(b c) = exp(-2 pi i b c / 25): compile-time twiddles of the in-register 25-point DFT
+__device__ constexpr float W25C[5][5] = {
+    {1.000000000f, 1.000000000f, 1.000000000f, 1.000000000f, 1.000000000f},
+    {1.000000000f, 0.968583161f, 0.876306680f, 0.728968627f, 0.535826795f},
+    {1.000000000f, 0.876306680f, 0.535826795f, 0.062790520f, -0.425779292f},
+    {1.000000000f, 0.728968627f, 0.062790520f, -0.637423990f, -0.992114701f},
+    {1.000000000f, 0.535826795f, -0.425779292f, -0.992114701f, -0.637423990f}};
+__device__ constexpr float W25S[5][5] = {
+    {0.f, 0.f, 0.f, 0.f, 0.f},
+    {0.f, -0.248689887f, -0.481753674f, -0.684547106f, -0.844327926f},
+    {0.f, -0.481753674f, -0.844327926f, -0.998026728f, -0.904827052f},
+    {0.f, -0.684547106f, -0.998026728f, -0.770513243f, -0.125333234f},
+    {0.f, -0.844327926f, -0.904827052f, -0.125333234f, 0.770513243f}};
+
+__global__ void __launch_bounds__(MEL_WARPS * 32, 2)
 logmel_fft_kernel(const float* __restrict__ wave, const int32_t* __restrict__ n_valid, const float* __restrict__ plan,
                   float* __restrict__ out, unsigned* __restrict__ clip_max) {
   extern __shared__ __align__(16) float sm[];
   const int* hdr = reinterpret_cast<const int*>(plan);
   const int n_mels = hdr[0], max_w = hdr[1];
   const int tab_words = (int)plan_words(n_mels, max_w) - PLAN_HDR;
-  float* s_tab = sm;                                 // plan tables
-  float* s_wave = s_tab + ((tab_words + 3) & ~3);    // [MEL_WAVE]
-  float* s_scr = s_wave + MEL_WAVE;                  // [warps][4 frames][400]
-  float* s_tile = s_scr + MEL_WARPS * MEL_FPW * 400; // [n_mels][33]
+  float* s_tab = sm;                                            // plan tables
+  float* s_wave = s_tab + ((tab_words + 3) & ~3);               // [MEL_WAVE_PAD] padded staged samples
+  float* s_pow = s_wave + MEL_WAVE_PAD;                         // [warps][4 frames][MEL_PSTRIDE] power spectra
   __shared__ float s_wmax[MEL_WARPS];
 
   const float* s_hann = s_tab;
   const float2* s_tw200 = reinterpret_cast<const float2*>(s_tab + 400);
   const float2* s_tw400 = reinterpret_cast<const float2*>(s_tab + 800);
-  const int* s_lut = reinterpret_cast<const int*>(s_tab + 1202);
-  const int* s_lo = s_lut + 201;
+  const int* s_lo = reinterpret_cast<const int*>(s_tab + 1202) + 201;
   const int* s_cnt = s_lo + n_mels;
   const float* s_w = reinterpret_cast<const float*>(s_cnt + n_mels);
 
@@ -151,107 +171,128 @@ logmel_fft_kernel(const float* __restrict__ wave, const int32_t* __restrict__ n_
       int s = s0 + j;
       if (s < 0) s = -s;                                              // reflect (torch.stft center=True)
       if (s >= DESTA_MEL_SAMPLES) s = 2 * (DESTA_MEL_SAMPLES - 1) - s;
-      s_wave[j] = (s < nv) ? __ldg(w + s) : 0.0f;
+      s_wave[j + 16 * (j / MEL_HOP)] = (s < nv) ? __ldg(w + s) : 0.0f;
     }
   }
   __syncthreads();
 
-  float2* scr = reinterpret_cast<float2*>(s_scr + warp * MEL_FPW * 400);   // 4 frames x 200 complex
-  const int fbase = warp * MEL_FPW;                                         // first local frame of this warp
-  float lmax = -INFINITY;
-
-  // ---- step 1: radix-8 over n1 (inputs z[25 n1 + n2]), twiddle W200^(n2 k1), store Y[k1][n2] ----
-  for (int it = lane; it < MEL_FPW * 25; it += 32) {
-    const int j = it / 25, n2 = it - j * 25;
-    const float* x = s_wave + (fbase + j) * MEL_HOP;
-    float2 a[8];
-#pragma unroll
-    for (int n1 = 0; n1 < 8; ++n1) {
-      const int idx = 50 * n1 + 2 * n2;
-      const float2 xv = *reinterpret_cast<const float2*>(x + idx);
-      const float2 hv = *reinterpret_cast<const float2*>(s_hann + idx);
-      a[n1] = make_float2(xv.x * hv.x, xv.y * hv.y);
-    }
-    dft8(a);
-#pragma unroll
-    for (int k1 = 0; k1 < 8; ++k1) scr[j * 200 + k1 * 25 + n2] = cmul(a[k1], s_tw200[n2 * k1]);
-  }
-  __syncwarp();
-  // ---- step 2a: radix-5 over a (inputs [k1][5a+b]), twiddle W25^(b c), store [k1][5c+b] ----
-  for (int it = lane; it < MEL_FPW * 40; it += 32) {
-    const int j = it / 40, r = it - j * 40, k1 = r / 5, b = r - k1 * 5;
-    float2* p = scr + j * 200 + k1 * 25 + b;
-    float2 x[5];
-#pragma unroll
-    for (int a = 0; a < 5; ++a) x[a] = p[5 * a];
-    dft5(x);
-#pragma unroll
-    for (int c = 0; c < 5; ++c) p[5 * c] = cmul(x[c], s_tw200[8 * b * c]);
-  }
-  __syncwarp();
-  // ---- step 2b: radix-5 over b (inputs [k1][5c+b]) -> Z[k1 + 8(c + 5e)] stored at [k1][5c+e] ----
-  for (int it = lane; it < MEL_FPW * 40; it += 32) {
-    const int j = it / 40, r = it - j * 40, k1 = r / 5, c = r - k1 * 5;
-    float2* p = scr + j * 200 + k1 * 25 + 5 * c;
-    float2 x[5];
-#pragma unroll
-    for (int b = 0; b < 5; ++b) x[b] = p[b];
-    dft5(x);
-#pragma unroll
-    for (int e = 0; e < 5; ++e) p[e] = x[e];
-  }
-  __syncwarp();
-  // ---- real-input post-pass: X[k] = E + T, X[200-k] = conj(E - T); power written back in place via the LUT ----
+  const int f = lane >> 3, t = lane & 7;                 // frame within the warp, thread within the frame's octet
+  const int fl = warp * MEL_FPW + f;                     // local frame
+  const int kap = ((t & 1) << 2) | (t & 2) | (t >> 2);   // bit-reversed octet index: this thread ends up with bins [25 kap, 25 kap + 25)
+  float2 z[25];
+  // ---- load x_t[m] = z[8m + t] = (x[16m + 2t], x[16m + 2t + 1]) * hann ----
   {
-    float* fs = reinterpret_cast<float*>(scr);
-    for (int it = lane; it < MEL_FPW * 101; it += 32) {
-      const int j = it / 101, k = it - j * 101;
-      float* f = fs + j * 400;
-      const int ia = s_lut[k], ib = (k == 0) ? s_lut[0] : s_lut[200 - k];
-      const float2 A = *reinterpret_cast<const float2*>(f + ia);
-      const float2 B = *reinterpret_cast<const float2*>(f + ib);
+    const float* xb = s_wave + fl * MEL_HOP_PAD + 2 * t;
+    const float* hb = s_hann + 2 * t;
+#pragma unroll
+    for (int m = 0; m < 25; ++m) {
+      const float2 xv = *reinterpret_cast<const float2*>(xb + 16 * m + 16 * (m / 10));
+      const float2 hv = *reinterpret_cast<const float2*>(hb + 16 * m);
+      z[m] = make_float2(xv.x * hv.x, xv.y * hv.y);
+    }
+  }
+  // ---- 25-point DFT in registers: m = 5a + b, k1 = c + 5e; result X[k1] in register 5c + e ----
+#pragma unroll
+  for (int b = 0; b < 5; ++b) {
+    float2 v[5] = {z[b], z[5 + b], z[10 + b], z[15 + b], z[20 + b]};
+    dft5(v);
+#pragma unroll
+    for (int c = 0; c < 5; ++c) z[5 * c + b] = (b == 0 || c == 0) ? v[c] : cmul(v[c], make_float2(W25C[b][c], W25S[b][c]));
+  }
+#pragma unroll
+  for (int c = 0; c < 5; ++c) {
+    float2 v[5] = {z[5 * c], z[5 * c + 1], z[5 * c + 2], z[5 * c + 3], z[5 * c + 4]};
+    dft5(v);
+#pragma unroll
+    for (int e = 0; e < 5; ++e) z[5 * c + e] = v[e];
+  }
+  // ---- twiddle W200^(t k1), then radix-8 across the octet: 3 shuffle butterfly stages (DIF) ----
+  {
+    const float r2 = 0.70710678118654752f;
+    // stage-1 twiddle of the upper lanes: W8^(t & 3); stage-2: W4^(t & 1)
+    const int q = t & 3;
+    const float2 w1 = (t & 4) ? (q == 0 ? make_float2(1.f, 0.f) : q == 1 ? make_float2(r2, -r2) : q == 2 ? make_float2(0.f, -1.f) : make_float2(-r2, -r2))
+                              : make_float2(1.f, 0.f);
+    const float2 w2 = ((t & 2) && (t & 1)) ? make_float2(0.f, -1.f) : make_float2(1.f, 0.f);
+    // butterfly as  d = o + sgn * v  (lower lane: v + o, upper lane: o - v), then * w (w = 1 on lower lanes)
+    const float sg4 = (t & 4) ? -1.f : 1.f, sg2 = (t & 2) ? -1.f : 1.f, sg1 = (t & 1) ? -1.f : 1.f;
+#pragma unroll
+    for (int r = 0; r < 25; ++r) {
+      const int k1 = (r / 5) + 5 * (r % 5);
+      float2 v = (k1 == 0) ? z[r] : cmul(z[r], s_tw200[t * k1]);
+      float2 o, d;
+      o.x = __shfl_xor_sync(0xffffffffu, v.x, 4); o.y = __shfl_xor_sync(0xffffffffu, v.y, 4);
+      d = make_float2(fmaf(sg4, v.x, o.x), fmaf(sg4, v.y, o.y));
+      v = cmul(d, w1);
+      o.x = __shfl_xor_sync(0xffffffffu, v.x, 2); o.y = __shfl_xor_sync(0xffffffffu, v.y, 2);
+      d = make_float2(fmaf(sg2, v.x, o.x), fmaf(sg2, v.y, o.y));
+      v = cmul(d, w2);
+      o.x = __shfl_xor_sync(0xffffffffu, v.x, 1); o.y = __shfl_xor_sync(0xffffffffu, v.y, 1);
+      z[r] = make_float2(fmaf(sg1, v.x, o.x), fmaf(sg1, v.y, o.y));
+    }
+  }
+  // now z[5c + e] = Z[25 kap + c + 5e]
+  // ---- real-input post-pass: X[k] = E + W400^k (-i O) with the mirror bin Z[200 - k] fetched from lane t ^ 7 ----
+  float* pw = s_pow + (warp * MEL_FPW + f) * MEL_PSTRIDE;
+  {
+    const int kap0 = (8 - kap) & 7;                                       // holder of Z[200 - 25 kap] (k1 = 0 case)
+    const int src0 = (lane & ~7) | (((kap0 & 1) << 2) | (kap0 & 2) | (kap0 >> 2));
+    const float2* tw = s_tw400 + 25 * kap;
+#pragma unroll
+    for (int r = 0; r < 25; ++r) {
+      const int c = r / 5, e = r % 5, k1 = c + 5 * e;
+      float2 B;
+      if (k1 == 0) {
+        B.x = __shfl_sync(0xffffffffu, z[0].x, src0); B.y = __shfl_sync(0xffffffffu, z[0].y, src0);
+      } else {
+        const int rp = (c >= 1) ? 5 * (5 - c) + (4 - e) : 5 - e;          // register of bin 25 - k1 in the mirror lane
+        B.x = __shfl_xor_sync(0xffffffffu, z[rp].x, 7); B.y = __shfl_xor_sync(0xffffffffu, z[rp].y, 7);
+      }
+      const float2 A = z[r];
       const float2 E = make_float2(0.5f * (A.x + B.x), 0.5f * (A.y - B.y));
       const float2 O = make_float2(0.5f * (A.x - B.x), 0.5f * (A.y + B.y));
-      const float2 T = cmul(s_tw400[k], mul_negi(O));
-      const float2 Xk = cadd(E, T), Xm = csub(E, T);
-      const float pk = Xk.x * Xk.x + Xk.y * Xk.y, pm = Xm.x * Xm.x + Xm.y * Xm.y;
-      // every item reads and then overwrites only its own two complex slots: no cross-lane hazard
-      f[ia] = pk;
-      if (k == 0) f[ia + 1] = pm;           // P[200]
-      else if (k != 100) f[ib] = pm;        // P[200-k]
+      const float2 T = cmul(tw[k1], mul_negi(O));
+      const float2 X = cadd(E, T);
+      pw[25 * kap + k1] = X.x * X.x + X.y * X.y;
     }
+    if (t == 0) { const float d = z[0].x - z[0].y; pw[200] = d * d; }     // bin 200 (kap == 0 holds Z[0])
   }
   __syncwarp();
-  // ---- sparse mel projection + log10 ----
-  {
-    const float* fs = reinterpret_cast<const float*>(scr);
-    for (int it = lane; it < MEL_FPW * n_mels; it += 32) {
-      const int j = it / n_mels, m = it - j * n_mels;
-      const float* f = fs + j * 400;
-      const int lo = s_lo[m], cnt = s_cnt[m];
-      const float* wv = s_w + m * max_w;
-      float acc = 0.f;
-      for (int i = 0; i < cnt; ++i) acc = fmaf(wv[i], f[s_lut[lo + i]], acc);
-      const float L = 0.30102999566398120f * __log2f(fmaxf(acc, 1e-10f));
-      const int tl = fbase + j;
-      s_tile[m * (MEL_TILE + 1) + tl] = L;
-      if (t0 + tl < DESTA_MEL_FRAMES) lmax = fmaxf(lmax, L);
+  // ---- sparse mel projection + log10: one lane = one mel bin for the warp's 4 frames -> one 16-byte store ----
+  float lmax = -INFINITY;
+  const int tw0 = t0 + warp * MEL_FPW;                                   // first frame of this warp (multiple of 4)
+  const bool frames_ok = tw0 < DESTA_MEL_FRAMES;                         // 3000 % 4 == 0: all four valid or none
+  const float* p0 = s_pow + warp * MEL_FPW * MEL_PSTRIDE;
+  float* o = out + (size_t)clip * n_mels * DESTA_MEL_FRAMES;
+  for (int m = lane; m < n_mels; m += 32) {
+    const int lo = s_lo[m], cnt = s_cnt[m];
+    const float* wv = s_w + m * max_w;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (int i = 0; i < cnt; ++i) {
+      const float wi = wv[i];
+      const float* pp = p0 + lo + i;
+      a0 = fmaf(wi, pp[0], a0);
+      a1 = fmaf(wi, pp[MEL_PSTRIDE], a1);
+      a2 = fmaf(wi, pp[2 * MEL_PSTRIDE], a2);
+      a3 = fmaf(wi, pp[3 * MEL_PSTRIDE], a3);
+    }
+    const float k = 0.30102999566398120f;
+    float4 L;
+    L.x = k * __log2f(fmaxf(a0, 1e-10f)); L.y = k * __log2f(fmaxf(a1, 1e-10f));
+    L.z = k * __log2f(fmaxf(a2, 1e-10f)); L.w = k * __log2f(fmaxf(a3, 1e-10f));
+    if (frames_ok) {
+      lmax = fmaxf(lmax, fmaxf(fmaxf(L.x, L.y), fmaxf(L.z, L.w)));
+      *reinterpret_cast<float4*>(o + (size_t)m * DESTA_MEL_FRAMES + tw0) = L;
     }
   }
 #pragma unroll
-  for (int o = 16; o; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+  for (int off = 16; off; off >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, off));
   if (lane == 0) s_wmax[warp] = lmax;
   __syncthreads();
   if (tid == 0) {
-    float m = s_wmax[0];
-    for (int i = 1; i < MEL_WARPS; ++i) m = fmaxf(m, s_wmax[i]);
-    atomicMax(clip_max + clip, order_f32(m));
-  }
-  // raw tile -> out[clip][m][t0 .. t0+31]: each warp writes whole 128-byte rows
-  float* o = out + (size_t)clip * n_mels * DESTA_MEL_FRAMES;
-  for (int m = warp; m < n_mels; m += MEL_WARPS) {
-    const int t = t0 + lane;
-    if (t < DESTA_MEL_FRAMES) o[(size_t)m * DESTA_MEL_FRAMES + t] = s_tile[m * (MEL_TILE + 1) + lane];
+    float mx = s_wmax[0];
+    for (int i = 1; i < MEL_WARPS; ++i) mx = fmaxf(mx, s_wmax[i]);
+    if (mx > -INFINITY) atomicMax(clip_max + clip, order_f32(mx));
   }
 }
 
@@ -277,9 +318,11 @@ logmel_finish_kernel(float* __restrict__ out, const unsigned* __restrict__ clip_
   if (!out_tm) return;
   __syncthreads();
   __nv_bfloat16* om = out_tm + (size_t)clip * DESTA_MEL_FRAMES * n_mels;
-  for (int i = threadIdx.x; i < MEL_TILE * n_mels; i += blockDim.x) {
-    const int tl = i / n_mels, m = i - tl * n_mels;
-    if (t0 + tl < DESTA_MEL_FRAMES) om[(size_t)(t0 + tl) * n_mels + m] = __float2bfloat16_rn(s_t[m * (MEL_TILE + 1) + tl]);
+  for (int tl = warp; tl < MEL_TILE; tl += 8) {          // one warp per frame row, lanes over mel pairs: 4-byte stores
+    if (t0 + tl >= DESTA_MEL_FRAMES) break;
+    __nv_bfloat162* row = reinterpret_cast<__nv_bfloat162*>(om + (size_t)(t0 + tl) * n_mels);
+    for (int m2 = lane; 2 * m2 < n_mels; m2 += 32)
+      row[m2] = __floats2bfloat162_rn(s_t[(2 * m2) * (MEL_TILE + 1) + tl], s_t[(2 * m2 + 1) * (MEL_TILE + 1) + tl]);
   }
 }
 #endif
@@ -344,7 +387,7 @@ extern "C" int desta_logmel(const float* wave, const int32_t* n_valid, int N, in
   if (N > 65535) { set_error("desta_logmel: at most 65535 clips per call"); return DESTA_ERR_ARG; }
   cudaStream_t s = (cudaStream_t)stream;
   const size_t tab = ((pb / 4 - PLAN_HDR) + 3) & ~(size_t)3;
-  const size_t smem1 = (tab + MEL_WAVE + MEL_WARPS * MEL_FPW * 400 + (size_t)n_mels * (MEL_TILE + 1)) * 4;
+  const size_t smem1 = (tab + MEL_WAVE_PAD + MEL_WARPS * MEL_FPW * MEL_PSTRIDE) * 4;
   static size_t attr1 = 0;
   if (smem1 > attr1) {
     cudaError_t e = cudaFuncSetAttribute(logmel_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
