@@ -29,6 +29,12 @@ WORKLOADS = {
     # name: (oracle config name, dims)
     "large_v3_llama": dict(n_mels=128, d_model=1280, n_heads=20, ffn=5120, n_layers=32, tap_layers=[7, 15, 23, 31],
                            qf_layers=6, prompt_size=64, d_llm=4096, vocab=128256),
+    # whisper-large-v3-turbo shares the large-v3 encoder (32 layers, d 1280); only the decoder differs
+    "turbo_llama": dict(n_mels=128, d_model=1280, n_heads=20, ffn=5120, n_layers=32, tap_layers=[7, 15, 23, 31],
+                        qf_layers=6, prompt_size=64, d_llm=4096, vocab=128256),
+    # Qwen3-4B backbone (docs/train_qwen3.md): d_llm 2560, vocab 151936
+    "large_v3_qwen3_4b": dict(n_mels=128, d_model=1280, n_heads=20, ffn=5120, n_layers=32, tap_layers=[7, 15, 23, 31],
+                              qf_layers=6, prompt_size=64, d_llm=2560, vocab=151936),
     "debug": dict(n_mels=80, d_model=384, n_heads=6, ffn=1536, n_layers=4, tap_layers=[0, 1, 2, 3], qf_layers=2,
                   prompt_size=64, d_llm=1024, vocab=151936),
 }
@@ -181,18 +187,34 @@ def run_ours(args):
     table = (0.02 * torch.randn(w["vocab"], w["d_llm"], device=dev, generator=g)).to(torch.bfloat16)
     wave_host = synth_wave_batch(n, 1234 + rank).pin_memory()
     wave_dev = wave_host.to(dev)
-    ids_host = torch.randint(0, w["vocab"], (n, SEQ_LEN), generator=torch.Generator().manual_seed(7 + rank)).pin_memory()
+    gen = torch.Generator().manual_seed(7 + rank)
+    if args.prompts == "multi":
+        # multi-clip prompts: B = N/4 prompts, 4 locators each, transcripts of 0/3/17/40 tokens, S = 512
+        assert n % 4 == 0, "--prompts multi needs clips divisible by 4"
+        S_len, tl = 512, [0, 3, 17, 40]
+        B_prompts = n // 4
+        positions, trans, start = [], [], 8
+        per_prompt = []
+        for j in range(4):
+            per_prompt.append(start)
+            start += w["prompt_size"] + tl[j] + 9
+        for i in range(n):
+            positions.append((i // 4, per_prompt[i % 4]))
+            trans.append(torch.randint(0, w["vocab"], (1, tl[i % 4]), generator=gen))
+    else:
+        S_len, B_prompts = SEQ_LEN, n
+        positions = [(i, START_POS) for i in range(n)]
+        trans = [torch.zeros(1, 0, dtype=torch.int64) for _ in range(n)]     # empty transcripts (simple_dataset.py:668)
+    ids_host = torch.randint(0, w["vocab"], (B_prompts, S_len), generator=gen).pin_memory()
     ids_dev = ids_host.to(dev)
-    positions = [(i, START_POS) for i in range(n)]
-    trans = [torch.zeros(1, 0, dtype=torch.int64) for _ in range(n)]     # empty transcripts (simple_dataset.py:668)
-    out_host = torch.empty(n, SEQ_LEN, w["d_llm"], dtype=torch.bfloat16).pin_memory()
+    out_host = torch.empty(B_prompts, S_len, w["d_llm"], dtype=torch.bfloat16).pin_memory()
 
     train = args.mode == "train"
     bucket = None
     if train:
         from desta_b200.dist import GradBucket
         perception.train()
-        grad_emb = (0.01 * torch.randn(n, SEQ_LEN, w["d_llm"], device=dev, generator=g)).to(torch.bfloat16)
+        grad_emb = (0.01 * torch.randn(B_prompts, S_len, w["d_llm"], device=dev, generator=g)).to(torch.bfloat16)
         if world > 1:
             bucket = GradBucket(list(perception.connector.parameters()))
 
@@ -283,8 +305,8 @@ def run_ours(args):
         "metric": "audio-sec/sec waveform->LLM embeds" if not train else "audio-sec/sec training step (frozen encoder fwd + Q-Former fwd/bwd)", "value": value, "unit": "audio-s/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": step_s * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: whisper-large-v3 encoder + Qformer6L -> Llama-3.1-8B embeds, 30 s clips",
-                   "mode": args.mode, "clips_per_gpu": n, "seq_len": SEQ_LEN, "l2": "working set >> 126 MB L2 (no flush needed)",
+        "config": {"workload": f"{args.workload}: whisper-large-v3(-turbo) encoder + Qformer6L -> d_llm {w['d_llm']} token embeds, 30 s clips",
+                   "mode": args.mode, "clips_per_gpu": n, "prompts": args.prompts, "seq_len": S_len, "l2": "working set >> 126 MB L2 (no flush needed)",
                    "parallelism": f"clips sharded over {world} GPU(s), no data-path collective"},
         "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": wave_host.numel() * 4 + ids_host.numel() * 8,
                 "d2h_bytes_per_step": out_host.numel() * 2, "ms_per_step": ms_e2e / args.steps},
@@ -315,6 +337,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="large_v3_llama", choices=sorted(WORKLOADS))
     ap.add_argument("--clips", type=int, default=64, help="clips per GPU per step")
+    ap.add_argument("--prompts", default="single", choices=["single", "multi"],
+                    help="single = one clip per prompt, S 128; multi = 4 clips per prompt with transcripts, S 512")
     ap.add_argument("--mode", default="forward", choices=["forward", "train"],
                     help="forward = BASELINE.json configs[1] (default); train = configs[4] step (connector fwd+bwd, grad all-reduce)")
     ap.add_argument("--cpu-clips", type=int, default=2, help="clips in the bounded cpu_baseline sample")

@@ -1,0 +1,31 @@
+"""install() against the REAL reference model class (build container only: skipped where /root/reference is absent)."""
+import os
+
+import pytest
+import torch
+
+REF = "/root/reference/desta/models/modeling_desta25.py"
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="reference tree not present on this machine")
+def test_install_keeps_reference_checkpoint_layout():
+    import desta_b200
+    from desta_b200.perception import WhisperPerceptionB200
+    from oracle.configs import CONFIGS
+    from oracle.refshim import load_reference
+    cfg = CONFIGS["micro"]
+    ref = load_reference(cfg)
+    rcfg = ref.DeSTA25Config(llm_model_id="llama-micro", encoder_model_id=cfg.encoder_model_id,
+                             qformer_num_hidden_layers=cfg.qf_layers, prompt_size=cfg.prompt_size)
+    model = ref.DeSTA25AudioModel(rcfg)
+    keys_before = sorted(model.state_dict().keys())
+    trainable_before = sorted(n for n, p in model.named_parameters() if p.requires_grad)
+    desta_b200.install(model)
+    assert isinstance(model.perception, WhisperPerceptionB200)
+    assert sorted(model.state_dict().keys()) == keys_before                    # trainable-only state_dict (:1284-1292)
+    assert all(k.startswith("perception.connector.") for k in keys_before)
+    assert sorted(n for n, p in model.named_parameters() if p.requires_grad) == trainable_before
+    assert model.perception.dims.tap_layers == [0, 1, 2, 3] and model.perception.dims.prompt_size == cfg.prompt_size
+    # the product path has no CPU fallback: calling it without CUDA must fail loudly, not silently run elsewhere
+    with pytest.raises((AssertionError, RuntimeError)):
+        model.perception(input_features=torch.zeros(1, cfg.n_mels, 3000))
