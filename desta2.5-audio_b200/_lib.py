@@ -1,7 +1,7 @@
 """ctypes binding of libdesta_b200.so (C ABI in include/desta_b200.h).  Fails loudly when the library is absent."""
 import ctypes
 import os
-from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_uint32, c_uint64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libdesta_b200.so")
@@ -11,6 +11,11 @@ class GemmEpilogue(Structure):
     _fields_ = [("out_f32", c_void_p), ("ld_f32", c_int), ("out_bf16", c_void_p), ("ld_bf16", c_int),
                 ("bias", c_void_p), ("resid", c_void_p), ("ld_resid", c_int), ("pos", c_void_p), ("pos_rows", c_int),
                 ("scale", c_float), ("scale_cols", c_int), ("gelu", c_int)]
+
+
+class Dropout(Structure):
+    """desta_dropout: keep iff rnd16 >= thr16, kept values * scale; (seed, site, element) -> Philox counter."""
+    _fields_ = [("thr16", c_uint32), ("scale", c_float), ("seed", c_uint64), ("site", c_uint32)]
 
 
 class SpliceDesc(Structure):
@@ -27,11 +32,14 @@ EXPORTS = {
     "desta_layernorm": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_float, c_int, c_int, c_void_p, c_int, c_void_p,
                                 c_int, c_void_p]),
     "desta_attention": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int,
-                                c_int, c_float, c_void_p, c_void_p]),
+                                c_int, c_float, c_void_p, POINTER(Dropout), c_void_p]),
     "desta_gemm_bf16_wgrad": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "desta_attention_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int,
                                     c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
-                                    c_float, c_void_p]),
+                                    c_float, POINTER(Dropout), c_void_p]),
+    "desta_dropout_add": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, POINTER(Dropout), c_void_p, c_int, c_void_p,
+                                  c_int, c_void_p]),
+    "desta_dropout_mask": (c_int, [POINTER(Dropout), c_int, c_int, c_void_p, c_void_p]),
     "desta_layernorm_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_float, c_int, c_int, c_void_p, c_int,
                                     c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "desta_gelu_fwd": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),

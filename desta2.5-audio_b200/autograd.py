@@ -2,8 +2,12 @@
 (row a6 of the scope table: autograd of desta/models/modeling_desta25.py:587-606 over $TF/models/bert/modeling_bert.py).
 
 Only the connector's parameters receive gradients: the Whisper encoder is frozen (modeling_desta25.py:1451-1453), so
-taps are constants and the K/V projections need a weight gradient but no data gradient.  Dropout is not applied
-(eval-mode semantics; see DESIGN.md "Dropout").
+taps are constants and the K/V projections need a weight gradient but no data gradient.
+
+Train-mode dropout of the Q-Former (BertConfig hidden_dropout_prob / attention_probs_dropout_prob = 0.1,
+$TF/models/bert/modeling_bert.py:198-201, 296, 354) is applied with a counter-based Philox mask: the forward draws one
+64-bit seed per step from torch's default generator (so torch.manual_seed governs it) and the backward regenerates
+every mask from (seed, site) instead of storing it.  In eval mode nothing is dropped, exactly like nn.Dropout.
 
 The autograd.Function exposes every connector parameter as an input so that HF Trainer / Adafactor / DDP see ordinary
 `.grad`s on the reference's own parameter names.
@@ -44,6 +48,27 @@ class ConnectorTPack:
         self.proj = _bf16_t(get("proj.1.weight"))
 
 
+SITE_SELF_PROBS, SITE_SELF_OUT, SITE_CROSS_PROBS, SITE_CROSS_OUT, SITE_FFN_OUT = range(5)
+
+
+class DropPlan:
+    """Dropout sites of one training step: site id = layer * 8 + position (the five nn.Dropout calls of a BertLayer)."""
+
+    def __init__(self, p_hidden: float = 0.0, p_attn: float = 0.0, seed: int = 0):
+        self.p_hidden, self.p_attn, self.seed = float(p_hidden), float(p_attn), int(seed)
+
+    @property
+    def active(self):
+        return self.p_hidden > 0 or self.p_attn > 0
+
+    def site(self, layer: int, which: int):
+        p = self.p_attn if which in (SITE_SELF_PROBS, SITE_CROSS_PROBS) else self.p_hidden
+        return ops.make_dropout(p, self.seed, layer * 8 + which)
+
+
+NO_DROP = DropPlan()
+
+
 class TrainState:
     """Saved activations (per Q-Former layer) + gradient buffers for one batch size."""
 
@@ -66,6 +91,7 @@ class TrainState:
         self.dkv = e(K * N * T, L * 2 * d)
         self.g_f32_a = e(R, d, dt=f32)
         self.g_f32_b = e(R, d, dt=f32)
+        self.g_f32_c = e(R, d, dt=f32)
         self.g_bf_a = e(R, d)
         self.g_bf_b = e(R, d)
         self.g_qkv = e(R, 3 * d)
@@ -92,7 +118,16 @@ class TrainState:
                 t.zero_()
 
 
-def connector_forward_train(con, dims: PathDims, ws, st: TrainState, out_f32):
+def _dense_res(a_bf, w, b, t, resid, drop):
+    """t = dropout(a W^T + b) + resid  (BertSelfOutput / BertOutput before their LayerNorm)."""
+    if drop is None:
+        ops.gemm(a_bf, w, b, out_f32=t, resid=resid)
+    else:
+        ops.gemm(a_bf, w, b, out_f32=t)
+        ops.dropout_add(t, resid, drop, out_f32=t)
+
+
+def connector_forward_train(con, dims: PathDims, ws, st: TrainState, out_f32, plan: DropPlan = NO_DROP):
     N, d, T, Q = ws.N, dims.d_model, dims.max_pos, dims.prompt_size
     K, H = len(dims.tap_layers), dims.n_heads
     B = K * N
@@ -103,17 +138,19 @@ def connector_forward_train(con, dims: PathDims, ws, st: TrainState, out_f32):
     x_bf.copy_(x_f32)
     for l, (L, S) in enumerate(zip(con.layers, st.layers)):
         ops.gemm(S["x_bf"], L["s_qkv_w"], L["s_qkv_b"], out_bf16=S["qkv"])
-        ops.attention(S["qkv"][:, :d], S["qkv"][:, d:2 * d], S["qkv"][:, 2 * d:], S["ao_s"], B, H, Q, Q, scale, lse=S["lse_s"])
-        ops.gemm(S["ao_s"], L["s_o_w"], L["s_o_b"], out_f32=S["t1"], resid=S["x_f32"])
+        ops.attention(S["qkv"][:, :d], S["qkv"][:, d:2 * d], S["qkv"][:, 2 * d:], S["ao_s"], B, H, Q, Q, scale, lse=S["lse_s"],
+                      drop=plan.site(l, SITE_SELF_PROBS))
+        _dense_res(S["ao_s"], L["s_o_w"], L["s_o_b"], S["t1"], S["x_f32"], plan.site(l, SITE_SELF_OUT))
         ops.layernorm(S["t1"], L["s_ln_w"], L["s_ln_b"], 1e-12, out_bf16=S["a_bf"], out_f32=S["a_f32"])
         ops.gemm(S["a_bf"], L["c_q_w"], L["c_q_b"], out_bf16=S["q_c"])
         kc = l * 2 * d
-        ops.attention(S["q_c"], ws.kv[:, kc:kc + d], ws.kv[:, kc + d:kc + 2 * d], S["ao_c"], B, H, Q, T, scale, lse=S["lse_c"])
-        ops.gemm(S["ao_c"], L["c_o_w"], L["c_o_b"], out_f32=S["t2"], resid=S["a_f32"])
+        ops.attention(S["q_c"], ws.kv[:, kc:kc + d], ws.kv[:, kc + d:kc + 2 * d], S["ao_c"], B, H, Q, T, scale, lse=S["lse_c"],
+                      drop=plan.site(l, SITE_CROSS_PROBS))
+        _dense_res(S["ao_c"], L["c_o_w"], L["c_o_b"], S["t2"], S["a_f32"], plan.site(l, SITE_CROSS_OUT))
         ops.layernorm(S["t2"], L["c_ln_w"], L["c_ln_b"], 1e-12, out_bf16=S["c_bf"], out_f32=S["c_f32"])
         ops.gemm(S["c_bf"], L["f1_w"], L["f1_b"], out_bf16=S["h1"])          # pre-activation kept for the backward
         ops.gelu_fwd(S["h1"], S["f"])
-        ops.gemm(S["f"], L["f2_w"], L["f2_b"], out_f32=S["t3"], resid=S["c_f32"])
+        _dense_res(S["f"], L["f2_w"], L["f2_b"], S["t3"], S["c_f32"], plan.site(l, SITE_FFN_OUT))
         nxt = st.layers[l + 1] if l + 1 < len(st.layers) else None
         ops.layernorm(S["t3"], L["f_ln_w"], L["f_ln_b"], 1e-12,
                       out_bf16=nxt["x_bf"] if nxt else st.x_out_bf, out_f32=nxt["x_f32"] if nxt else st.x_out)
@@ -123,7 +160,7 @@ def connector_forward_train(con, dims: PathDims, ws, st: TrainState, out_f32):
     return out_f32
 
 
-def connector_backward(con, conT: ConnectorTPack, dims: PathDims, ws, st: TrainState, grad_out):
+def connector_backward(con, conT: ConnectorTPack, dims: PathDims, ws, st: TrainState, grad_out, plan: DropPlan = NO_DROP):
     """grad_out fp32 [N*Q, d_llm] -> fills st.grads / st.lgrads (+=; call st.zero_grads() first)."""
     N, d, T, Q = ws.N, dims.d_model, dims.max_pos, dims.prompt_size
     K, H = len(dims.tap_layers), dims.n_heads
@@ -143,9 +180,10 @@ def connector_backward(con, conT: ConnectorTPack, dims: PathDims, ws, st: TrainS
         L, LT, S, g = con.layers[l], conT.layers[l], st.layers[l], st.lgrads[l]
         # x' = LN(t3)
         ops.layernorm_bwd(dx, S["t3"], L["f_ln_w"], 1e-12, g["f_ln_w"], g["f_ln_b"], dx_f32=st.g_f32_a, dx_bf16=st.g_bf_a)
-        # t3 = f W2^T + b2 + c
+        # t3 = dropout(f W2^T + b2) + c : the dense branch sees the masked gradient, the residual the full one
+        gd = _drop_grad(st, plan.site(l, SITE_FFN_OUT))
         ops.gemm_wgrad(st.g_bf_a, S["f"], g["f2_w"])
-        ops.colsum(st.g_f32_a, g["f2_b"])
+        ops.colsum(gd, g["f2_b"])
         ops.gemm(st.g_bf_a, LT["f2"], None, out_bf16=st.g_ff)                       # df
         ops.gelu_bwd(st.g_ff, S["h1"], st.g_h1)                                     # dh1
         # h1 = c W1^T + b1
@@ -154,13 +192,15 @@ def connector_backward(con, conT: ConnectorTPack, dims: PathDims, ws, st: TrainS
         ops.gemm(st.g_h1, LT["f1"], None, out_f32=st.g_f32_b, resid=st.g_f32_a)     # dc = dt3 + dh1 W1
         # c = LN(t2)
         ops.layernorm_bwd(st.g_f32_b, S["t2"], L["c_ln_w"], 1e-12, g["c_ln_w"], g["c_ln_b"], dx_f32=st.g_f32_a, dx_bf16=st.g_bf_a)
-        # t2 = ao_c Wco^T + b + a
+        # t2 = dropout(ao_c Wco^T + b) + a
+        gd = _drop_grad(st, plan.site(l, SITE_CROSS_OUT))
         ops.gemm_wgrad(st.g_bf_a, S["ao_c"], g["c_o_w"])
-        ops.colsum(st.g_f32_a, g["c_o_b"])
+        ops.colsum(gd, g["c_o_b"])
         ops.gemm(st.g_bf_a, LT["c_o"], None, out_bf16=st.g_bf_b)                    # d(ao_c)
         kc = l * 2 * d
         ops.attention_bwd(S["q_c"], ws.kv[:, kc:kc + d], ws.kv[:, kc + d:kc + 2 * d], S["ao_c"], st.g_bf_b, S["lse_c"],
-                          st.g_qkv[:, :d], st.dkv[:, kc:kc + d], st.dkv[:, kc + d:kc + 2 * d], B, H, Q, T, scale)
+                          st.g_qkv[:, :d], st.dkv[:, kc:kc + d], st.dkv[:, kc + d:kc + 2 * d], B, H, Q, T, scale,
+                          drop=plan.site(l, SITE_CROSS_PROBS))
         dq_c = st.g_qkv[:, :d]
         # q_c = a Wq^T + bq
         ops.gemm_wgrad(dq_c, S["a_bf"], g["c_q_w"])
@@ -168,12 +208,14 @@ def connector_backward(con, conT: ConnectorTPack, dims: PathDims, ws, st: TrainS
         ops.gemm(dq_c, LT["c_q"], None, out_f32=st.g_f32_b, resid=st.g_f32_a)        # da = dt2 + dq_c Wq
         # a = LN(t1)
         ops.layernorm_bwd(st.g_f32_b, S["t1"], L["s_ln_w"], 1e-12, g["s_ln_w"], g["s_ln_b"], dx_f32=st.g_f32_a, dx_bf16=st.g_bf_a)
-        # t1 = ao_s Wso^T + b + x
+        # t1 = dropout(ao_s Wso^T + b) + x
+        gd = _drop_grad(st, plan.site(l, SITE_SELF_OUT))
         ops.gemm_wgrad(st.g_bf_a, S["ao_s"], g["s_o_w"])
-        ops.colsum(st.g_f32_a, g["s_o_b"])
+        ops.colsum(gd, g["s_o_b"])
         ops.gemm(st.g_bf_a, LT["s_o"], None, out_bf16=st.g_bf_b)                    # d(ao_s)
         ops.attention_bwd(S["qkv"][:, :d], S["qkv"][:, d:2 * d], S["qkv"][:, 2 * d:], S["ao_s"], st.g_bf_b, S["lse_s"],
-                          st.g_qkv[:, :d], st.g_qkv[:, d:2 * d], st.g_qkv[:, 2 * d:], B, H, Q, Q, scale)
+                          st.g_qkv[:, :d], st.g_qkv[:, d:2 * d], st.g_qkv[:, 2 * d:], B, H, Q, Q, scale,
+                          drop=plan.site(l, SITE_SELF_PROBS))
         # qkv = x Wqkv^T + b
         ops.gemm_wgrad(st.g_qkv, S["x_bf"], g["s_qkv_w"])
         ops.colsum(st.g_qkv, g["s_qkv_b"])
@@ -185,6 +227,15 @@ def connector_backward(con, conT: ConnectorTPack, dims: PathDims, ws, st: TrainS
     # ---- cross-attention K/V projections of all layers: one weight-gradient GEMM over all taps' rows ----
     ops.gemm_wgrad(st.dkv, ws.taps.view(K * N * T, d), G["kv_w"])
     ops.colsum(st.dkv, G["kv_b"])
+
+
+def _drop_grad(st: TrainState, drop):
+    """Gradient entering a dropped dense branch: masks st.g_f32_a into (st.g_f32_c fp32, st.g_bf_a bf16) and returns the
+    fp32 tensor for the bias gradient; st.g_f32_a keeps the residual branch's unmasked gradient."""
+    if drop is None:
+        return st.g_f32_a
+    ops.dropout_add(st.g_f32_a, None, drop, out_f32=st.g_f32_c, out_bf16=st.g_bf_a)
+    return st.g_f32_c
 
 
 def param_order(connector) -> List[str]:
@@ -226,8 +277,9 @@ class _ConnectorFn(torch.autograd.Function):
         ws = perception._workspace(N)
         st = perception._train_state(N)
         out = torch.empty(N * perception.dims.prompt_size, perception.dims.d_llm, dtype=torch.float32, device=ws.h.device)
-        connector_forward_train(con, perception.dims, ws, st, out)
-        ctx.perception, ctx.N = perception, N
+        plan = perception._drop_plan()
+        connector_forward_train(con, perception.dims, ws, st, out, plan)
+        ctx.perception, ctx.N, ctx.plan = perception, N, plan
         return out.view(N, perception.dims.prompt_size, perception.dims.d_llm)
 
     @staticmethod
@@ -238,7 +290,7 @@ class _ConnectorFn(torch.autograd.Function):
         ws, st = p._workspace(N), p._train_state(N)
         st.zero_grads()
         g = grad_out.to(torch.float32).contiguous().view(N * p.dims.prompt_size, p.dims.d_llm)
-        connector_backward(con, conT, p.dims, ws, st, g)
+        connector_backward(con, conT, p.dims, ws, st, g, ctx.plan)
         by_name = grads_by_name(st, p.dims)
         grads = []
         for name, prm in p.connector.named_parameters():

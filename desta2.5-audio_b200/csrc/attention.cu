@@ -33,14 +33,17 @@ struct AttnArgs {
   float scale_log2;    // scale * log2(e)
   int q_rows, kv_rows; // TMA box rows actually loaded (min(tile, T))
   float* lse;          // optional [batch, heads, Tq]: log2-domain log-sum-exp of the scaled scores (for the backward)
+  DropoutCfg drop;     // train-mode dropout on the probabilities (modeling_bert.py:198-201); thr16 == 0 -> off
 };
 
 // One softmax pass over a 128 x 64 score block held in TMEM: p = exp2(c*s - mc) written as bf16 into the swizzled
 // A-operand tile, row sum and row max returned.  MASKED (ragged last key block only) selects -inf for padded keys
 // with predicated selects - no per-element branches.
-template <bool MASKED>
+// DROP: the row sum l is taken over the undropped probabilities (softmax normaliser); the P tile fed to P V holds
+// keep ? p / (1 - p_drop) : 0, one Philox call per aligned group of 8 keys (grp0 = group index of this block's key 0).
+template <bool MASKED, bool DROP>
 __device__ __forceinline__ void softmax_pass(uint32_t tS, uint8_t* prow, int rx, float c, float mc, int kv_valid, float& l_blk,
-                                             float& m_blk) {
+                                             float& m_blk, const DropoutCfg& dc, uint64_t grp0) {
   float l0 = 0.f, l1 = 0.f, m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
   for (int ch = 0; ch < 2; ++ch) {
@@ -48,6 +51,7 @@ __device__ __forceinline__ void softmax_pass(uint32_t tS, uint8_t* prow, int rx,
     tmem_ld_32x32(tS + ch * 32, v);
     tmem_wait_ld();
     uint32_t pk[16];
+    uint32_t keep = 0;
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
       float s0 = __uint_as_float(v[i]), s1 = __uint_as_float(v[i + 1]), s2 = __uint_as_float(v[i + 2]), s3 = __uint_as_float(v[i + 3]);
@@ -60,10 +64,18 @@ __device__ __forceinline__ void softmax_pass(uint32_t tS, uint8_t* prow, int rx,
       }
       m0 = max3(m0, s0, s1);
       m1 = max3(m1, s2, s3);
-      const float p0 = fast_exp2(fmaf(s0, c, -mc)), p1 = fast_exp2(fmaf(s1, c, -mc));
-      const float p2 = fast_exp2(fmaf(s2, c, -mc)), p3 = fast_exp2(fmaf(s3, c, -mc));
+      float p0 = fast_exp2(fmaf(s0, c, -mc)), p1 = fast_exp2(fmaf(s1, c, -mc));
+      float p2 = fast_exp2(fmaf(s2, c, -mc)), p3 = fast_exp2(fmaf(s3, c, -mc));
       l0 += p0 + p1;
       l1 += p2 + p3;
+      if (DROP) {
+        if ((i & 7) == 0) keep = dropout_keep8(dc, grp0 + (uint64_t)((ch * 32 + i) >> 3));
+        const uint32_t kb = keep >> (i & 4);
+        p0 = (kb & 1) ? p0 * dc.scale : 0.f;
+        p1 = (kb & 2) ? p1 * dc.scale : 0.f;
+        p2 = (kb & 4) ? p2 * dc.scale : 0.f;
+        p3 = (kb & 8) ? p3 * dc.scale : 0.f;
+      }
       pk[i >> 1] = pack_bf16(p0, p1);
       pk[(i >> 1) + 1] = pack_bf16(p2, p3);
     }
@@ -77,6 +89,7 @@ __device__ __forceinline__ void softmax_pass(uint32_t tS, uint8_t* prow, int rx,
   m_blk = fmaxf(m0, m1);
 }
 
+template <bool DROP>
 __global__ void __launch_bounds__(AT_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnArgs a) {
@@ -172,7 +185,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const float c = a.scale_log2;
     float m_run = -INFINITY, l_run = 0.f;
     const int rx = r & 7;
+    // dropout group index of key 0 for this thread's row: row = (batch*heads + head)*Tq + query
+    const uint64_t grp_row = DROP ? (((uint64_t)batch * gridDim.y + head) * a.Tq + (q0 + r)) * (uint64_t)((a.Tk + 7) >> 3) : 0;
     for (int j = 0; j < n_kv; ++j) {
+      const uint64_t grp0 = grp_row + (uint64_t)(j * (AT_BKV / 8));
       const uint32_t tS = tmem_base + (j & 1) * AT_BKV + lane_off;
       uint8_t* prow = sP + (j & 1) * AT_P_BYTES + r * 128;
       mbar_wait(&s_full[j & 1], (j >> 1) & 1);        // (implies PV_{j-2} finished: the P buffer is free)
@@ -195,8 +211,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       // exp pass against the running max of the PREVIOUS blocks; the block max comes out of the same pass
       float l_blk, m_blk;
-      if (kv_valid >= AT_BKV) softmax_pass<false>(tS, prow, rx, c, m_run * c, kv_valid, l_blk, m_blk);
-      else softmax_pass<true>(tS, prow, rx, c, m_run * c, kv_valid, l_blk, m_blk);
+      if (kv_valid >= AT_BKV) softmax_pass<false, DROP>(tS, prow, rx, c, m_run * c, kv_valid, l_blk, m_blk, a.drop, grp0);
+      else softmax_pass<true, DROP>(tS, prow, rx, c, m_run * c, kv_valid, l_blk, m_blk, a.drop, grp0);
       // P is bf16 and O / l are fp32, so exponents up to 2^20 above the reference are harmless; only beyond that is the
       // reference raised (FA-style lazy rescale; the common case never takes the slow path)
       const bool need = (m_blk - m_run) * c > 20.0f;
@@ -220,7 +236,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           tmem_wait_st();
         }
         m_run = m_new;
-        softmax_pass<true>(tS, prow, rx, c, m_run * c, kv_valid, l_blk, m_blk);
+        softmax_pass<true, DROP>(tS, prow, rx, c, m_run * c, kv_valid, l_blk, m_blk, a.drop, grp0);
       }
       l_run += l_blk;
       fence_proxy_async_smem();       // generic-proxy smem writes -> visible to the tensor core (async proxy)
@@ -272,7 +288,8 @@ static int make_qkv_tmap(CUtensorMap* m, const void* base, int heads, int T, int
 using namespace desta;
 
 extern "C" int desta_attention(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo,
-                               int batch, int heads, int Tq, int Tk, float scale, float* lse, void* stream) {
+                               int batch, int heads, int Tq, int Tk, float scale, float* lse, const desta_dropout* drop,
+                               void* stream) {
   if (!q || !k || !v || !out) { set_error("desta_attention: null pointer"); return DESTA_ERR_ARG; }
   if (batch <= 0 || heads <= 0 || Tq <= 0 || Tk <= 0) { set_error("desta_attention: bad shape"); return DESTA_ERR_ARG; }
   if ((ldq % 8) || (ldk % 8) || (ldv % 8) || (ldo % 8) || ldq < heads * 64 || ldk < heads * 64 || ldv < heads * 64 || ldo < heads * 64) {
@@ -285,6 +302,7 @@ extern "C" int desta_attention(const void* q, int ldq, const void* k, int ldk, c
   a.out = (__nv_bfloat16*)out; a.ldo = ldo; a.Tq = Tq; a.Tk = Tk;
   a.scale_log2 = scale * 1.4426950408889634f;
   a.lse = lse;
+  a.drop = make_dropout_cfg(drop);
   a.q_rows = Tq < AT_BQ ? Tq : AT_BQ;
   a.kv_rows = Tk < AT_BKV ? Tk : AT_BKV;
   CUtensorMap tmQ, tmK, tmV;
@@ -293,11 +311,13 @@ extern "C" int desta_attention(const void* q, int ldq, const void* k, int ldk, c
   if (make_qkv_tmap(&tmV, v, heads, Tk, ldv, batch, a.kv_rows)) return DESTA_ERR_CUDA;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
     if (e != cudaSuccess) { set_error("attention smem attribute: %s", cudaGetErrorString(e)); return DESTA_ERR_CUDA; }
     attr_set = true;
   }
   const dim3 grid((Tq + AT_BQ - 1) / AT_BQ, heads, batch);
-  attn_fwd_kernel<<<grid, AT_THREADS, AT_SMEM, (cudaStream_t)stream>>>(tmQ, tmK, tmV, a);
+  if (a.drop.thr16) attn_fwd_kernel<true><<<grid, AT_THREADS, AT_SMEM, (cudaStream_t)stream>>>(tmQ, tmK, tmV, a);
+  else attn_fwd_kernel<false><<<grid, AT_THREADS, AT_SMEM, (cudaStream_t)stream>>>(tmQ, tmK, tmV, a);
   return check_launch("attn_fwd_kernel");
 }

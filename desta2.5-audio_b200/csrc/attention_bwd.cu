@@ -1,6 +1,8 @@
 // Attention backward for the Q-Former (<= 128 queries per sequence; 64 in DeSTA2.5) on tcgen05/TMEM.
 // Autograd counterpart of the eager Bert self / cross attention ($TF/models/bert/modeling_bert.py:168-207, 234-284):
 //   P = softmax(scale Q K^T),  dV = P^T dO,  dP = dO V^T,  dS = scale * P o (dP - rowsum(dO o O)),  dQ = dS K,  dK = dS^T Q.
+// With train-mode dropout Z (keep / (1 - p), regenerated from the forward's Philox counter; modeling_bert.py:198-201):
+//   O = (P o Z) V  ->  dV = (P o Z)^T dO,  dS = scale * P o (Z o dP - rowsum(dO o O))   (rowsum(dO o O) is unchanged).
 //
 // One CTA per (sequence, head); keys are streamed in blocks of 128 through a 2-stage TMA ring.  All five products run
 // on the tensor cores with operands read as they lie in shared memory:
@@ -32,6 +34,7 @@ struct AttnBwdArgs {
   int Tq, Tk;
   float scale, scale_log2;
   int q_rows, kv_rows;
+  DropoutCfg drop;
 };
 
 __device__ __forceinline__ void store_swizzled_row32(uint8_t* tile_row, int rx, int ch, const uint32_t (&pk)[16]) {
@@ -44,6 +47,7 @@ __device__ __forceinline__ void store_swizzled_row32(uint8_t* tile_row, int rx, 
   }
 }
 
+template <bool DROP>
 __global__ void __launch_bounds__(AB_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
                 const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, const AttnBwdArgs a) {
@@ -170,6 +174,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     uint8_t* prow = sP + r * 128;
     uint8_t* dsrow = sDS + r * 128;
     const int rx = r & 7;
+    const uint64_t grp_row = DROP ? (((uint64_t)batch * gridDim.x + head) * a.Tq + r) * (uint64_t)((a.Tk + 7) >> 3) : 0;
     for (int j = 0; j < n_kv; ++j) {
       mbar_wait(sdp_full, j & 1);
       tcgen05_fence_after();
@@ -181,14 +186,21 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tmem_ld_32x32(tDP + lane_off + ch * 32, dp);
         tmem_wait_ld();
         uint32_t pk[16], dk[16];
+        uint32_t keep = 0;
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
           float p0 = 0.f, p1 = 0.f;
           if (q_ok && ch * 32 + i < kv_valid) p0 = fast_exp2(fmaf(__uint_as_float(s[i]), a.scale_log2, -lse));
           if (q_ok && ch * 32 + i + 1 < kv_valid) p1 = fast_exp2(fmaf(__uint_as_float(s[i + 1]), a.scale_log2, -lse));
-          const float d0 = p0 * (__uint_as_float(dp[i]) - Drow) * a.scale;
-          const float d1 = p1 * (__uint_as_float(dp[i + 1]) - Drow) * a.scale;
-          pk[i >> 1] = pack_bf16(p0, p1);
+          float z0 = 1.f, z1 = 1.f;
+          if (DROP) {
+            if ((i & 7) == 0) keep = dropout_keep8(a.drop, grp_row + (uint64_t)((j * AB_T + ch * 32 + i) >> 3));
+            z0 = ((keep >> (i & 7)) & 1) ? a.drop.scale : 0.f;
+            z1 = ((keep >> (i & 7)) & 2) ? a.drop.scale : 0.f;
+          }
+          const float d0 = p0 * (z0 * __uint_as_float(dp[i]) - Drow) * a.scale;
+          const float d1 = p1 * (z1 * __uint_as_float(dp[i + 1]) - Drow) * a.scale;
+          pk[i >> 1] = pack_bf16(p0 * z0, p1 * z1);
           dk[i >> 1] = pack_bf16(d0, d1);
         }
         store_swizzled_row32(prow, rx, ch, pk);
@@ -272,7 +284,7 @@ using namespace desta;
 extern "C" int desta_attention_bwd(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, const void* o,
                                    int ldo, const void* dout, int lddo, const float* lse, void* dq, int lddq, void* dk,
                                    int lddk, void* dv, int lddv, int batch, int heads, int Tq, int Tk, float scale,
-                                   void* stream) {
+                                   const desta_dropout* drop, void* stream) {
   if (!q || !k || !v || !o || !dout || !lse || !dq || !dk || !dv) { set_error("desta_attention_bwd: null pointer"); return DESTA_ERR_ARG; }
   if (batch <= 0 || heads <= 0 || Tq <= 0 || Tk <= 0) { set_error("desta_attention_bwd: bad shape"); return DESTA_ERR_ARG; }
   if (Tq > AB_T) { set_error("desta_attention_bwd: at most 128 queries per sequence (Q-Former prompts), got %d", Tq); return DESTA_ERR_SHAPE; }
@@ -286,6 +298,7 @@ extern "C" int desta_attention_bwd(const void* q, int ldq, const void* k, int ld
   a.Tq = Tq; a.Tk = Tk; a.scale = scale; a.scale_log2 = scale * 1.4426950408889634f;
   a.q_rows = Tq < AB_T ? Tq : AB_T;
   a.kv_rows = Tk < AB_T ? Tk : AB_T;
+  a.drop = make_dropout_cfg(drop);
   CUtensorMap tmQ, tmDO, tmK, tmV;
   if (make_tmap3(&tmQ, q, heads, Tq, ldq, batch, a.q_rows)) return DESTA_ERR_CUDA;
   if (make_tmap3(&tmDO, dout, heads, Tq, lddo, batch, a.q_rows)) return DESTA_ERR_CUDA;
@@ -293,10 +306,12 @@ extern "C" int desta_attention_bwd(const void* q, int ldq, const void* k, int ld
   if (make_tmap3(&tmV, v, heads, Tk, ldv, batch, a.kv_rows)) return DESTA_ERR_CUDA;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM);
     if (e != cudaSuccess) { set_error("attention bwd smem attribute: %s", cudaGetErrorString(e)); return DESTA_ERR_CUDA; }
     attr_set = true;
   }
-  attn_bwd_kernel<<<dim3(heads, batch), AB_THREADS, AB_SMEM, (cudaStream_t)stream>>>(tmQ, tmDO, tmK, tmV, a);
+  if (a.drop.thr16) attn_bwd_kernel<true><<<dim3(heads, batch), AB_THREADS, AB_SMEM, (cudaStream_t)stream>>>(tmQ, tmDO, tmK, tmV, a);
+  else attn_bwd_kernel<false><<<dim3(heads, batch), AB_THREADS, AB_SMEM, (cudaStream_t)stream>>>(tmQ, tmDO, tmK, tmV, a);
   return check_launch("attn_bwd_kernel");
 }

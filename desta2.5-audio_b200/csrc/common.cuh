@@ -7,6 +7,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include "desta_b200.h"
+
 namespace desta {
 
 // ----------------------------------------------------------------------------------------------
@@ -21,6 +23,25 @@ int make_tmap(CUtensorMap* out, const void* base, CUtensorMapDataType dt, int el
               const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz);
 int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
                       uint32_t box_rows, uint32_t box_cols);
+
+// ---- dropout configuration as the kernels take it (by value); built from the ABI's desta_dropout (NULL -> off) ----
+struct DropoutCfg {
+  uint32_t thr16;      // keep iff rnd16 >= thr16; 0 disables dropout
+  float scale;         // 1 / (1 - p)
+  uint32_t seed_lo, seed_hi;
+  uint32_t site;       // which dropout call of the step (layer / position), part of the counter
+};
+inline DropoutCfg make_dropout_cfg(const desta_dropout* d) {
+  DropoutCfg c = {0u, 1.0f, 0u, 0u, 0u};
+  if (d && d->thr16) {
+    c.thr16 = d->thr16 > 65535u ? 65535u : d->thr16;
+    c.scale = d->scale;
+    c.seed_lo = (uint32_t)d->seed;
+    c.seed_hi = (uint32_t)(d->seed >> 32);
+    c.site = d->site;
+  }
+  return c;
+}
 
 #ifdef __CUDACC__
 // ----------------------------------------------------------------------------------------------
@@ -244,6 +265,31 @@ __device__ __forceinline__ void gelu_erf_x32(float (&f)[32]) {
     const float hx = 0.5f * f[j];
     f[j] = fmaf(hx, p[j] * z, hx);
   }
+}
+
+// ---- dropout RNG: Philox-4x32-7, counter-based (the same (seed, site, element) always yields the same bit, so the
+//      backward regenerates the forward's mask instead of storing it).  One call = 8 elements x 16 random bits.
+//      Q-Former dropout of the reference: BertConfig hidden_dropout_prob = attention_probs_dropout_prob = 0.1
+//      ($TF/models/bert/modeling_bert.py:198-201 attention probs, :296,354 dense outputs), active in train mode. ----
+__device__ __forceinline__ uint4 philox4x32_7(uint32_t k0, uint32_t k1, uint4 c) {
+#pragma unroll
+  for (int r = 0; r < 7; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0);
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return c;
+}
+// 8 keep-bits (bit i = element 8*group + i is kept) for the aligned group of 8 elements `group`
+__device__ __forceinline__ uint32_t dropout_keep8(const DropoutCfg& d, uint64_t group) {
+  const uint4 r = philox4x32_7(d.seed_lo, d.seed_hi, make_uint4((uint32_t)group, (uint32_t)(group >> 32), d.site, 0x0DE57Au));
+  uint32_t m = 0;
+  m |= ((r.x & 0xFFFFu) >= d.thr16) << 0; m |= ((r.x >> 16) >= d.thr16) << 1;
+  m |= ((r.y & 0xFFFFu) >= d.thr16) << 2; m |= ((r.y >> 16) >= d.thr16) << 3;
+  m |= ((r.z & 0xFFFFu) >= d.thr16) << 4; m |= ((r.z >> 16) >= d.thr16) << 5;
+  m |= ((r.w & 0xFFFFu) >= d.thr16) << 6; m |= ((r.w >> 16) >= d.thr16) << 7;
+  return m;
 }
 
 __device__ __forceinline__ float fast_exp2(float x) {

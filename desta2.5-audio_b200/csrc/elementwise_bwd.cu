@@ -288,3 +288,71 @@ extern "C" int desta_cast_f32_bf16(const float* x, void* y, size_t n, void* stre
   cast_f32_bf16_kernel<<<ew_grid(n / 4), 256, 0, (cudaStream_t)stream>>>((const float4*)x, (uint2*)y, n / 4);
   return check_launch("cast_f32_bf16_kernel");
 }
+
+// ---- train-mode dropout of the Q-Former's dense outputs (BertSelfOutput / BertOutput: LayerNorm(dropout(dense) + x),
+//      $TF/models/bert/modeling_bert.py:294-298, 352-356).  One thread per aligned group of 8 elements = one Philox call;
+//      the same kernel serves the forward (resid != NULL) and the backward of the dropped branch (resid == NULL). ----
+namespace desta {
+
+__global__ void __launch_bounds__(256)
+dropout_add_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ resid, int ldr, int M, int ngrp,
+                   DropoutCfg dc, float* __restrict__ out_f32, int ld_f32, __nv_bfloat16* __restrict__ out_bf16, int ld_bf16) {
+  const size_t total = (size_t)M * ngrp;
+  for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (size_t)gridDim.x * blockDim.x) {
+    const int row = (int)(g / ngrp), col = (int)(g % ngrp) * 8;
+    const float4* xp = reinterpret_cast<const float4*>(x + (size_t)row * ldx + col);
+    float4 a = xp[0], b = xp[1];
+    const uint32_t keep = dc.thr16 ? dropout_keep8(dc, g) : 0xFFu;
+    float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = ((keep >> i) & 1) ? v[i] * dc.scale : 0.f;
+    if (resid) {
+      const float4* rp = reinterpret_cast<const float4*>(resid + (size_t)row * ldr + col);
+      const float4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+      v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w; v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+    }
+    if (out_f32) {
+      float4* op = reinterpret_cast<float4*>(out_f32 + (size_t)row * ld_f32 + col);
+      op[0] = make_float4(v[0], v[1], v[2], v[3]);
+      op[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+    if (out_bf16)
+      *reinterpret_cast<uint4*>(out_bf16 + (size_t)row * ld_bf16 + col) =
+          make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+dropout_mask_kernel(DropoutCfg dc, int rows, int cols, int ngrp, uint8_t* __restrict__ mask) {
+  const size_t total = (size_t)rows * ngrp;
+  for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (size_t)gridDim.x * blockDim.x) {
+    const int row = (int)(g / ngrp), col = (int)(g % ngrp) * 8;
+    const uint32_t keep = dc.thr16 ? dropout_keep8(dc, g) : 0xFFu;
+    for (int i = 0; i < 8 && col + i < cols; ++i) mask[(size_t)row * cols + col + i] = (keep >> i) & 1;
+  }
+}
+
+}  // namespace desta
+
+extern "C" int desta_dropout_add(const float* x, int ldx, const float* resid, int ld_resid, int M, int N,
+                                 const desta_dropout* drop, float* out_f32, int ld_f32, void* out_bf16, int ld_bf16,
+                                 void* stream) {
+  if (!x || (!out_f32 && !out_bf16)) { set_error("desta_dropout_add: null pointer"); return DESTA_ERR_ARG; }
+  if (M <= 0 || N <= 0) return DESTA_OK;
+  if ((N % 8) || (ldx % 4) || (resid && (ld_resid % 4)) || (out_f32 && (ld_f32 % 4)) || (out_bf16 && (ld_bf16 % 8))) {
+    set_error("desta_dropout_add: N must be a multiple of 8 and leading dims 16-byte aligned (N=%d)", N);
+    return DESTA_ERR_ARG;
+  }
+  const size_t total = (size_t)M * (N / 8);
+  dropout_add_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(x, ldx, resid, ld_resid, M, N / 8, make_dropout_cfg(drop),
+                                                                      out_f32, ld_f32, (__nv_bfloat16*)out_bf16, ld_bf16);
+  return check_launch("dropout_add_kernel");
+}
+
+extern "C" int desta_dropout_mask(const desta_dropout* drop, int rows, int cols, uint8_t* mask, void* stream) {
+  if (!mask) { set_error("desta_dropout_mask: null pointer"); return DESTA_ERR_ARG; }
+  if (rows <= 0 || cols <= 0) return DESTA_OK;
+  const int ngrp = (cols + 7) / 8;
+  dropout_mask_kernel<<<ew_grid((size_t)rows * ngrp), 256, 0, (cudaStream_t)stream>>>(make_dropout_cfg(drop), rows, cols, ngrp, mask);
+  return check_launch("dropout_mask_kernel");
+}

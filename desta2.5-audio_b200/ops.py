@@ -4,7 +4,7 @@ import ctypes
 import numpy as np
 import torch
 
-from ._lib import GemmEpilogue, SpliceDesc, check, lib
+from ._lib import Dropout, GemmEpilogue, SpliceDesc, check, lib
 
 N_SAMPLES = 480000
 N_FRAMES = 3000
@@ -110,7 +110,20 @@ def layernorm(x, gamma, beta, eps, *, out_bf16=None, out_f32=None):
                                     _p(out_f32), out_f32.stride(0) if out_f32 is not None else 0, _stream()), "desta_layernorm")
 
 
-def attention(q, k, v, out, batch, heads, Tq, Tk, scale, lse=None):
+def make_dropout(p, seed, site):
+    """desta_dropout for probability p (None when p == 0): thr16 = round(p * 65536), scale = 1 / (1 - thr16 / 65536)."""
+    thr = int(round(float(p) * 65536.0))
+    if thr <= 0:
+        return None
+    thr = min(thr, 65535)
+    return Dropout(thr, 1.0 / (1.0 - thr / 65536.0), int(seed) & 0xFFFFFFFFFFFFFFFF, int(site))
+
+
+def _dp(drop):
+    return ctypes.byref(drop) if drop is not None else None
+
+
+def attention(q, k, v, out, batch, heads, Tq, Tk, scale, lse=None, drop=None):
     """q/k/v/out: 2-D bf16 views [batch*T, >= heads*64] (row stride = leading dim; may be slices of a fused buffer)."""
     for t in (q, k, v, out):
         _cuda(t, torch.bfloat16)
@@ -118,10 +131,10 @@ def attention(q, k, v, out, batch, heads, Tq, Tk, scale, lse=None):
     assert q.shape[0] == batch * Tq and k.shape[0] == batch * Tk and v.shape[0] == batch * Tk and out.shape[0] == batch * Tq
     with _op("attention", 1, 4.0 * batch * heads * Tq * Tk * 64):
         check(lib().desta_attention(_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(out), out.stride(0),
-                                    batch, heads, Tq, Tk, float(scale), _p(lse), _stream()), "desta_attention")
+                                    batch, heads, Tq, Tk, float(scale), _p(lse), _dp(drop), _stream()), "desta_attention")
 
 
-def attention_bwd(q, k, v, o, dout, lse, dq, dk, dv, batch, heads, Tq, Tk, scale):
+def attention_bwd(q, k, v, o, dout, lse, dq, dk, dv, batch, heads, Tq, Tk, scale, drop=None):
     for t in (q, k, v, o, dout, dq, dk, dv):
         _cuda(t, torch.bfloat16)
         assert t.stride(1) == 1
@@ -129,7 +142,32 @@ def attention_bwd(q, k, v, o, dout, lse, dq, dk, dv, batch, heads, Tq, Tk, scale
     with _op("attention_bwd", 1, 10.0 * batch * heads * Tq * Tk * 64):
         check(lib().desta_attention_bwd(_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(o), o.stride(0),
                                         _p(dout), dout.stride(0), _p(lse), _p(dq), dq.stride(0), _p(dk), dk.stride(0),
-                                        _p(dv), dv.stride(0), batch, heads, Tq, Tk, float(scale), _stream()), "desta_attention_bwd")
+                                        _p(dv), dv.stride(0), batch, heads, Tq, Tk, float(scale), _dp(drop), _stream()),
+              "desta_attention_bwd")
+
+
+def dropout_add(x, resid, drop, *, out_f32=None, out_bf16=None):
+    """out = dropout(x) (+ resid) on an fp32 [M, N] grid (N % 8 == 0); out_f32 may alias x."""
+    _cuda(x, torch.float32)
+    M, N = x.shape
+    assert x.stride(1) == 1 and (out_f32 is not None or out_bf16 is not None)
+    if resid is not None:
+        _cuda(resid, torch.float32)
+        assert resid.shape == (M, N) and resid.stride(1) == 1
+    nbytes = M * N * (4 + (4 if resid is not None else 0) + (4 if out_f32 is not None else 0) + (2 if out_bf16 is not None else 0))
+    with _op("dropout", 1, nbytes, "byte"):
+        check(lib().desta_dropout_add(_p(x), x.stride(0), _p(resid), resid.stride(0) if resid is not None else 0, M, N, _dp(drop),
+                                      _p(out_f32), out_f32.stride(0) if out_f32 is not None else 0,
+                                      _p(out_bf16), out_bf16.stride(0) if out_bf16 is not None else 0, _stream()),
+              "desta_dropout_add")
+
+
+def dropout_mask(drop, rows, cols, device):
+    """Test hook: the keep mask (bool [rows, cols]) the kernels generate for `drop` over a [rows, cols] grid."""
+    mask = torch.empty(rows, cols, dtype=torch.uint8, device=device)
+    with _op("dropout", 1, rows * cols, "byte"):
+        check(lib().desta_dropout_mask(_dp(drop), rows, cols, _p(mask), _stream()), "desta_dropout_mask")
+    return mask.bool()
 
 
 def gemm_wgrad(dy, x, dw):

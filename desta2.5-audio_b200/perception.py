@@ -74,6 +74,18 @@ class WhisperPerceptionB200(nn.Module):
             self._train = {key: TrainState(self.dims, N, dev)}
         return self._train[key]
 
+    def _drop_plan(self):
+        """Dropout of the Q-Former for this step: BertConfig probabilities in train mode (one fresh seed per step from
+        torch's default generator), nothing in eval mode — the behaviour of the nn.Dropout modules it replaces."""
+        from .autograd import NO_DROP, DropPlan
+        qcfg = self.connector.qformer.config
+        p_h, p_a = float(qcfg.hidden_dropout_prob), float(qcfg.attention_probs_dropout_prob)
+        if not self.connector.training or (p_h <= 0 and p_a <= 0):
+            return NO_DROP
+        seed = int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+        self.last_drop_plan = DropPlan(p_h, p_a, seed)
+        return self.last_drop_plan
+
     def _t_pack(self):
         from .autograd import ConnectorTPack
         versions = tuple(p._version for p in self.connector.parameters())

@@ -54,6 +54,20 @@ typedef struct desta_gemm_epilogue {
 int desta_gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int K,
                     const desta_gemm_epilogue* ep, void* stream);
 
+/* Counter-based dropout (Philox-4x32-7) for the Q-Former in train mode.  keep iff rnd16 >= thr16
+ * (thr16 = round(p * 65536); 0 = off); kept values are multiplied by scale = 1/(1-p).  (seed, site, element index) fully
+ * determine the mask, so the backward regenerates it instead of storing it.  One Philox call covers an aligned group
+ * of 8 consecutive elements of a row; element grid: [M, N] tensors -> group = row * (N/8) + col/8 (N % 8 == 0);
+ * attention probabilities -> row = (b*heads + h)*Tq + t, group = row * ceil(Tk/8) + key/8.
+ * Reference: BertConfig hidden_dropout_prob / attention_probs_dropout_prob = 0.1, active in train mode
+ * ($TF/models/bert/modeling_bert.py:198-201 probabilities, :296, :354 dense outputs). */
+typedef struct desta_dropout {
+  uint32_t thr16;
+  float scale;
+  uint64_t seed;
+  uint32_t site;       /* which dropout call of the step (layer / position) */
+} desta_dropout;
+
 /* LayerNorm over the last dim (fp32 in; fp32 statistics).  out_bf16 and/or out_f32.
  * Replaces nn.LayerNorm at modeling_whisper.py:393,403 (eps 1e-5), modeling_bert.py:297,355 (eps 1e-12),
  * modeling_desta25.py:166 (proj.0). */
@@ -65,7 +79,8 @@ int desta_layernorm(const float* x, int ldx, const float* gamma, const float* be
  * Replaces WhisperAttention (modeling_whisper.py:284-358, scale 1 because q is pre-scaled) and the eager
  * Bert self/cross attention (modeling_bert.py:168-207, 234-284, scale head_dim^-1/2). */
 int desta_attention(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo,
-                    int batch, int heads, int Tq, int Tk, float scale, float* lse /* optional [batch,heads,Tq] */, void* stream);
+                    int batch, int heads, int Tq, int Tk, float scale, float* lse /* optional [batch,heads,Tq] */,
+                    const desta_dropout* drop /* optional: dropout on the attention probabilities */, void* stream);
 
 /* im2col for the conv stem (modeling_desta25.py:563-564): Conv1d(k=3,pad=1,stride s) as GEMM rows.
  * x time-major bf16 [N, T_in, C] -> cols bf16 [N*T_out, 3*C] with column index = tap*C + c  (T_out = T_in/stride). */
@@ -83,7 +98,15 @@ int desta_gemm_bf16_wgrad(const void* dY, int ldy, const void* X, int ldx, int M
 /* Attention backward (Tq <= 128): dq/dk/dv bf16 with the same row layout as q/k/v; lse from desta_attention. */
 int desta_attention_bwd(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, const void* o, int ldo,
                         const void* dout, int lddo, const float* lse, void* dq, int lddq, void* dk, int lddk, void* dv,
-                        int lddv, int batch, int heads, int Tq, int Tk, float scale, void* stream);
+                        int lddv, int batch, int heads, int Tq, int Tk, float scale, const desta_dropout* drop, void* stream);
+/* y = (keep ? x * scale : 0) (+ resid) with the mask of (seed, site) over the [M,N] grid, N % 8 == 0.
+ * Forward: BertSelfOutput / BertOutput  LayerNorm(dropout(dense(x)) + residual)  (modeling_bert.py:294-298, 352-356) with
+ * resid != NULL; backward of the dropped dense output with resid == NULL.  out_f32 and/or out_bf16 (out_f32 may alias x). */
+int desta_dropout_add(const float* x, int ldx, const float* resid, int ld_resid, int M, int N, const desta_dropout* drop,
+                      float* out_f32, int ld_f32, void* out_bf16, int ld_bf16, void* stream);
+/* Test hook: materialise the keep mask (1 byte per element, rows of `cols` elements padded to groups of 8 internally)
+ * of (seed, site) for a [rows, cols] grid. */
+int desta_dropout_mask(const desta_dropout* drop, int rows, int cols, uint8_t* mask, void* stream);
 /* LayerNorm backward from the saved fp32 input; dgamma/dbeta are accumulated (+=). */
 int desta_layernorm_bwd(const float* dy, int lddy, const float* x, int ldx, const float* gamma, float eps, int M, int D,
                         float* dx_f32, int ld_f32, void* dx_bf16, int ld_bf16, float* dgamma, float* dbeta, void* stream);

@@ -116,6 +116,19 @@ def main():
     assert worst < 1e-3 and len(ref_grads) == sum(k.startswith("perception.connector.") for k in W)
     torch.set_grad_enabled(False)
 
+    # train mode: the Q-Former's five dropout sites per layer (BertConfig p = 0.1).  Replaying torch's RNG stream through
+    # the restatement pins the site order / placement against the reference; the reference's output is stored.
+    model.train()
+    torch.manual_seed(123)
+    feats_train_ref, _ = model.perception(input_features=mel)
+    model.eval()
+    torch.manual_seed(123)
+    feats_train_o = o_qf.connector(W, cfg, taps_o, drop=o_qf.torch_dropout(0.1, 0.1))
+    e = (feats_train_ref - feats_train_o).abs().max().item()
+    print(f"connector out, train mode (dropout 0.1, seed 123): oracle vs reference max abs err {e:.3e}; "
+          f"train vs eval differ by {(feats_train_ref - feats_ref).abs().max().item():.3f}")
+    assert e < 2e-4, e
+
     # splice (a7): 2 prompts, 3 clips, transcript lengths 5/0/2
     B, S = 2, 160
     g = torch.Generator().manual_seed(3)
@@ -135,7 +148,7 @@ def main():
         os.path.join(GOLD, "micro_path.npz"),
         kat_tokens=kat["tokens"], kat_result=kat["result"], kat_starts=kat["starts"],
         **{f'tap{i}': taps_ref[i][:, ::25, :].numpy() for i in range(4)},
-        feats=feats_ref.numpy(), gout=gout.numpy(),
+        feats=feats_ref.numpy(), gout=gout.numpy(), feats_train_seed123=feats_train_ref.numpy(),
         grad_names=np.array(sorted(ref_grads)),
         grad_norms=np.array([ref_grads[k].double().norm().item() for k in sorted(ref_grads)]),
         grad_layer_weights=ref_grads["perception.connector.layer_weights"].numpy(),

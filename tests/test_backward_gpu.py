@@ -140,7 +140,7 @@ def test_connector_gradients_vs_oracle(name, n_clips, golden_dir):
     out_ref = o_qf.connector(Wg, cfg, taps)
     (out_ref * gout).sum().backward()
 
-    p = build_perception(cfg, W).train()
+    p = build_perception(cfg, W)          # eval mode: no dropout, exact parity (train-mode dropout: test_dropout_gpu.py)
     for prm in p.whisper.parameters():
         prm.requires_grad_(False)
     wave = torch.from_numpy(np.stack([o_mel.pad_or_truncate(w) for w in waves])).cuda()

@@ -71,6 +71,21 @@ def test_path_oracle_vs_golden(gold):
     assert (gq - torch.from_numpy(gold["grad_q0"])).abs().max().item() < 1e-4 * max(1.0, np.abs(gold["grad_q0"]).max())
 
 
+def test_train_mode_dropout_sites_vs_golden(gold):
+    """The reference's train-mode output (BertConfig dropout 0.1, torch.manual_seed(123)) is reproduced by replaying
+    torch's RNG stream through the restatement's five dropout sites per layer: pins their placement and order."""
+    cfg = CONFIGS["micro"]
+    W = make_weights(cfg, seed=11)
+    mel = torch.from_numpy(o_mel.logmel(synth_waves(seed=7, kinds=KINDS)[:3], cfg.n_mels))
+    with torch.no_grad():
+        taps = o_enc.encoder_taps(W, cfg, mel)
+        torch.manual_seed(123)
+        feats = o_qf.connector(W, cfg, taps, drop=o_qf.torch_dropout(0.1, 0.1))
+    ref = torch.from_numpy(gold["feats_train_seed123"])
+    assert (feats - ref).abs().max().item() < 1e-4
+    assert (ref - torch.from_numpy(gold["feats"])).abs().max().item() > 1e-2      # dropout really was active
+
+
 def test_splice_oracle_vs_golden(gold):
     cfg = CONFIGS["micro"]
     W = make_weights(cfg, seed=11)
