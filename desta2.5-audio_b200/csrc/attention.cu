@@ -3,29 +3,34 @@
 // pre-scaled) and the eager Bert self / cross attention of the Q-Former ($TF/models/bert/modeling_bert.py:168-207,
 // 234-284; 64 queries x 64 or 1500 keys, scale 1/8).
 //
-// One CTA = 128 query rows of one (batch, head); two CTAs are co-resident per SM (112 KB smem, 256 TMEM columns each).
-// Keys are processed in blocks of 64 with DOUBLE-BUFFERED scores (S) and probabilities (P): the MMA warp computes
-// S_{j+2} = Q K_{j+2}^T while the softmax warps are still exponentiating block j, so the softmax warps — which are the
-// bottleneck at head_dim 64 (MUFU ex2 throughput) — never wait on the tensor core.
-//   warp 0   : TMA producer  (Q once; K/V blocks of 64 keys through a 4-stage mbarrier ring, SWIZZLE_128B)
-//   warp 1   : TMEM allocator + MMA issuer: S = Q K^T (UMMA 128x64x16, both operands K-major),
-//              O += P V (UMMA 128x64x16, A = P from shared memory K-major, B = V MN-major as it lies in memory)
-//   warps 2-5: softmax, one query row per thread (TMEM lane == row).  ONE TMEM pass per block: exponentials are taken
+// One CTA = 128 query rows of one (batch, head); two CTAs are co-resident per SM (96 KB smem, 256 TMEM columns each).
+// Keys are processed in blocks of 64.  TMEM holds THREE score buffers of 64 fp32 columns and the 64-column output
+// accumulator.  P never touches shared memory: each softmax thread reads its row of S into registers, and writes
+// the probabilities back IN PLACE as packed bf16 (32 columns) with tcgen05.st; the P V product takes its A operand
+// straight from TMEM.  (At head_dim 64 every UMMA 128x64x16 re-reads 4 KB of A and 2 KB of B from shared memory, so a
+// P round trip through shared memory was 40 % of all shared-memory traffic, the busiest unit of the first version.)
+// With three buffers the MMA warp runs S = Q K^T two full blocks ahead of the softmax, so neither the wake-up of the
+// MMA warp nor the tensor-pipe latency of P V -> next S is ever on the softmax warps' critical path.
+//   warp 0   : TMA producer  (Q once; K/V blocks of 64 keys through a 5-stage mbarrier ring, SWIZZLE_128B)
+//   warp 1   : TMEM allocator + MMA issuer: S_j = Q K_j^T (UMMA 128x64x16, both operands K-major in smem) into buffer
+//              j % 3; O += P_j V_j (UMMA 128x64x16, A = P_j from TMEM, B = V MN-major as it lies in memory); tcgen05
+//              MMAs execute in issue order, so S_{j+3} may overwrite buffer j % 3 as soon as P_j V_j has been issued
+//   warps 2-5: softmax, one query row per thread (TMEM lane == row).  ONE pass per block: exponentials are taken
 //              against the running max of the previous blocks while the block max is gathered in the same pass; only
 //              when a row's max grows by more than 2^20 is the reference raised (O and l rescaled in TMEM) and the block
-//              redone.  P is written as bf16 into the 128B-swizzled A-operand layout; final 1/l and 128-byte row stores.
+//              redone from the scores still held in registers.  Final 1/l and 128-byte row stores.
 #include "common.cuh"
 #include "desta_b200.h"
 
 namespace desta {
 
-constexpr int AT_BQ = 128, AT_BKV = 64, AT_HD = 64, AT_STAGES = 4;
+constexpr int AT_BQ = 128, AT_BKV = 64, AT_HD = 64, AT_STAGES = 5, AT_SBUF = 3;
 constexpr int AT_Q_BYTES = AT_BQ * AT_HD * 2;      // 16 KB
 constexpr int AT_KV_BYTES = AT_BKV * AT_HD * 2;    // 8 KB (K) + 8 KB (V) per stage
-constexpr int AT_P_BYTES = AT_BQ * AT_BKV * 2;     // 16 KB, double-buffered
-constexpr int AT_SMEM = AT_Q_BYTES + AT_STAGES * 2 * AT_KV_BYTES + 2 * AT_P_BYTES + 128;   // 114,816 B -> 2 CTAs / SM
+constexpr int AT_SMEM = AT_Q_BYTES + AT_STAGES * 2 * AT_KV_BYTES + 256;   // 98,560 B -> 2 CTAs / SM
 constexpr int AT_THREADS = 192;
-constexpr int AT_TMEM_COLS = 256;                  // S0: [0,64)  S1: [64,128)  O: [128,192)
+constexpr int AT_TMEM_COLS = 256;                  // S/P buffers: [0,64) [64,128) [128,192)   O: [192,256)
+constexpr int AT_TMEM_O = AT_SBUF * AT_BKV;
 
 struct AttnArgs {
   __nv_bfloat16* out; int ldo;
@@ -36,57 +41,67 @@ struct AttnArgs {
   DropoutCfg drop;     // train-mode dropout on the probabilities (modeling_bert.py:198-201); thr16 == 0 -> off
 };
 
-// One softmax pass over a 128 x 64 score block held in TMEM: p = exp2(c*s - mc) written as bf16 into the swizzled
-// A-operand tile, row sum and row max returned.  MASKED (ragged last key block only) selects -inf for padded keys
+// Compiler-level ordering helper: the 32 registers written by an (asynchronous) tcgen05.ld may only be consumed after
+// tcgen05.wait::ld; routing them through an empty asm after the wait makes that dependency explicit.
+__device__ __forceinline__ void reg_fence32(uint32_t (&v)[32]) {
+  asm volatile("" : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                    "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
+                    "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]),
+                    "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31]));
+}
+
+struct SoftmaxAcc { float l0, l1, m0, m1; };
+
+// 32 score columns (one TMEM chunk held in registers) of one query row: p = exp2(c*s - mc) packed as bf16 pairs into
+// pk; running row sum / row max accumulated in `acc`.  MASKED (ragged last key block only) selects -inf for padded keys
 // with predicated selects - no per-element branches.
 // DROP: the row sum l is taken over the undropped probabilities (softmax normaliser); the P tile fed to P V holds
 // keep ? p / (1 - p_drop) : 0, one Philox call per aligned group of 8 keys (grp0 = group index of this block's key 0).
 template <bool MASKED, bool DROP>
-__device__ __forceinline__ void softmax_pass(uint32_t tS, uint8_t* prow, int rx, float c, float mc, int kv_valid, float& l_blk,
-                                             float& m_blk, const DropoutCfg& dc, uint64_t grp0) {
-  float l0 = 0.f, l1 = 0.f, m0 = -INFINITY, m1 = -INFINITY;
+__device__ __forceinline__ void softmax_chunk(const uint32_t (&v)[32], int ch, uint32_t (&pk)[16], float c, float mc,
+                                              int kv_valid, SoftmaxAcc& acc, const DropoutCfg& dc, uint64_t grp0) {
+  uint32_t keep = 0;
 #pragma unroll
-  for (int ch = 0; ch < 2; ++ch) {
-    uint32_t v[32];
-    tmem_ld_32x32(tS + ch * 32, v);
-    tmem_wait_ld();
-    uint32_t pk[16];
-    uint32_t keep = 0;
-#pragma unroll
-    for (int i = 0; i < 32; i += 4) {
-      float s0 = __uint_as_float(v[i]), s1 = __uint_as_float(v[i + 1]), s2 = __uint_as_float(v[i + 2]), s3 = __uint_as_float(v[i + 3]);
-      if (MASKED) {
-        const int col = ch * 32 + i;
-        s0 = col < kv_valid ? s0 : -INFINITY;
-        s1 = col + 1 < kv_valid ? s1 : -INFINITY;
-        s2 = col + 2 < kv_valid ? s2 : -INFINITY;
-        s3 = col + 3 < kv_valid ? s3 : -INFINITY;
-      }
-      m0 = max3(m0, s0, s1);
-      m1 = max3(m1, s2, s3);
-      float p0 = fast_exp2(fmaf(s0, c, -mc)), p1 = fast_exp2(fmaf(s1, c, -mc));
-      float p2 = fast_exp2(fmaf(s2, c, -mc)), p3 = fast_exp2(fmaf(s3, c, -mc));
-      l0 += p0 + p1;
-      l1 += p2 + p3;
-      if (DROP) {
-        if ((i & 7) == 0) keep = dropout_keep8(dc, grp0 + (uint64_t)((ch * 32 + i) >> 3));
-        const uint32_t kb = keep >> (i & 4);
-        p0 = (kb & 1) ? p0 * dc.scale : 0.f;
-        p1 = (kb & 2) ? p1 * dc.scale : 0.f;
-        p2 = (kb & 4) ? p2 * dc.scale : 0.f;
-        p3 = (kb & 8) ? p3 * dc.scale : 0.f;
-      }
-      pk[i >> 1] = pack_bf16(p0, p1);
-      pk[(i >> 1) + 1] = pack_bf16(p2, p3);
+  for (int i = 0; i < 32; i += 4) {
+    float s0 = __uint_as_float(v[i]), s1 = __uint_as_float(v[i + 1]), s2 = __uint_as_float(v[i + 2]), s3 = __uint_as_float(v[i + 3]);
+    if (MASKED) {
+      const int col = ch * 32 + i;
+      s0 = col < kv_valid ? s0 : -INFINITY;
+      s1 = col + 1 < kv_valid ? s1 : -INFINITY;
+      s2 = col + 2 < kv_valid ? s2 : -INFINITY;
+      s3 = col + 3 < kv_valid ? s3 : -INFINITY;
     }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int chunk = (ch * 4 + q) ^ rx;
-      *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+    acc.m0 = max3(acc.m0, s0, s1);
+    acc.m1 = max3(acc.m1, s2, s3);
+    float p0 = fast_exp2(fmaf(s0, c, -mc)), p1 = fast_exp2(fmaf(s1, c, -mc));
+    float p2 = fast_exp2(fmaf(s2, c, -mc)), p3 = fast_exp2(fmaf(s3, c, -mc));
+    acc.l0 += p0 + p1;
+    acc.l1 += p2 + p3;
+    if (DROP) {
+      if ((i & 7) == 0) keep = dropout_keep8(dc, grp0 + (uint64_t)((ch * 32 + i) >> 3));
+      const uint32_t kb = keep >> (i & 4);
+      p0 = (kb & 1) ? p0 * dc.scale : 0.f;
+      p1 = (kb & 2) ? p1 * dc.scale : 0.f;
+      p2 = (kb & 4) ? p2 * dc.scale : 0.f;
+      p3 = (kb & 8) ? p3 * dc.scale : 0.f;
     }
+    pk[i >> 1] = pack_bf16(p0, p1);
+    pk[(i >> 1) + 1] = pack_bf16(p2, p3);
   }
-  l_blk = l0 + l1;
-  m_blk = fmaxf(m0, m1);
+}
+
+// Both chunks of a 64-key block from the scores in registers; P written in place over the block's S columns [0, 32).
+template <bool MASKED, bool DROP>
+__device__ __forceinline__ void softmax_block(const uint32_t (&va)[32], const uint32_t (&vb)[32], uint32_t tS, float c, float mc,
+                                              int kv_valid, float& l_blk, float& m_blk, const DropoutCfg& dc, uint64_t grp0) {
+  SoftmaxAcc acc = {0.f, 0.f, -INFINITY, -INFINITY};
+  uint32_t pk[16];
+  softmax_chunk<MASKED, DROP>(va, 0, pk, c, mc, kv_valid, acc, dc, grp0);
+  tmem_st_32x16(tS, pk);            // keys [0, 32): A operand of P V, K-major, two bf16 per column
+  softmax_chunk<MASKED, DROP>(vb, 1, pk, c, mc, kv_valid, acc, dc, grp0);
+  tmem_st_32x16(tS + 16, pk);       // keys [32, 64)
+  l_blk = acc.l0 + acc.l1;
+  m_blk = fmaxf(acc.m0, acc.m1);
 }
 
 template <bool DROP>
@@ -97,15 +112,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (smem_u32(smem) & 1023) __trap();
   uint8_t* sQ = smem;
   uint8_t* sKV = sQ + AT_Q_BYTES;                       // stage s: K at s*16K, V at s*16K + 8K
-  uint8_t* sP = sKV + AT_STAGES * 2 * AT_KV_BYTES;      // two P tiles of 16 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * AT_P_BYTES);
-  uint64_t* q_full = bars;            // 1
-  uint64_t* kv_full = bars + 1;       // [4]
-  uint64_t* kv_empty = bars + 5;      // [4]
-  uint64_t* s_full = bars + 9;        // [2]
-  uint64_t* p_ready = bars + 11;      // [2]
-  uint64_t* pv_done = bars + 13;      // [2]: PV_j commits to pv_done[j & 1] (two barriers: a waiter is never 2 phases behind)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + AT_STAGES * 2 * AT_KV_BYTES);
+  uint64_t* q_full = bars;                              // 1
+  uint64_t* kv_full = bars + 1;                         // [AT_STAGES]
+  uint64_t* kv_empty = kv_full + AT_STAGES;             // [AT_STAGES]
+  uint64_t* s_full = kv_empty + AT_STAGES;              // [3]  S_j landed in buffer j % 3
+  uint64_t* p_ready = s_full + AT_SBUF;                 // [3]  P_j written over S_j (128 arrivals), O rescaled if needed
+  uint64_t* pv_done = p_ready + AT_SBUF;                // [3]  P_j V_j accumulated into O
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + AT_SBUF);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * AT_BQ, head = blockIdx.y, batch = blockIdx.z;
@@ -120,8 +134,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
     mbar_init(q_full, 1);
     for (int i = 0; i < AT_STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 128); }
-    mbar_init(&pv_done[0], 1); mbar_init(&pv_done[1], 1);
+    for (int i = 0; i < AT_SBUF; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 128); mbar_init(&pv_done[i], 1); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<AT_TMEM_COLS>(tmem_slot);
@@ -129,53 +142,64 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_O = tmem_base + 128;
+  const uint32_t tmem_O = tmem_base + AT_TMEM_O;
 
+  // Warps 0 and 1 run their loops CONVERGED (all 32 lanes wait on the mbarriers) and hand each TMA / tcgen05
+  // instruction group to one lane with elect.sync: ptxas then keeps descriptors in uniform registers and issues
+  // UTMALDG / UTCHMMA directly, instead of the per-instruction waterfall loop it emits inside an `if (lane == 0)` branch
+  // (tools/umma_bench.cu: 48 -> 32 cycles per 128x64x16 TS instruction; the issue loop, not the tensor pipe, was the
+  // bottleneck of this kernel).
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_arrive_expect_tx(q_full, a.q_rows * AT_HD * 2);
       tma_load_3d(sQ, &tmQ, q_full, head * AT_HD, q0, batch);
-      for (int j = 0; j < n_kv; ++j) {
-        const int st = j % AT_STAGES;
-        mbar_wait_sleep(&kv_empty[st], ((j / AT_STAGES) & 1) ^ 1);
+    }
+    for (int j = 0; j < n_kv; ++j) {
+      const int st = j % AT_STAGES;
+      mbar_wait_sleep(&kv_empty[st], ((j / AT_STAGES) & 1) ^ 1);
+      if (elect_one()) {
         mbar_arrive_expect_tx(&kv_full[st], 2 * a.kv_rows * AT_HD * 2);
         tma_load_3d(sKV + st * 2 * AT_KV_BYTES, &tmK, &kv_full[st], head * AT_HD, j * AT_BKV, batch);
         tma_load_3d(sKV + st * 2 * AT_KV_BYTES + AT_KV_BYTES, &tmV, &kv_full[st], head * AT_HD, j * AT_BKV, batch);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_qk = umma_idesc_bf16(AT_BQ, AT_BKV, 0, 0);
-      constexpr uint32_t idesc_pv = umma_idesc_bf16(AT_BQ, AT_HD, 0, 1);   // B (= V) is MN-major
-      const uint64_t qdesc = umma_desc_sw128(smem_u32(sQ), 16, 1024);
-      // S_j = Q K_j^T into S buffer (j & 1); issued two blocks ahead of the softmax
-      auto issue_qk = [&](int j) {
-        const int st = j % AT_STAGES;
-        mbar_wait_sleep(&kv_full[st], (j / AT_STAGES) & 1);
-        tcgen05_fence_after();
-        const uint64_t kdesc = umma_desc_sw128(smem_u32(sKV + st * 2 * AT_KV_BYTES), 16, 1024);
+    constexpr uint32_t idesc_qk = umma_idesc_bf16(AT_BQ, AT_BKV, 0, 0);
+    constexpr uint32_t idesc_pv = umma_idesc_bf16(AT_BQ, AT_HD, 0, 1);   // B (= V) is MN-major
+    const uint64_t qdesc = umma_desc_sw128(smem_u32(sQ), 16, 1024);
+    // S_j = Q K_j^T into buffer j % 3; issued three blocks ahead of the P V product of the same buffer
+    auto issue_qk = [&](int j) {
+      const int st = j % AT_STAGES;
+      mbar_wait(&kv_full[st], (j / AT_STAGES) & 1);
+      tcgen05_fence_after();
+      const uint64_t kdesc = umma_desc_sw128(smem_u32(sKV + st * 2 * AT_KV_BYTES), 16, 1024);
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < AT_HD / 16; ++k)
-          umma_bf16_ss(tmem_base + (j & 1) * AT_BKV, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, k != 0);
-        umma_commit(&s_full[j & 1]);
-      };
-      mbar_wait(q_full, 0);
-      issue_qk(0);
-      if (n_kv > 1) issue_qk(1);
-      for (int j = 0; j < n_kv; ++j) {
-        const int st = j % AT_STAGES;
-        mbar_wait_sleep(&p_ready[j & 1], (j >> 1) & 1);   // P_j in smem, S_j consumed, O rescaled if needed
-        tcgen05_fence_after();
-        // V stage: 64 key rows x 128 B (64 head-dim values) -> MN-major B operand, 8-row groups 1024 B apart
-        const uint64_t vdesc = umma_desc_sw128(smem_u32(sKV + st * 2 * AT_KV_BYTES + AT_KV_BYTES), 1024, 1024);
-        const uint64_t pdesc = umma_desc_sw128(smem_u32(sP + (j & 1) * AT_P_BYTES), 16, 1024);
-#pragma unroll
-        for (int k = 0; k < AT_BKV / 16; ++k)
-          umma_bf16_ss(tmem_O, pdesc + 2 * k, vdesc + (uint64_t)(k * 128), idesc_pv, (j | k) != 0);
-        umma_commit(&kv_empty[st]);
-        umma_commit(&pv_done[j & 1]);
-        if (j + 2 < n_kv) issue_qk(j + 2);          // S buffer (j & 1) is free again
+          umma_bf16_ss(tmem_base + (j % AT_SBUF) * AT_BKV, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, k != 0);
+        umma_commit(&s_full[j % AT_SBUF]);
       }
+      __syncwarp();
+    };
+    mbar_wait(q_full, 0);
+    for (int j = 0; j < AT_SBUF && j < n_kv; ++j) issue_qk(j);
+    for (int j = 0; j < n_kv; ++j) {
+      const int st = j % AT_STAGES, b = j % AT_SBUF;
+      mbar_wait(&p_ready[b], (j / AT_SBUF) & 1);           // P_j in TMEM (over S_j), O rescaled if needed
+      tcgen05_fence_after();
+      // V stage: 64 key rows x 128 B (64 head-dim values) -> MN-major B operand, 8-row groups 1024 B apart
+      const uint64_t vdesc = umma_desc_sw128(smem_u32(sKV + st * 2 * AT_KV_BYTES + AT_KV_BYTES), 1024, 1024);
+      const uint32_t tP = tmem_base + b * AT_BKV;
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < AT_BKV / 16; ++k)     // 16 keys = 8 packed columns of P per UMMA
+          umma_bf16_ts(tmem_O, tP + k * 8, vdesc + (uint64_t)(k * 128), idesc_pv, (j | k) != 0);
+        umma_commit(&kv_empty[st]);
+        umma_commit(&pv_done[b]);
+      }
+      __syncwarp();
+      if (j + AT_SBUF < n_kv) issue_qk(j + AT_SBUF);   // in-order tensor pipe: overwrites buffer b after P_j V_j
     }
   } else {
     // ---- softmax warps: TMEM lane quarter = warp % 4, one query row per thread ----
@@ -184,43 +208,64 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     const float c = a.scale_log2;
     float m_run = -INFINITY, l_run = 0.f;
-    const int rx = r & 7;
     // dropout group index of key 0 for this thread's row: row = (batch*heads + head)*Tq + query
     const uint64_t grp_row = DROP ? (((uint64_t)batch * gridDim.y + head) * a.Tq + (q0 + r)) * (uint64_t)((a.Tk + 7) >> 3) : 0;
-    for (int j = 0; j < n_kv; ++j) {
+    // Software pipeline over 32-column chunks with three register sets: while the exponentials of one chunk occupy the
+    // MUFU pipe, the tcgen05.ld of the next chunk (the second half of this block, then the first half of the NEXT block,
+    // which the three S buffers make available early) is already in flight, and the tcgen05.st of the previous block's P
+    // is only waited for - and announced to the MMA warp - one chunk later.  `ca` = this block's keys [0,32) (already
+    // requested), `cb` = keys [32,64), `na` = the next block's keys [0,32).
+    auto step = [&](int j, uint32_t (&ca)[32], uint32_t (&cb)[32], uint32_t (&na)[32]) {
+      const int b = j % AT_SBUF;
       const uint64_t grp0 = grp_row + (uint64_t)(j * (AT_BKV / 8));
-      const uint32_t tS = tmem_base + (j & 1) * AT_BKV + lane_off;
-      uint8_t* prow = sP + (j & 1) * AT_P_BYTES + r * 128;
-      mbar_wait(&s_full[j & 1], (j >> 1) & 1);        // (implies PV_{j-2} finished: the P buffer is free)
-      tcgen05_fence_after();
+      const uint32_t tS = tmem_base + b * AT_BKV + lane_off;
       const int kv_valid = a.Tk - j * AT_BKV;
+      tmem_wait_ld();                                   // ca
+      reg_fence32(ca);
+      tmem_ld_32x32(tS + 32, cb);
       if (j == 0) {
-        // first block: no reference max yet -> plain max pass
+        // first block: no reference max yet -> its own row max
+        tmem_wait_ld();
+        reg_fence32(cb);
         float m0 = -INFINITY;
-#pragma unroll 1
-        for (int ch = 0; ch < 2; ++ch) {
-          uint32_t v[32];
-          tmem_ld_32x32(tS + ch * 32, v);
-          tmem_wait_ld();
 #pragma unroll
-          for (int i = 0; i < 32; i += 2)
-            m0 = max3(m0, (ch * 32 + i < kv_valid) ? __uint_as_float(v[i]) : -INFINITY,
-                      (ch * 32 + i + 1 < kv_valid) ? __uint_as_float(v[i + 1]) : -INFINITY);
+        for (int i = 0; i < 32; i += 2) {
+          m0 = max3(m0, (i < kv_valid) ? __uint_as_float(ca[i]) : -INFINITY, (i + 1 < kv_valid) ? __uint_as_float(ca[i + 1]) : -INFINITY);
+          m0 = max3(m0, (32 + i < kv_valid) ? __uint_as_float(cb[i]) : -INFINITY, (33 + i < kv_valid) ? __uint_as_float(cb[i + 1]) : -INFINITY);
         }
         m_run = m0;
       }
       // exp pass against the running max of the PREVIOUS blocks; the block max comes out of the same pass
-      float l_blk, m_blk;
-      if (kv_valid >= AT_BKV) softmax_pass<false, DROP>(tS, prow, rx, c, m_run * c, kv_valid, l_blk, m_blk, a.drop, grp0);
-      else softmax_pass<true, DROP>(tS, prow, rx, c, m_run * c, kv_valid, l_blk, m_blk, a.drop, grp0);
+      const float mc = m_run * c;
+      SoftmaxAcc acc = {0.f, 0.f, -INFINITY, -INFINITY};
+      uint32_t pk[16];
+      if (kv_valid >= AT_BKV) softmax_chunk<false, DROP>(ca, 0, pk, c, mc, kv_valid, acc, a.drop, grp0);
+      else softmax_chunk<true, DROP>(ca, 0, pk, c, mc, kv_valid, acc, a.drop, grp0);
+      if (j > 0) {                                      // P_{j-1} has landed in TMEM: its stores were issued 32 exponentials ago
+        tmem_wait_st();
+        tcgen05_fence_before();
+        mbar_arrive(&p_ready[(j - 1) % AT_SBUF]);
+      }
+      tmem_st_32x16(tS, pk);                            // P keys [0,32) in place over S columns [0,16)
+      tmem_wait_ld();                                   // cb
+      reg_fence32(cb);
+      if (j + 1 < n_kv) {
+        mbar_wait(&s_full[(j + 1) % AT_SBUF], ((j + 1) / AT_SBUF) & 1);
+        tcgen05_fence_after();
+        tmem_ld_32x32(tmem_base + ((j + 1) % AT_SBUF) * AT_BKV + lane_off, na);
+      }
+      if (kv_valid >= AT_BKV) softmax_chunk<false, DROP>(cb, 1, pk, c, mc, kv_valid, acc, a.drop, grp0);
+      else softmax_chunk<true, DROP>(cb, 1, pk, c, mc, kv_valid, acc, a.drop, grp0);
+      tmem_st_32x16(tS + 16, pk);                       // P keys [32,64) over S columns [16,32)
+      float l_blk = acc.l0 + acc.l1, m_blk = fmaxf(acc.m0, acc.m1);
       // P is bf16 and O / l are fp32, so exponents up to 2^20 above the reference are harmless; only beyond that is the
       // reference raised (FA-style lazy rescale; the common case never takes the slow path)
       const bool need = (m_blk - m_run) * c > 20.0f;
       if (__any_sync(0xffffffffu, need)) {
-        // rare: raise the reference max, rescale O and l, redo the block's exponentials
+        // rare: raise the reference max, rescale O and l, redo the block's exponentials from the registers
         const float m_new = fmaxf(m_run, m_blk);
         if (j > 0) {
-          mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);   // PV_{j-1} must have landed in O
+          mbar_wait(&pv_done[(j - 1) % AT_SBUF], ((j - 1) / AT_SBUF) & 1);   // P_{j-1} V_{j-1} must have landed in O
           tcgen05_fence_after();
           const float f = exp2f((m_run - m_new) * c);
           l_run *= f;
@@ -233,18 +278,25 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
             tmem_st_32x16(tmem_O + lane_off + ch * 16, o);
           }
-          tmem_wait_st();
         }
         m_run = m_new;
-        softmax_pass<true, DROP>(tS, prow, rx, c, m_run * c, kv_valid, l_blk, m_blk, a.drop, grp0);
+        softmax_block<true, DROP>(ca, cb, tS, c, m_run * c, kv_valid, l_blk, m_blk, a.drop, grp0);
       }
       l_run += l_blk;
-      fence_proxy_async_smem();       // generic-proxy smem writes -> visible to the tensor core (async proxy)
-      tcgen05_fence_before();         // orders this thread's TMEM loads/stores before the MMA warp's next MMAs
-      mbar_arrive(&p_ready[j & 1]);
+    };
+    uint32_t ra[32], rb[32], rc[32];
+    mbar_wait(&s_full[0], 0);
+    tcgen05_fence_after();
+    tmem_ld_32x32(tmem_base + lane_off, ra);
+    for (int j = 0; j < n_kv; j += 2) {
+      step(j, ra, rb, rc);
+      if (j + 1 < n_kv) step(j + 1, rc, rb, ra);
     }
+    tmem_wait_st();                 // the last P (and a rescaled O) have landed in TMEM
+    tcgen05_fence_before();         // orders this thread's TMEM accesses before the MMA warp's next MMAs
+    mbar_arrive(&p_ready[(n_kv - 1) % AT_SBUF]);
     // ---- epilogue: O / l -> bf16, one 128-byte row per thread ----
-    mbar_wait(&pv_done[(n_kv - 1) & 1], ((n_kv - 1) >> 1) & 1);
+    mbar_wait(&pv_done[(n_kv - 1) % AT_SBUF], ((n_kv - 1) / AT_SBUF) & 1);
     tcgen05_fence_after();
     const float inv = 1.0f / l_run;
     const int row = q0 + r;

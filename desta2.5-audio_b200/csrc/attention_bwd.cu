@@ -92,47 +92,54 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tS = tmem_base, tDP = tmem_base + 128, tDV = tmem_base + 256, tDK = tmem_base + 320, tDQ = tmem_base + 384;
 
+  // Warps 0 and 1 run converged; each TMA / tcgen05 group is handed to one lane with elect.sync (see attention.cu).
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_arrive_expect_tx(q_full, 2 * a.q_rows * AB_HD * 2);
       tma_load_3d(sQ, &tmQ, q_full, head * AB_HD, 0, batch);
       tma_load_3d(sDO, &tmDO, q_full, head * AB_HD, 0, batch);
-      for (int j = 0; j < n_kv; ++j) {
-        const int st = j & 1;
-        mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
+    }
+    for (int j = 0; j < n_kv; ++j) {
+      const int st = j & 1;
+      mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
+      if (elect_one()) {
         mbar_arrive_expect_tx(&kv_full[st], 2 * a.kv_rows * AB_HD * 2);
         tma_load_3d(sKV + st * 2 * AB_TILE, &tmK, &kv_full[st], head * AB_HD, j * AB_T, batch);
         tma_load_3d(sKV + st * 2 * AB_TILE + AB_TILE, &tmV, &kv_full[st], head * AB_HD, j * AB_T, batch);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t id_kk_128 = umma_idesc_bf16(128, 128, 0, 0);    // S, dP
-      constexpr uint32_t id_mm_64 = umma_idesc_bf16(128, 64, 1, 1);      // dV, dK: A and B MN-major
-      constexpr uint32_t id_km_64 = umma_idesc_bf16(128, 64, 0, 1);      // dQ: A K-major, B MN-major
-      const uint64_t q_k = umma_desc_sw128(smem_u32(sQ), 16, 1024);      // Q as K-major A
-      const uint64_t do_k = umma_desc_sw128(smem_u32(sDO), 16, 1024);    // dO as K-major A
-      const uint64_t q_mn = umma_desc_sw128(smem_u32(sQ), 1024, 1024);   // Q as MN-major B (reduction = query rows)
-      const uint64_t do_mn = umma_desc_sw128(smem_u32(sDO), 1024, 1024);
-      const uint64_t p_mn = umma_desc_sw128(smem_u32(sP), AB_T * 128, 1024);    // P^T: M = key columns (2 atoms of 16 KB)
-      const uint64_t ds_mn = umma_desc_sw128(smem_u32(sDS), AB_T * 128, 1024);  // dS^T
-      const uint64_t ds_k = umma_desc_sw128(smem_u32(sDS), 16, 1024);           // dS as K-major A
-      mbar_wait(q_full, 0);
-      for (int j = 0; j < n_kv; ++j) {
-        const int st = j & 1;
-        const uint32_t sK = smem_u32(sKV + st * 2 * AB_TILE), sV = sK + AB_TILE;
-        mbar_wait(&kv_full[st], (j >> 1) & 1);
-        tcgen05_fence_after();
-        const uint64_t k_k = umma_desc_sw128(sK, 16, 1024), v_k = umma_desc_sw128(sV, 16, 1024);
+    constexpr uint32_t id_kk_128 = umma_idesc_bf16(128, 128, 0, 0);    // S, dP
+    constexpr uint32_t id_mm_64 = umma_idesc_bf16(128, 64, 1, 1);      // dV, dK: A and B MN-major
+    constexpr uint32_t id_km_64 = umma_idesc_bf16(128, 64, 0, 1);      // dQ: A K-major, B MN-major
+    const uint64_t q_k = umma_desc_sw128(smem_u32(sQ), 16, 1024);      // Q as K-major A
+    const uint64_t do_k = umma_desc_sw128(smem_u32(sDO), 16, 1024);    // dO as K-major A
+    const uint64_t q_mn = umma_desc_sw128(smem_u32(sQ), 1024, 1024);   // Q as MN-major B (reduction = query rows)
+    const uint64_t do_mn = umma_desc_sw128(smem_u32(sDO), 1024, 1024);
+    const uint64_t p_mn = umma_desc_sw128(smem_u32(sP), AB_T * 128, 1024);    // P^T: M = key columns (2 atoms of 16 KB)
+    const uint64_t ds_mn = umma_desc_sw128(smem_u32(sDS), AB_T * 128, 1024);  // dS^T
+    const uint64_t ds_k = umma_desc_sw128(smem_u32(sDS), 16, 1024);           // dS as K-major A
+    mbar_wait(q_full, 0);
+    for (int j = 0; j < n_kv; ++j) {
+      const int st = j & 1;
+      const uint32_t sK = smem_u32(sKV + st * 2 * AB_TILE), sV = sK + AB_TILE;
+      mbar_wait(&kv_full[st], (j >> 1) & 1);
+      tcgen05_fence_after();
+      const uint64_t k_k = umma_desc_sw128(sK, 16, 1024), v_k = umma_desc_sw128(sV, 16, 1024);
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < AB_HD / 16; ++k) umma_bf16_ss(tS, q_k + 2 * k, k_k + 2 * k, id_kk_128, k != 0);
 #pragma unroll
         for (int k = 0; k < AB_HD / 16; ++k) umma_bf16_ss(tDP, do_k + 2 * k, v_k + 2 * k, id_kk_128, k != 0);
         umma_commit(sdp_full);
-        mbar_wait(pds_ready, j & 1);                       // P, dS tiles written; S, dP consumed
-        if (j > 0) mbar_wait(dkv_empty, (j - 1) & 1);      // previous dV / dK drained from TMEM
-        tcgen05_fence_after();
-        const uint64_t k_mn = umma_desc_sw128(sK, 1024, 1024);           // K as MN-major B (reduction = key rows)
+      }
+      __syncwarp();
+      mbar_wait(pds_ready, j & 1);                       // P, dS tiles written; S, dP consumed
+      if (j > 0) mbar_wait(dkv_empty, (j - 1) & 1);      // previous dV / dK drained from TMEM
+      tcgen05_fence_after();
+      const uint64_t k_mn = umma_desc_sw128(sK, 1024, 1024);           // K as MN-major B (reduction = key rows)
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < AB_T / 16; ++k) {               // reduction over the 128 query rows, 16 per step = 2048 B
           umma_bf16_ss(tDV, p_mn + 128 * k, do_mn + 128 * k, id_mm_64, k != 0);
@@ -146,6 +153,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         umma_commit(&kv_empty[st]);
         umma_commit(dkv_full);
       }
+      __syncwarp();
     }
   } else {
     const int quarter = warp & 3;

@@ -78,8 +78,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Warps 0 and 1 run their loops converged and hand each TMA / tcgen05 group to one lane with elect.sync (ptxas then
+  // issues UTMALDG / UTCHMMA from uniform registers instead of a per-instruction waterfall loop; tools/umma_bench.cu).
   if (warp == 0) {
-    if (lane == 0) {
+    {
       int stage = 0; uint32_t phase = 0;
       for (int item = blockIdx.x; item < num_tiles; item += gridDim.x) {
         const int tile = item / g.splits, split = item - tile * g.splits;
@@ -87,24 +89,27 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int kb0 = split * kb_per, kb1 = min(k_blocks_total, kb0 + kb_per);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait_sleep(&empty[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
-          uint8_t* sa = smem + stage * STAGE_BYTES;
-          if (MODE == MODE_TN) {
-            tma_load_2d(sa, &tmA, &full[stage], kb * BK, m_blk * BM);
-            tma_load_2d(sa + A_STAGE_BYTES, &tmB, &full[stage], kb * BK, n_blk * BN);
-          } else {
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
+            uint8_t* sa = smem + stage * STAGE_BYTES;
+            if (MODE == MODE_TN) {
+              tma_load_2d(sa, &tmA, &full[stage], kb * BK, m_blk * BM);
+              tma_load_2d(sa + A_STAGE_BYTES, &tmB, &full[stage], kb * BK, n_blk * BN);
+            } else {
 #pragma unroll
-            for (int a = 0; a < BM / 64; ++a) tma_load_2d(sa + a * ATOM_BYTES, &tmA, &full[stage], m_blk * BM + a * 64, kb * BK);
+              for (int a = 0; a < BM / 64; ++a) tma_load_2d(sa + a * ATOM_BYTES, &tmA, &full[stage], m_blk * BM + a * 64, kb * BK);
 #pragma unroll
-            for (int a = 0; a < BN / 64; ++a)
-              tma_load_2d(sa + A_STAGE_BYTES + a * ATOM_BYTES, &tmB, &full[stage], n_blk * BN + a * 64, kb * BK);
+              for (int a = 0; a < BN / 64; ++a)
+                tma_load_2d(sa + A_STAGE_BYTES + a * ATOM_BYTES, &tmB, &full[stage], n_blk * BN + a * 64, kb * BK);
+            }
           }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, MODE == MODE_WGRAD, MODE == MODE_WGRAD);
       int stage = 0; uint32_t phase = 0;
       int local = 0;
@@ -120,6 +125,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_wait(&full[stage], phase);
           tcgen05_fence_after();
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          if (elect_one()) {
           if (MODE == MODE_TN) {
             const uint64_t adesc = umma_desc_sw128(sa, 16, 1024);
             const uint64_t bdesc = umma_desc_sw128(sa + A_STAGE_BYTES, 16, 1024);
@@ -138,9 +144,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
           umma_commit(&empty[stage]);
+          if (kb == kb1 - 1) umma_commit(&acc_full[as]);
+          }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&acc_full[as]);
       }
     }
   } else if (warp >= EPI_WARP0) {

@@ -145,26 +145,29 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Warps 0 and 1 run their loops converged and hand each TMA / tcgen05 group to one lane with elect.sync (ptxas then
+  // issues UTMALDG / UTCHMMA from uniform registers instead of a per-instruction waterfall loop; tools/umma_bench.cu).
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int tile = pair; tile < num_tiles; tile += n_pairs) {
-        const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
-        const int row_a = m_blk * 2 * BM + (int)rank * BM;
-        const int row_b = n_blk * BN + (int)rank * BNH;
-        for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait_sleep(&empty[stage], phase ^ 1);
+    int stage = 0; uint32_t phase = 0;
+    for (int tile = pair; tile < num_tiles; tile += n_pairs) {
+      const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+      const int row_a = m_blk * 2 * BM + (int)rank * BM;
+      const int row_b = n_blk * BN + (int)rank * BNH;
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait_sleep(&empty[stage], phase ^ 1);
+        if (elect_one()) {
           uint8_t* sa = smem + stage * STAGE_BYTES;
           tma_load_2d_2sm(sa, &tmA, &full[stage], kb * BK, row_a);
           tma_load_2d_2sm(sa + A_BYTES, &tmB, &full[stage], kb * BK, row_b);
           if (leader) mbar_arrive_expect_tx(&full[stage], 2 * STAGE_BYTES);
           else mbar_arrive_cluster(&full[stage], 0);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (leader && lane == 0) {
+    if (leader) {
       constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN, 0, 0);
       int stage = 0; uint32_t phase = 0;
       int local = 0;
@@ -180,12 +183,15 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
           const uint64_t adesc = umma_desc_sw128(sa, 16, 1024);
           const uint64_t bdesc = umma_desc_sw128(sa + A_BYTES, 16, 1024);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) umma_bf16_ss_2cta(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-          umma_commit_2cta(&empty[stage]);
+            for (int k = 0; k < BK / UMMA_K; ++k) umma_bf16_ss_2cta(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            umma_commit_2cta(&empty[stage]);
+            if (kb == k_blocks - 1) umma_commit_2cta(&acc_full[as]);
+          }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit_2cta(&acc_full[as]);
       }
     }
   } else if (warp >= EPI_WARP0) {
