@@ -171,7 +171,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // S_j = Q K_j^T into buffer j % 3; issued three blocks ahead of the P V product of the same buffer
     auto issue_qk = [&](int j) {
       const int st = j % AT_STAGES;
-      mbar_wait(&kv_full[st], (j / AT_STAGES) & 1);
+      mbar_wait_sleep(&kv_full[st], (j / AT_STAGES) & 1);
       tcgen05_fence_after();
       const uint64_t kdesc = umma_desc_sw128(smem_u32(sKV + st * 2 * AT_KV_BYTES), 16, 1024);
       if (elect_one()) {
@@ -186,7 +186,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     for (int j = 0; j < AT_SBUF && j < n_kv; ++j) issue_qk(j);
     for (int j = 0; j < n_kv; ++j) {
       const int st = j % AT_STAGES, b = j % AT_SBUF;
-      mbar_wait(&p_ready[b], (j / AT_SBUF) & 1);           // P_j in TMEM (over S_j), O rescaled if needed
+      mbar_wait_sleep(&p_ready[b], (j / AT_SBUF) & 1);     // P_j in TMEM (over S_j), O rescaled if needed
       tcgen05_fence_after();
       // V stage: 64 key rows x 128 B (64 head-dim values) -> MN-major B operand, 8-row groups 1024 B apart
       const uint64_t vdesc = umma_desc_sw128(smem_u32(sKV + st * 2 * AT_KV_BYTES + AT_KV_BYTES), 1024, 1024);

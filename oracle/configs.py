@@ -32,6 +32,11 @@ CONFIGS = {
     # 4-layer toy with Whisper's structure: used for committed golden vectors (small weights)
     "micro": PathConfig("micro", 80, 128, 2, 256, 4, [0, 1, 2, 3], 2, qf_ffn=3072, prompt_size=64, d_llm=256, vocab=512,
                         encoder_model_id="openai/whisper-tiny"),
+    # the flagship's exact layer shapes (d 1280, 20 heads, ffn 5120, 128 mels, 1500 positions, d_llm 4096) with only two
+    # encoder layers / one Q-Former layer so that the CPU oracle finishes in seconds: pins every flagship GEMM / attention
+    # shape against the oracle, which the 32-layer model cannot do within the test budget
+    "l3_slim": PathConfig("l3_slim", 128, 1280, 20, 5120, 2, [0, 1], 1, d_llm=4096, vocab=1024,
+                          encoder_model_id="openai/whisper-large-v3"),
     # openai/whisper-tiny + Qformer 2L -> Qwen3-0.6B dims (desta25_debug.yaml)
     "debug": PathConfig("debug", 80, 384, 6, 1536, 4, [0, 1, 2, 3], 2, d_llm=1024, vocab=151936,
                         encoder_model_id="openai/whisper-tiny"),
