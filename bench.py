@@ -289,7 +289,14 @@ def run_ours(args):
                "achieved": round(v["work"] / (v["ms"] * 1e-3) / (1e12 if v["unit"] == "flop" else 1e9), 1),
                "unit": "TFLOP/s" if v["unit"] == "flop" else "GB/s"} for k, v in prof.items()}
     gm = {"work": sum(prof[k]["work"] for k in ("gemm", "gemm_wgrad") if k in prof),
-          "ms": sum(prof[k]["ms"] for k in ("gemm", "gemm_wgrad") if k in prof)}
+          "ms": sum(prof[k]["ms"] for k in ("gemm", "gemm_wgrad") if k in prof),
+          "bytes": sum(prof[k]["bytes"] for k in ("gemm", "gemm_wgrad") if k in prof),
+          "calls": sum(prof[k]["calls"] for k in ("gemm", "gemm_wgrad") if k in prof)}
+    # DRAM traffic of the same kernel from the committed ncu capture of this command (per launch, like `achieved`)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r1d_gemm_traffic.json")
+    if os.path.exists(tpath) and not train and args.workload == "large_v3_llama" and n == 64:
+        traffic = json.load(open(tpath))["dram_bytes_per_launch_avg"]
     gemm_tflops = gm["work"] / (gm["ms"] * 1e-3) / 1e12
     step_s = ms * 1e-3 / args.steps
     value = 30.0 * n * world / step_s
@@ -312,9 +319,12 @@ def run_ours(args):
                 "d2h_bytes_per_step": out_host.numel() * 2, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "gemm_bf16_tn_2cta_kernel (all GEMM launches of one step)",
+        "roofline": {"bound": "tensor", "kernel": "gemm_bf16_tn_2cta_kernel (per launch, averaged over the GEMM launches of one step)",
                      "achieved": round(gemm_tflops, 1), "peak": tf_sust, "unit": "TFLOP/s",
-                     "frac": round(gemm_tflops / tf_sust, 4), "traffic": None, "peak_kind": f"{peak_kind} sustained bf16",
+                     "frac": round(gemm_tflops / tf_sust, 4), "traffic": traffic,
+                     "algorithmic_bytes": round(gm["bytes"] / max(gm["calls"], 1)), "launches_per_step": gm["calls"],
+                     "avg_launch_ms": round(gm["ms"] / max(gm["calls"], 1), 4), "flop_per_launch": round(gm["work"] / max(gm["calls"], 1)),
+                     "peak_kind": f"{peak_kind} sustained bf16 (cuBLAS under the power cap; burst {tf_burst})",
                      "share_of_step": round(gm["ms"] / total_ms, 4)},
         "step_tensor_frac": round(flops_clip * n / step_s / 1e12 / tf_sust, 4),
         "kernels": fam,

@@ -52,6 +52,18 @@ __device__ __forceinline__ void reg_fence32(uint32_t (&v)[32]) {
 
 struct SoftmaxAcc { float l0, l1, m0, m1; };
 
+#ifdef DESTA_ATTN_TRACE
+// Debug build only (tools/attn_trace.py): per-CTA cycle accounting of the MMA warp and of softmax warp 2.
+__device__ long long g_attn_trace[8];
+#define TRACE_T0() const long long _t0 = clock64()
+#define TRACE_ADD(slot) do { trace_acc[slot] += clock64() - _t0; } while (0)
+#define TRACE_FLUSH() do { if (lane == 0) for (int _i = 0; _i < 8; ++_i) if (trace_acc[_i]) atomicAdd((unsigned long long*)&g_attn_trace[_i], (unsigned long long)trace_acc[_i]); } while (0)
+#else
+#define TRACE_T0()
+#define TRACE_ADD(slot)
+#define TRACE_FLUSH()
+#endif
+
 // 32 score columns (one TMEM chunk held in registers) of one query row: p = exp2(c*s - mc) packed as bf16 pairs into
 // pk; running row sum / row max accumulated in `acc`.  MASKED (ragged last key block only) selects -inf for padded keys
 // with predicated selects - no per-element branches.
@@ -123,6 +135,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * AT_BQ, head = blockIdx.y, batch = blockIdx.z;
+#ifdef DESTA_ATTN_TRACE
+  long long trace_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
   const int n_kv = (a.Tk + AT_BKV - 1) / AT_BKV;
 
   if (a.kv_rows < AT_BKV) {   // short key sequences: rows the TMA box never writes must read as zeros (P = 0 there)
@@ -171,7 +186,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // S_j = Q K_j^T into buffer j % 3; issued three blocks ahead of the P V product of the same buffer
     auto issue_qk = [&](int j) {
       const int st = j % AT_STAGES;
-      mbar_wait_sleep(&kv_full[st], (j / AT_STAGES) & 1);
+      { TRACE_T0(); mbar_wait_sleep(&kv_full[st], (j / AT_STAGES) & 1); TRACE_ADD(0); }
       tcgen05_fence_after();
       const uint64_t kdesc = umma_desc_sw128(smem_u32(sKV + st * 2 * AT_KV_BYTES), 16, 1024);
       if (elect_one()) {
@@ -183,10 +198,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       __syncwarp();
     };
     mbar_wait(q_full, 0);
+    TRACE_T0();
     for (int j = 0; j < AT_SBUF && j < n_kv; ++j) issue_qk(j);
     for (int j = 0; j < n_kv; ++j) {
       const int st = j % AT_STAGES, b = j % AT_SBUF;
-      mbar_wait_sleep(&p_ready[b], (j / AT_SBUF) & 1);     // P_j in TMEM (over S_j), O rescaled if needed
+      { TRACE_T0(); mbar_wait_sleep(&p_ready[b], (j / AT_SBUF) & 1); TRACE_ADD(1); }     // P_j in TMEM (over S_j), O rescaled if needed
       tcgen05_fence_after();
       // V stage: 64 key rows x 128 B (64 head-dim values) -> MN-major B operand, 8-row groups 1024 B apart
       const uint64_t vdesc = umma_desc_sw128(smem_u32(sKV + st * 2 * AT_KV_BYTES + AT_KV_BYTES), 1024, 1024);
@@ -201,6 +217,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       __syncwarp();
       if (j + AT_SBUF < n_kv) issue_qk(j + AT_SBUF);   // in-order tensor pipe: overwrites buffer b after P_j V_j
     }
+    TRACE_ADD(3);
   } else {
     // ---- softmax warps: TMEM lane quarter = warp % 4, one query row per thread ----
     const int quarter = warp & 3;
@@ -250,7 +267,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tmem_wait_ld();                                   // cb
       reg_fence32(cb);
       if (j + 1 < n_kv) {
-        mbar_wait(&s_full[(j + 1) % AT_SBUF], ((j + 1) / AT_SBUF) & 1);
+        { TRACE_T0(); mbar_wait(&s_full[(j + 1) % AT_SBUF], ((j + 1) / AT_SBUF) & 1); if (warp == 2) TRACE_ADD(2); if (warp == 4) TRACE_ADD(5); if (warp == 5) TRACE_ADD(6); if (warp == 3) TRACE_ADD(7); }
         tcgen05_fence_after();
         tmem_ld_32x32(tmem_base + ((j + 1) % AT_SBUF) * AT_BKV + lane_off, na);
       }
@@ -285,6 +302,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       l_run += l_blk;
     };
     uint32_t ra[32], rb[32], rc[32];
+    TRACE_T0();
     mbar_wait(&s_full[0], 0);
     tcgen05_fence_after();
     tmem_ld_32x32(tmem_base + lane_off, ra);
@@ -295,6 +313,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tmem_wait_st();                 // the last P (and a rescaled O) have landed in TMEM
     tcgen05_fence_before();         // orders this thread's TMEM accesses before the MMA warp's next MMAs
     mbar_arrive(&p_ready[(n_kv - 1) % AT_SBUF]);
+    if (warp == 2) TRACE_ADD(4);
     // ---- epilogue: O / l -> bf16, one 128-byte row per thread ----
     mbar_wait(&pv_done[(n_kv - 1) % AT_SBUF], ((n_kv - 1) / AT_SBUF) & 1);
     tcgen05_fence_after();
@@ -320,6 +339,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
     }
   }
+  TRACE_FLUSH();
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -338,6 +358,14 @@ static int make_qkv_tmap(CUtensorMap* m, const void* base, int heads, int T, int
 }  // namespace desta
 
 using namespace desta;
+
+#ifdef DESTA_ATTN_TRACE
+extern "C" int desta_attention_trace(long long* host8, int reset) {
+  long long z[8] = {0};
+  if (reset) return cudaMemcpyToSymbol(g_attn_trace, z, sizeof(z)) == cudaSuccess ? 0 : -2;
+  return cudaMemcpyFromSymbol(host8, g_attn_trace, sizeof(z)) == cudaSuccess ? 0 : -2;
+}
+#endif
 
 extern "C" int desta_attention(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo,
                                int batch, int heads, int Tq, int Tk, float scale, float* lse, const desta_dropout* drop,

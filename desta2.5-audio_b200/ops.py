@@ -26,17 +26,19 @@ def stop_profile():
     rec, _PROFILE = _PROFILE, None
     torch.cuda.synchronize()
     out = {}
-    for fam, work, unit, e0, e1 in rec:
-        d = out.setdefault(fam, {"ms": 0.0, "work": 0.0, "unit": unit, "calls": 0})
+    for fam, work, unit, e0, e1, nbytes in rec:
+        d = out.setdefault(fam, {"ms": 0.0, "work": 0.0, "unit": unit, "calls": 0, "bytes": 0.0})
         d["ms"] += e0.elapsed_time(e1)
         d["work"] += work
+        d["bytes"] += nbytes
         d["calls"] += 1
     return out
 
 
 class _op:
-    def __init__(self, family, launches, work=0.0, unit="flop"):
+    def __init__(self, family, launches, work=0.0, unit="flop", nbytes=0.0):
         self.family, self.launches, self.work, self.unit = family, launches, work, unit
+        self.nbytes = nbytes if unit == "flop" else work      # algorithmic DRAM bytes of the launch
 
     def __enter__(self):
         STATS["launches"] += self.launches
@@ -48,7 +50,7 @@ class _op:
     def __exit__(self, *exc):
         if _PROFILE is not None and exc[0] is None:
             self.e1.record()
-            _PROFILE.append((self.family, self.work, self.unit, self.e0, self.e1))
+            _PROFILE.append((self.family, self.work, self.unit, self.e0, self.e1, self.nbytes))
         return False
 
 
@@ -95,7 +97,10 @@ def gemm(a, w, bias=None, *, out_bf16=None, out_f32=None, resid=None, pos=None, 
         assert pos.shape[1] == N and pos.is_contiguous()
         ep.pos, ep.pos_rows = pos.data_ptr(), pos.shape[0]
     ep.scale, ep.scale_cols, ep.gelu = float(scale), int(scale_cols), int(bool(gelu))
-    with _op("gemm", 1, 2.0 * M * N * K):
+    # algorithmic bytes: A and W read once, every output written once, the residual read once
+    nbytes = 2.0 * (M * K + N * K) + M * N * ((4 if out_f32 is not None else 0) + (2 if out_bf16 is not None else 0)
+                                              + (4 if resid is not None else 0))
+    with _op("gemm", 1, 2.0 * M * N * K, nbytes=nbytes):
         check(lib().desta_gemm_bf16(_p(a), a.stride(0), _p(w), w.stride(0), M, N, K, ctypes.byref(ep), _stream()), "desta_gemm_bf16")
 
 
@@ -176,7 +181,7 @@ def gemm_wgrad(dy, x, dw):
     M, Nout = dy.shape
     M2, Kin = x.shape
     assert M == M2 and dw.shape == (Nout, Kin) and dy.stride(1) == 1 and x.stride(1) == 1 and dw.stride(1) == 1
-    with _op("gemm_wgrad", 1, 2.0 * M * Nout * Kin):
+    with _op("gemm_wgrad", 1, 2.0 * M * Nout * Kin, nbytes=2.0 * M * (Nout + Kin) + 8.0 * Nout * Kin):
         check(lib().desta_gemm_bf16_wgrad(_p(dy), dy.stride(0), _p(x), x.stride(0), M, Nout, Kin, _p(dw), dw.stride(0), _stream()),
               "desta_gemm_bf16_wgrad")
 

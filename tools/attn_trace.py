@@ -1,0 +1,61 @@
+"""Cycle accounting of the attention kernel's warp roles (debug build with -DDESTA_ATTN_TRACE).
+Build here:  python tools/attn_trace.py build      Run on the GPU box:  python tools/attn_trace.py"""
+import ctypes
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "desta2.5-audio_b200", "csrc")
+OUT = os.path.join(ROOT, "tools", "_bin", "libdesta_trace.so")
+SOURCES = ["api.cu", "gemm.cu", "gemm2.cu", "attention.cu", "attention_bwd.cu", "elementwise.cu", "elementwise_bwd.cu", "logmel.cu", "splice.cu"]
+
+
+def build():
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared",
+           "-DDESTA_ATTN_TRACE", "-I", os.path.join(ROOT, "include"), "-I", CSRC, *[os.path.join(CSRC, s) for s in SOURCES],
+           "-o", OUT, "-lcudart_static", "-ldl", "-lrt", "-lpthread"]
+    subprocess.run(cmd, check=True)
+    print(OUT)
+
+
+def run():
+    import torch
+    L = ctypes.CDLL(OUT)
+    B, H, T = 64, 20, 1500
+    d = H * 64
+    vp = ctypes.c_void_p
+    names = ["MMA warp: wait kv_full", "MMA warp: wait p_ready", "softmax warp 2: wait s_full", "MMA warp: total loop", "softmax warp 2: total loop",
+             "softmax warp 4 (SMSP 0, with TMA warp): wait s_full", "softmax warp 5 (SMSP 1, with MMA warp): wait s_full",
+             "softmax warp 3 (SMSP 3): wait s_full"]
+    ctas, blocks = 12 * H * B, 24
+    # layouts: (label, row pitch in elements, junk bytes allocated before the buffer to shift its address)
+    for label, pitch, junk in [("fused qkv pitch 3840", 3 * d, 0), ("pitch 3840, base shifted 3 MB + 512 B", 3 * d, 3 * 2 ** 20 + 512),
+                               ("pitch 3840 + 64", 3 * d + 64, 0), ("pitch 4096", 4096, 0), ("pitch 3840 again", 3 * d, 0)]:
+        pad = torch.empty(junk, dtype=torch.uint8, device="cuda") if junk else None
+        buf_t = torch.empty(B * T, pitch, device="cuda", dtype=torch.bfloat16)
+        buf_t.normal_(0, 0.5)
+        out = torch.empty(B * T, d, device="cuda", dtype=torch.bfloat16)
+        args = [vp(buf_t.data_ptr()), pitch, vp(buf_t.data_ptr() + 2 * d), pitch, vp(buf_t.data_ptr() + 4 * d), pitch, vp(out.data_ptr()), d,
+                B, H, T, T, ctypes.c_float(1.0), None, None, vp(torch.cuda.current_stream().cuda_stream)]
+        for _ in range(3):
+            assert L.desta_attention(*args) == 0
+        torch.cuda.synchronize()
+        buf = (ctypes.c_longlong * 8)()
+        L.desta_attention_trace(buf, 1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            assert L.desta_attention(*args) == 0
+        e1.record()
+        torch.cuda.synchronize()
+        L.desta_attention_trace(buf, 0)
+        print(f"{label}: {e0.elapsed_time(e1) / 5:.3f} ms  (qkv at 0x{buf_t.data_ptr():x})  per key block per CTA: "
+              f"kv_full wait {buf[0] / ctas / blocks / 5:.0f}, p_ready wait {buf[1] / ctas / blocks / 5:.0f}, MMA loop {buf[3] / ctas / blocks / 5:.0f}, "
+              f"softmax s_full wait {buf[2] / ctas / blocks / 5:.0f}, softmax loop {buf[4] / ctas / blocks / 5:.0f}", flush=True)
+        del buf_t, out, pad
+
+
+if __name__ == "__main__":
+    build() if sys.argv[1:] == ["build"] else run()
