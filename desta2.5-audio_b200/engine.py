@@ -61,6 +61,10 @@ class EncoderPack:
         self.conv2_w = _bf16(get("conv2.weight").permute(0, 2, 1).reshape(d, 3 * d))
         self.conv2_b = _f32(get("conv2.bias"))
         self.pos = _f32(get("embed_positions.weight")[: dims.max_pos])
+        # final encoder LayerNorm: NOT on the tap path (modeling_desta25.py:577-598 never applies it) but needed for the
+        # HF-compatible encoder output that the ASR pass (whisper.generate, :1586) consumes
+        self.final_ln_w = _f32(get("layer_norm.weight")) if ENC + "layer_norm.weight" in sd else None
+        self.final_ln_b = _f32(get("layer_norm.bias")) if ENC + "layer_norm.bias" in sd else None
         self.layers = []
         for i in range(dims.n_layers):
             p = f"layers.{i}."

@@ -24,6 +24,9 @@ def install(model, wrap_processor: bool = True):
                                       batch_features, batch_transcription_ids, batch_start_positions)
 
     model._prepare_inputs_for_llm = types.MethodType(_prepare_inputs_for_llm, model)
+    if hasattr(model.perception.whisper, "generate"):
+        # ASR pass of generate() (:1582-1601): encoder through the same kernels, shared with the perception call
+        model.perception.wrap_whisper_generate()
     if wrap_processor and getattr(model, "processor", None) is not None and not isinstance(model.processor, WaveformProcessor):
         model.processor = WaveformProcessor(model.processor)
     return model

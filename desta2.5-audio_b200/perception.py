@@ -37,6 +37,7 @@ class WhisperPerceptionB200(nn.Module):
         self._t_versions = None
         self._ws = {}
         self._train = {}
+        self._enc_cache = None      # (input clone, N): encoder state of the last whisper.generate() call, see share_encoder
 
     # ---- reference-compatible constructor: wrap an existing reference WhisperPerception ----
     @classmethod
@@ -112,23 +113,75 @@ class WhisperPerceptionB200(nn.Module):
         return x.to(device=dev, non_blocking=True).transpose(1, 2).to(torch.bfloat16).contiguous()
 
     @torch.no_grad()
-    def forward_features(self, input_features: torch.Tensor) -> torch.Tensor:
-        enc, con = self._packs()
+    def _run_encoder(self, input_features: torch.Tensor):
+        """Encoder forward into the workspace (taps + residual stream).  If the previous call was the ASR pass of
+        `generate()` on exactly these clips (scope row n2: modeling_desta25.py:1582-1601 re-encodes the same audio with
+        whisper.generate), the workspace already holds their encoder state and the 2.27 TFLOP/clip are not repeated."""
+        enc, _ = self._packs()
         N = input_features.size(0)
         ws = self._workspace(N)
-        mel_tm = self.mel_time_major(input_features)
-        engine.encoder_forward(enc, self.dims, ws, mel_tm)
-        out = torch.empty(N * self.dims.prompt_size, self.dims.d_llm, dtype=torch.float32, device=mel_tm.device)
+        cached, self._enc_cache = self._enc_cache, None
+        if (cached is not None and cached[1] == N and cached[0].shape == input_features.shape
+                and cached[0].dtype == input_features.dtype and cached[0].device == input_features.device
+                and torch.equal(cached[0], input_features)):
+            self.encoder_runs_skipped = getattr(self, "encoder_runs_skipped", 0) + 1
+            return ws
+        engine.encoder_forward(enc, self.dims, ws, self.mel_time_major(input_features))
+        return ws
+
+    @torch.no_grad()
+    def forward_features(self, input_features: torch.Tensor) -> torch.Tensor:
+        _, con = self._packs()
+        N = input_features.size(0)
+        ws = self._run_encoder(input_features)
+        out = torch.empty(N * self.dims.prompt_size, self.dims.d_llm, dtype=torch.float32, device=ws.h.device)
         engine.connector_forward(con, self.dims, ws, out)
         return out.view(N, self.dims.prompt_size, self.dims.d_llm)
 
     def taps(self, input_features: torch.Tensor):
         """The four tapped hidden states (bf16 [N, 1500, d]) — exposed for parity tests."""
-        enc, _ = self._packs()
         N = input_features.size(0)
-        ws = self._workspace(N)
-        engine.encoder_forward(enc, self.dims, ws, self.mel_time_major(input_features))
+        ws = self._run_encoder(input_features)
         return [ws.taps[k].view(N, self.dims.max_pos, self.dims.d_model) for k in range(len(self.dims.tap_layers))]
+
+    @torch.no_grad()
+    def encoder_outputs(self, input_features: torch.Tensor, share: bool = False):
+        """HF-compatible WhisperEncoder output — `layer_norm(h_last)`, [N, 1500, d] in the whisper module's dtype — from
+        the same kernels ($TF/models/whisper/modeling_whisper.py: WhisperEncoder.forward ends with self.layer_norm).
+        `share=True` remembers the input so that the next perception call on the same clips skips its encoder run."""
+        from transformers.modeling_outputs import BaseModelOutput
+        enc, _ = self._packs()
+        if enc.final_ln_w is None:
+            raise RuntimeError("the wrapped Whisper encoder has no final layer_norm parameters")
+        N = input_features.size(0)
+        dev = self._device()
+        x = input_features.to(dev) if input_features.device != dev else input_features
+        ws = self._run_encoder(x)
+        out = torch.empty(N * self.dims.max_pos, self.dims.d_model, dtype=torch.float32, device=dev)
+        ops.layernorm(ws.h, enc.final_ln_w, enc.final_ln_b, 1e-5, out_f32=out)
+        if share:
+            self._enc_cache = (x.clone(), N)
+        dtype = self.whisper.model.encoder.conv1.weight.dtype
+        return BaseModelOutput(last_hidden_state=out.view(N, self.dims.max_pos, self.dims.d_model).to(dtype))
+
+    def wrap_whisper_generate(self):
+        """Route the ASR pass through this encoder: `perception.whisper.generate(input_features=...)` keeps its signature
+        (modeling_desta25.py:1586-1590) but the encoder runs on libdesta_b200.so — from the padded waveform of the
+        processor shim or from a log-mel — and HF's generate only decodes from `encoder_outputs`."""
+        whisper = self.whisper
+        if getattr(whisper, "_desta_b200_generate", None) is not None:
+            return
+        original = whisper.generate
+        perception = self
+
+        def generate(input_features=None, *args, **kwargs):
+            if input_features is None or "encoder_outputs" in kwargs:
+                return original(input_features, *args, **kwargs)
+            kwargs["encoder_outputs"] = perception.encoder_outputs(input_features, share=True)
+            return original(*args, **kwargs)
+
+        whisper._desta_b200_generate = original
+        whisper.generate = generate
 
     def forward(self, input_features: torch.Tensor, attention_mask: Optional[torch.Tensor] = None,
                 transcription_embeddings_list: Optional[List[torch.Tensor]] = None, **kwargs):
