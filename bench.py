@@ -234,16 +234,38 @@ def run_ours(args):
         with torch.no_grad():
             return prepare_inputs_for_llm(table, perception, ids_dev, None, wave_dev, trans, positions)
 
+    # e2e: the public call fed from PINNED HOST memory through the double-buffered stager (desta_b200.staging, scope row
+    # n1): the H2D copy of step k+1 runs on the copy stream while the kernels of step k execute, the D2H read of the
+    # result runs on its own stream; every step still moves its own inputs and outputs (bytes counted below).
+    from desta_b200.staging import WaveformStager
+    stager = WaveformStager(n, dev, slots=2)
+    for sl in range(2):
+        stager.fill(sl, wave_host.numpy())
+    d2h_stream = torch.cuda.Stream(dev)
+    e2e_state = {"k": 0, "primed": False}
+
     def step_e2e():
-        wv = wave_host.to(dev, non_blocking=True)
+        k = e2e_state["k"]
+        slot = k % 2
+        if not e2e_state["primed"]:
+            stager.submit(slot)
+            e2e_state["primed"] = True
+        stager.submit((k + 1) % 2)                      # next step's inputs: in flight during this step's kernels
+        wv, _ = stager.acquire(slot)
         ii = ids_host.to(dev, non_blocking=True)
         if train:
             emb = train_step(ii, wv)
+        else:
+            with torch.no_grad():
+                emb = prepare_inputs_for_llm(table, perception, ii, None, wv, trans, positions)
+        stager.release(slot)
+        done = torch.cuda.Event()
+        done.record()
+        d2h_stream.wait_event(done)
+        with torch.cuda.stream(d2h_stream):
             out_host.copy_(emb.detach(), non_blocking=True)
-            return emb
-        with torch.no_grad():
-            emb = prepare_inputs_for_llm(table, perception, ii, None, wv, trans, positions)
-            out_host.copy_(emb, non_blocking=True)
+        emb.record_stream(d2h_stream)
+        e2e_state["k"] = k + 1
         return emb
 
     def timed(fn, steps):
@@ -256,6 +278,8 @@ def run_ours(args):
         e0.record()
         for _ in range(steps):
             fn()
+        torch.cuda.current_stream().wait_stream(d2h_stream)      # the steps' D2H reads and H2D copies belong to the timed region
+        torch.cuda.current_stream().wait_stream(stager.copy_stream)
         e1.record()
         torch.cuda.synchronize()
         t1 = time.time()

@@ -11,24 +11,34 @@ N_SAMPLES = 480000
 SAMPLING_RATE = 16000
 
 
-def pad_or_truncate_batch(raw_speech) -> np.ndarray:
-    """$TF/models/whisper/feature_extraction_whisper.py:296-320: first 480000 samples, zero right-padding."""
+def pad_or_truncate_batch(raw_speech, out=None, lengths=None):
+    """$TF/models/whisper/feature_extraction_whisper.py:296-320: first 480000 samples, zero right-padding.
+    Returns (waveforms [n, 480000] fp32, valid lengths [n] int32); with `out` / `lengths` (e.g. rows of a pinned staging
+    slot, see desta_b200.staging) the clips are written in place and views of the first n rows are returned."""
     if isinstance(raw_speech, np.ndarray) and raw_speech.ndim == 2:
         clips = list(raw_speech)
     elif isinstance(raw_speech, (list, tuple)) and len(raw_speech) and isinstance(raw_speech[0], (np.ndarray, list, tuple)):
         clips = list(raw_speech)
+    elif isinstance(raw_speech, (list, tuple)) and len(raw_speech) == 0:
+        clips = []
     else:
         clips = [raw_speech]
-    out = np.zeros((len(clips), N_SAMPLES), dtype=np.float32)
-    lengths = np.zeros(len(clips), dtype=np.int32)
+    n = len(clips)
+    if out is None:
+        out = np.zeros((n, N_SAMPLES), dtype=np.float32)
+    else:
+        assert out.dtype == np.float32 and out.shape[0] >= n and out.shape[1] == N_SAMPLES
+    if lengths is None:
+        lengths = np.zeros(n, dtype=np.int32)
     for i, c in enumerate(clips):
-        c = np.asarray(c, dtype=np.float32).reshape(-1)
+        c = np.asarray(c, dtype=np.float32)
         if c.ndim != 1:
             raise ValueError("Only mono-channel audio is supported")
-        n = min(c.shape[0], N_SAMPLES)
-        out[i, :n] = c[:n]
-        lengths[i] = n
-    return out, lengths
+        m = min(c.shape[0], N_SAMPLES)
+        out[i, :m] = c[:m]
+        out[i, m:] = 0.0
+        lengths[i] = m
+    return out[:n], lengths[:n]
 
 
 class _Features(dict):

@@ -122,3 +122,25 @@ def test_gradient_reaches_connector_through_the_splice():
     emb.backward(g)
     gw = model.perception.connector.proj[1].bias.grad
     assert gw is not None and torch.allclose(gw, torch.full_like(gw, 64.0), rtol=2e-2)
+
+
+def test_stager_double_buffer_feeds_the_path():
+    """Scope row n1: batches staged through pinned slots + copy stream give the same features as direct transfers."""
+    from desta_b200.staging import WaveformStager, stage_batches
+    cfg = CONFIGS["micro"]
+    W = make_weights(cfg, seed=11, with_table=False)
+    p = build_perception(cfg, W)
+    waves = synth_waves(seed=7, kinds=KINDS)
+    batches = [waves[0:2], [w.tolist() for w in waves[2:4]], waves[4:6], waves[1:3]]
+    st = WaveformStager(2, "cuda", slots=2)
+    got = []
+    with torch.no_grad():
+        for wave, lens in stage_batches(st, batches):
+            assert wave.is_cuda and wave.shape == (2, 480000) and lens.dtype == torch.int32
+            feats, _ = p(input_features=wave)
+            got.append(feats.clone())
+        for k, b in enumerate(batches):
+            direct = torch.from_numpy(np.stack([o_mel.pad_or_truncate(np.asarray(w, np.float32)) for w in b])).cuda()
+            want, _ = p(input_features=direct)
+            assert torch.equal(got[k], want), k
+    assert st.h2d_bytes == 4 * 2 * (480000 * 4 + 4)

@@ -1,0 +1,52 @@
+"""Host logic of the collate-side staging (scope row n1): pad / truncate into a reusable slot equals the oracle's
+restatement of WhisperFeatureExtractor's padding ($TF/models/whisper/feature_extraction_whisper.py:296-320)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import logmel as o_mel
+from oracle.synth import synth_waves
+
+KINDS = ("noise_full", "speechy_12s", "short_3p5s", "silence", "long_31s", "tone_clip")
+
+
+def test_pad_or_truncate_in_place_matches_oracle_and_clears_stale_data():
+    from desta_b200.processor import N_SAMPLES, pad_or_truncate_batch
+    waves = synth_waves(seed=7, kinds=KINDS)
+    want = np.stack([o_mel.pad_or_truncate(w) for w in waves])
+    got, lens = pad_or_truncate_batch(waves)
+    assert got.dtype == np.float32 and np.array_equal(got, want)
+    assert list(lens) == [min(len(w), N_SAMPLES) for w in waves]
+    slot = np.full((8, N_SAMPLES), 7.0, dtype=np.float32)            # a reused slot full of stale samples
+    ln = np.full(8, -1, dtype=np.int32)
+    got2, lens2 = pad_or_truncate_batch([w.tolist() if i == 2 else w for i, w in enumerate(waves)], out=slot, lengths=ln)
+    assert got2.base is slot and np.array_equal(got2, want) and np.array_equal(lens2, lens)
+    assert np.all(slot[6:] == 7.0)                                   # rows beyond the batch are untouched
+    empty, el = pad_or_truncate_batch([])
+    assert empty.shape == (0, N_SAMPLES) and el.shape == (0,)
+    with pytest.raises(ValueError):
+        pad_or_truncate_batch([np.zeros((2, 100), np.float32)])
+
+
+def test_processor_shim_contract():
+    from desta_b200.processor import WaveformProcessor
+    waves = synth_waves(seed=7, kinds=KINDS)[:2]
+    proc = WaveformProcessor()
+    feats = proc(waves, sampling_rate=16000, return_tensors="pt").input_features
+    assert feats.shape == (2, 480000) and feats.dtype == torch.float32
+    assert np.array_equal(feats[1].numpy(), o_mel.pad_or_truncate(waves[1]))
+    with pytest.raises(ValueError, match="sampling rate"):            # same error as WhisperFeatureExtractor.__call__
+        proc(waves, sampling_rate=8000)
+    with pytest.raises(AttributeError):
+        proc.batch_decode                                              # nothing wrapped: delegation has no target
+
+
+def test_stager_host_side_without_cuda():
+    from desta_b200.staging import WaveformStager
+    waves = synth_waves(seed=7, kinds=KINDS)
+    st = WaveformStager(4, "cpu", slots=2, pin=False)
+    assert st.fill(0, waves[:3]) == 3 and st.fill(1, waves[3:6]) == 3
+    assert np.array_equal(st.host[0][:3].numpy(), np.stack([o_mel.pad_or_truncate(w) for w in waves[:3]]))
+    assert st.host_len[1][:3].tolist() == [min(len(w), 480000) for w in waves[3:6]]
+    with pytest.raises(ValueError):
+        st.fill(0, waves[:5])
