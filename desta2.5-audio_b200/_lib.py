@@ -18,6 +18,33 @@ class Dropout(Structure):
     _fields_ = [("thr16", c_uint32), ("scale", c_float), ("seed", c_uint64), ("site", c_uint32)]
 
 
+class Dims(Structure):
+    _fields_ = [("n_mels", c_int), ("d_model", c_int), ("n_heads", c_int), ("ffn", c_int), ("n_layers", c_int),
+                ("n_taps", c_int), ("tap_layers", c_int * 8), ("qf_layers", c_int), ("qf_ffn", c_int), ("prompt_size", c_int),
+                ("d_llm", c_int), ("max_pos", c_int)]
+
+
+class EncLayer(Structure):
+    _fields_ = [(n, c_void_p) for n in ("ln1_w", "ln1_b", "qkv_w", "qkv_b", "o_w", "o_b", "ln2_w", "ln2_b", "fc1_w", "fc1_b",
+                                        "fc2_w", "fc2_b")]
+
+
+class EncoderWeights(Structure):
+    _fields_ = [("conv1_w", c_void_p), ("conv1_b", c_void_p), ("conv2_w", c_void_p), ("conv2_b", c_void_p), ("pos", c_void_p),
+                ("layers", POINTER(EncLayer))]
+
+
+class QfLayer(Structure):
+    _fields_ = [(n, c_void_p) for n in ("s_qkv_w", "s_qkv_b", "s_o_w", "s_o_b", "s_ln_w", "s_ln_b", "c_q_w", "c_q_b", "c_o_w",
+                                        "c_o_b", "c_ln_w", "c_ln_b", "f1_w", "f1_b", "f2_w", "f2_b", "f_ln_w", "f_ln_b")]
+
+
+class ConnectorWeights(Structure):
+    _fields_ = [("layer_weights", c_void_p), ("prompts", c_void_p), ("kv_w", c_void_p), ("kv_b", c_void_p),
+                ("proj_ln_w", c_void_p), ("proj_ln_b", c_void_p), ("proj_w", c_void_p), ("proj_b", c_void_p),
+                ("layers", POINTER(QfLayer))]
+
+
 class SpliceDesc(Structure):
     _fields_ = [("prompt", c_int32), ("start", c_int32), ("n_trans", c_int32), ("trans_off", c_int32)]
 
@@ -50,6 +77,12 @@ EXPORTS = {
     "desta_splice_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "desta_im2col_k3": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "desta_layer_mix": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "desta_encoder_workspace_bytes": (c_size_t, [POINTER(Dims), c_int]),
+    "desta_encoder_fwd": (c_int, [POINTER(Dims), POINTER(EncoderWeights), c_void_p, c_int, c_void_p, c_size_t, c_void_p, c_void_p,
+                                  c_void_p]),
+    "desta_connector_workspace_bytes": (c_size_t, [POINTER(Dims), c_int]),
+    "desta_connector_fwd": (c_int, [POINTER(Dims), POINTER(ConnectorWeights), c_void_p, c_int, c_void_p, c_size_t, c_void_p,
+                                    c_void_p]),
     "desta_splice": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, POINTER(SpliceDesc), c_int, c_void_p, c_void_p, c_int,
                              c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
 }

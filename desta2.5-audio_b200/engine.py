@@ -12,7 +12,10 @@ from typing import Dict, List
 
 import torch
 
+import ctypes
+
 from . import ops
+from ._lib import ConnectorWeights, Dims, EncLayer, EncoderWeights, QfLayer, check, lib
 
 ENC = "whisper.model.encoder."
 CON = "connector."
@@ -35,6 +38,11 @@ class PathDims:
     @property
     def head_dim(self):
         return self.d_model // self.n_heads
+
+    def c_struct(self) -> Dims:
+        taps = (ctypes.c_int * 8)(*self.tap_layers)
+        return Dims(self.n_mels, self.d_model, self.n_heads, self.ffn, self.n_layers, len(self.tap_layers), taps, self.qf_layers,
+                    self.qf_ffn, self.prompt_size, self.d_llm, self.max_pos)
 
 
 def _bf16(t):
@@ -80,6 +88,12 @@ class EncoderPack:
                 fc2_w=_bf16(get(p + "fc2.weight")), fc2_b=_f32(get(p + "fc2.bias")),
             )
             self.layers.append(L)
+        # desta_encoder_weights for the native schedule (desta_encoder_fwd); the tensors above keep the memory alive
+        self._c_layers = (EncLayer * dims.n_layers)(*[
+            EncLayer(*[L[k].data_ptr() for k in ("ln1_w", "ln1_b", "qkv_w", "qkv_b", "o_w", "o_b", "ln2_w", "ln2_b", "fc1_w",
+                                                 "fc1_b", "fc2_w", "fc2_b")]) for L in self.layers])
+        self.c_weights = EncoderWeights(self.conv1_w.data_ptr(), self.conv1_b.data_ptr(), self.conv2_w.data_ptr(),
+                                        self.conv2_b.data_ptr(), self.pos.data_ptr(), self._c_layers)
 
 
 class ConnectorPack:
@@ -119,30 +133,65 @@ class ConnectorPack:
         self.kv_b = _f32(torch.cat(kv_b, 0))
         self.proj_ln_w, self.proj_ln_b = _f32(get("proj.0.weight")), _f32(get("proj.0.bias"))
         self.proj_w, self.proj_b = _bf16(get("proj.1.weight")), _f32(get("proj.1.bias"))
+        names = ("s_qkv_w", "s_qkv_b", "s_o_w", "s_o_b", "s_ln_w", "s_ln_b", "c_q_w", "c_q_b", "c_o_w", "c_o_b", "c_ln_w", "c_ln_b",
+                 "f1_w", "f1_b", "f2_w", "f2_b", "f_ln_w", "f_ln_b")
+        self._c_layers = (QfLayer * dims.qf_layers)(*[QfLayer(*[L[k].data_ptr() for k in names]) for L in self.layers])
+        self.c_weights = ConnectorWeights(self.layer_weights.data_ptr(), self.prompts.data_ptr(), self.kv_w.data_ptr(),
+                                          self.kv_b.data_ptr(), self.proj_ln_w.data_ptr(), self.proj_ln_b.data_ptr(),
+                                          self.proj_w.data_ptr(), self.proj_b.data_ptr(), self._c_layers)
 
 
 class Workspace:
-    """Caller-owned device buffers for one batch size (the library allocates nothing)."""
+    """Caller-owned device buffers for one batch size (the library allocates nothing): the outputs of the encoder stage
+    (taps, residual stream), one byte workspace per native stage entry point, and - allocated only when the per-op Python
+    schedule is used (profiling / training) - the individual activation buffers."""
+
+    _PY = ("cols1", "c1", "cols2", "y", "qkv", "ao", "ff", "kv", "x_f32", "x_bf", "q_qkv", "q_ao", "q_tmp", "a_f32", "a_bf", "q_q",
+           "c_f32", "c_bf", "q_ff", "mix", "mix_bf")
 
     def __init__(self, dims: PathDims, N: int, device, keep_for_backward: bool = False):
+        d, T, Q = dims.d_model, dims.max_pos, dims.prompt_size
+        K = len(dims.tap_layers)
+        self.dims, self.N, self.device = dims, N, device
+        self.R = K * N * Q
+        self.h = torch.empty(N * T, d, dtype=torch.float32, device=device)
+        self.taps = torch.empty(K, N * T, d, dtype=torch.bfloat16, device=device)
+        self._c_dims = dims.c_struct()
+        self._enc_ws = None
+        self._con_ws = None
+
+    def native_ws(self, which: str) -> torch.Tensor:
+        attr = "_enc_ws" if which == "encoder" else "_con_ws"
+        if getattr(self, attr) is None:
+            fn = lib().desta_encoder_workspace_bytes if which == "encoder" else lib().desta_connector_workspace_bytes
+            nbytes = fn(ctypes.byref(self._c_dims), self.N)
+            if nbytes == 0:
+                raise ValueError(f"unsupported dims for the native {which} schedule: {lib().desta_last_error().decode()}")
+            setattr(self, attr, torch.empty(nbytes, dtype=torch.uint8, device=self.device))
+        return getattr(self, attr)
+
+    def __getattr__(self, name):
+        if name in Workspace._PY:                       # first use of the per-op schedule: allocate its buffers
+            self._alloc_py()
+            return self.__dict__[name]
+        raise AttributeError(name)
+
+    def _alloc_py(self):
+        dims, N, device = self.dims, self.N, self.device
         d, T, Q = dims.d_model, dims.max_pos, dims.prompt_size
         M = N * T
         K = len(dims.tap_layers)
         bf, f32 = torch.bfloat16, torch.float32
         e = lambda *s, dt=bf: torch.empty(*s, dtype=dt, device=device)  # noqa: E731
-        self.N = N
         self.cols1 = e(N * 2 * T, 3 * dims.n_mels)
         self.c1 = e(N * 2 * T, d)
         self.cols2 = e(M, 3 * d)
-        self.h = e(M, d, dt=f32)
         self.y = e(M, d)
         self.qkv = e(M, 3 * d)
         self.ao = e(M, d)
         self.ff = e(M, dims.ffn)
-        self.taps = e(K, M, d)
         self.kv = e(K * M, dims.qf_layers * 2 * d)
-        R = K * N * Q
-        self.R = R
+        R = self.R
         self.x_f32 = e(R, d, dt=f32)
         self.x_bf = e(R, d)
         self.q_qkv = e(R, 3 * d)
@@ -158,8 +207,38 @@ class Workspace:
         self.mix_bf = e(N * Q, d)
 
 
+def _native_enabled():
+    return ops._PROFILE is None        # the per-family CUDA-event profile of bench.py needs the per-op schedule
+
+
 def encoder_forward(enc: EncoderPack, dims: PathDims, ws: Workspace, mel_tm: torch.Tensor):
-    """mel_tm: bf16 time-major log-mel [N, 3000, n_mels].  Fills ws.taps[k] (bf16 [N*1500, d]) for every tap layer."""
+    """mel_tm: bf16 time-major log-mel [N, 3000, n_mels] -> ws.taps[k] (bf16 [N*1500, d]) and ws.h.  One call of the
+    native schedule desta_encoder_fwd (same launches, same order as encoder_forward_ops below)."""
+    if not _native_enabled():
+        return encoder_forward_ops(enc, dims, ws, mel_tm)
+    ops._cuda(mel_tm, torch.bfloat16)
+    assert mel_tm.is_contiguous() and mel_tm.shape == (ws.N, 2 * dims.max_pos, dims.n_mels)
+    wsb = ws.native_ws("encoder")
+    ops.STATS["launches"] += 4 + 7 * dims.n_layers
+    check(lib().desta_encoder_fwd(ctypes.byref(ws._c_dims), ctypes.byref(enc.c_weights), ops._p(mel_tm), ws.N, ops._p(wsb), wsb.numel(),
+                                  ops._p(ws.taps), ops._p(ws.h), ops._stream()), "desta_encoder_fwd")
+
+
+def connector_forward(con: ConnectorPack, dims: PathDims, ws: Workspace, out_f32: torch.Tensor):
+    """Q-Former over ws.taps -> out_f32 [N*Q, d_llm] through the native schedule desta_connector_fwd (eval mode)."""
+    if not _native_enabled():
+        return connector_forward_ops(con, dims, ws, out_f32)
+    ops._cuda(out_f32, torch.float32)
+    assert out_f32.is_contiguous() and out_f32.shape == (ws.N * dims.prompt_size, dims.d_llm)
+    wsb = ws.native_ws("connector")
+    ops.STATS["launches"] += 2 + 11 * dims.qf_layers + 3
+    check(lib().desta_connector_fwd(ctypes.byref(ws._c_dims), ctypes.byref(con.c_weights), ops._p(ws.taps), ws.N, ops._p(wsb),
+                                    wsb.numel(), ops._p(out_f32), ops._stream()), "desta_connector_fwd")
+    return out_f32
+
+
+def encoder_forward_ops(enc: EncoderPack, dims: PathDims, ws: Workspace, mel_tm: torch.Tensor):
+    """Per-op schedule of the encoder (one C-ABI call per kernel; profiling / reference for the native schedule)."""
     N, d, T = ws.N, dims.d_model, dims.max_pos
     hd = dims.head_dim
     ops.im2col_k3(mel_tm, N, 2 * T, dims.n_mels, 1, ws.cols1)
@@ -182,8 +261,8 @@ def encoder_forward(enc: EncoderPack, dims: PathDims, ws: Workspace, mel_tm: tor
     assert tap_idx == len(dims.tap_layers)
 
 
-def connector_forward(con: ConnectorPack, dims: PathDims, ws: Workspace, out_f32: torch.Tensor):
-    """Q-Former over the taps in ws.taps (all taps batched as K*N sequences) -> out_f32 [N*Q, d_llm]."""
+def connector_forward_ops(con: ConnectorPack, dims: PathDims, ws: Workspace, out_f32: torch.Tensor):
+    """Per-op schedule of the connector: taps in ws.taps (all taps batched as K*N sequences) -> out_f32 [N*Q, d_llm]."""
     N, d, T, Q = ws.N, dims.d_model, dims.max_pos, dims.prompt_size
     K = len(dims.tap_layers)
     hd = dims.head_dim

@@ -138,6 +138,55 @@ int desta_splice(const int64_t* input_ids, const void* table, int64_t vocab, con
 int desta_splice_bwd(const void* grad_out, const desta_splice_desc* descs_dev, int n_desc, int Q, int S, int d, float* dfeats,
                      void* stream);
 
+/* ---- (2)/(3) stage-level entry points: the whole encoder / connector forward as ONE call (native schedule over the
+ *      building blocks above; nothing is allocated - the caller passes a workspace of desta_*_workspace_bytes()).
+ *      desta_encoder_fwd replaces WhisperPerception.forward_whisper's conv stem + layer loop with taps
+ *      (modeling_desta25.py:563-598); desta_connector_fwd replaces the Q-Former use at :587-606.  The connector
+ *      backward (training) is scheduled by the host over the (3b) entry points. ---- */
+#define DESTA_MAX_TAPS 8
+typedef struct desta_dims {
+  int n_mels, d_model, n_heads, ffn, n_layers;
+  int n_taps, tap_layers[DESTA_MAX_TAPS];     /* 0-based encoder layer ids, ascending (modeling_desta25.py:132-146) */
+  int qf_layers, qf_ffn, prompt_size, d_llm, max_pos;
+} desta_dims;
+typedef struct desta_enc_layer {              /* bf16 GEMM weights [out,in] row-major, fp32 bias / LayerNorm */
+  const float *ln1_w, *ln1_b;
+  const void* qkv_w; const float* qkv_b;      /* [3d,d] = cat(q,k,v); bias with zeros for k (k_proj has none) */
+  const void* o_w; const float* o_b;
+  const float *ln2_w, *ln2_b;
+  const void* fc1_w; const float* fc1_b;
+  const void* fc2_w; const float* fc2_b;
+} desta_enc_layer;
+typedef struct desta_encoder_weights {
+  const void* conv1_w; const float* conv1_b;  /* [d, 3*n_mels] (tap-major im2col order) */
+  const void* conv2_w; const float* conv2_b;  /* [d, 3*d] */
+  const float* pos;                           /* [max_pos, d] */
+  const desta_enc_layer* layers;              /* [n_layers] (host array) */
+} desta_encoder_weights;
+size_t desta_encoder_workspace_bytes(const desta_dims* dims, int N);
+/* mel_tm: bf16 time-major log-mel [N, 2*max_pos, n_mels].  taps: bf16 [n_taps, N*max_pos, d].  h: fp32 [N*max_pos, d]
+ * residual stream after the last layer (input of the final LayerNorm for the ASR pass). */
+int desta_encoder_fwd(const desta_dims* dims, const desta_encoder_weights* w, const void* mel_tm, int N, void* workspace,
+                      size_t workspace_bytes, void* taps, float* h, void* stream);
+
+typedef struct desta_qf_layer {
+  const void* s_qkv_w; const float* s_qkv_b; const void* s_o_w; const float* s_o_b; const float *s_ln_w, *s_ln_b;
+  const void* c_q_w; const float* c_q_b; const void* c_o_w; const float* c_o_b; const float *c_ln_w, *c_ln_b;
+  const void* f1_w; const float* f1_b; const void* f2_w; const float* f2_b; const float *f_ln_w, *f_ln_b;
+} desta_qf_layer;
+typedef struct desta_connector_weights {
+  const float* layer_weights;                 /* [prompt_size, n_taps] */
+  const float* prompts;                       /* [n_taps * prompt_size, d] */
+  const void* kv_w; const float* kv_b;        /* cross-attention K/V of all layers: [qf_layers*2*d, d], [qf_layers*2*d] */
+  const float *proj_ln_w, *proj_ln_b;
+  const void* proj_w; const float* proj_b;    /* [d_llm, d] */
+  const desta_qf_layer* layers;               /* [qf_layers] (host array) */
+} desta_connector_weights;
+size_t desta_connector_workspace_bytes(const desta_dims* dims, int N);
+/* taps as written by desta_encoder_fwd -> out fp32 [N*prompt_size, d_llm] (eval mode: no dropout). */
+int desta_connector_fwd(const desta_dims* dims, const desta_connector_weights* w, const void* taps, int N, void* workspace,
+                        size_t workspace_bytes, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

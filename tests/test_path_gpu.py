@@ -79,3 +79,36 @@ def test_taps_and_connector_vs_oracle(name, n_clips, golden_dir):
         assert _rel(feats, torch.from_numpy(gold["feats"])) <= 2e-2
     with pytest.raises(ValueError), torch.no_grad():
         p(input_features=mel[..., :2000])
+
+
+@pytest.mark.parametrize("name", ["micro", "debug"])
+def test_native_schedule_equals_per_op_schedule(name):
+    """desta_encoder_fwd / desta_connector_fwd (one C call per stage) launch the same kernels in the same order as the
+    per-op schedule: taps, residual stream and connector output are bit-identical."""
+    from desta_b200 import engine
+    cfg = CONFIGS[name]
+    W = make_weights(cfg, seed=11, with_table=False)
+    waves = synth_waves(seed=7, kinds=KINDS)[:3]
+    p = build_perception(cfg, W)
+    wave = torch.from_numpy(np.stack([o_mel.pad_or_truncate(w) for w in waves])).cuda()
+    enc, con = p._packs()
+    ws = p._workspace(3)
+    mel_tm = p.mel_time_major(wave)
+    out_native = torch.empty(3 * cfg.prompt_size, cfg.d_llm, device="cuda")
+    out_ops = torch.empty_like(out_native)
+    engine.encoder_forward(enc, p.dims, ws, mel_tm)
+    engine.connector_forward(con, p.dims, ws, out_native)
+    taps_native, h_native = ws.taps.clone(), ws.h.clone()
+    ws.taps.zero_(); ws.h.zero_()
+    engine.encoder_forward_ops(enc, p.dims, ws, mel_tm)
+    engine.connector_forward_ops(con, p.dims, ws, out_ops)
+    assert torch.equal(ws.taps, taps_native) and torch.equal(ws.h, h_native) and torch.equal(out_ops, out_native)
+    assert out_native.abs().max().item() > 0
+    # argument validation of the stage entry points
+    import ctypes
+    from desta_b200._lib import DestaError, lib
+    small = torch.empty(16, dtype=torch.uint8, device="cuda")
+    rc = lib().desta_encoder_fwd(ctypes.byref(ws._c_dims), ctypes.byref(enc.c_weights), ctypes.c_void_p(mel_tm.data_ptr()), 3,
+                                 ctypes.c_void_p(small.data_ptr()), 16, ctypes.c_void_p(ws.taps.data_ptr()),
+                                 ctypes.c_void_p(ws.h.data_ptr()), None)
+    assert rc == -1 and b"workspace too small" in lib().desta_last_error()
