@@ -4,7 +4,7 @@ import os
 from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_uint32, c_uint64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libdesta_b200.so")
+LIB_PATH = os.environ.get("DESTA_B200_LIB") or os.path.join(HERE, "libdesta_b200.so")   # override: A/B runs of two builds
 
 
 class GemmEpilogue(Structure):

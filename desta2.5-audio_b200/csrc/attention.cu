@@ -140,9 +140,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #endif
   const int n_kv = (a.Tk + AT_BKV - 1) / AT_BKV;
 
-  if (a.kv_rows < AT_BKV) {   // short key sequences: rows the TMA box never writes must read as zeros (P = 0 there)
-    uint4* z = reinterpret_cast<uint4*>(sKV);
-    for (int i = threadIdx.x; i < AT_STAGES * 2 * AT_KV_BYTES / 16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+  if (a.kv_rows < AT_BKV || a.q_rows < AT_BQ) {
+    // short sequences: rows the TMA boxes never write must read as zeros (keys: P = 0 there; queries: finite scores, so
+    // that the unused rows of a 64-query Q-Former tile can never send their warps down the rescale path)
+    uint4* z = reinterpret_cast<uint4*>(smem);
+    for (int i = threadIdx.x; i < (AT_Q_BYTES + AT_STAGES * 2 * AT_KV_BYTES) / 16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
     fence_proxy_async_smem();
   }
   if (warp == 0 && lane == 0) {
