@@ -64,6 +64,26 @@ __device__ long long g_attn_trace[8];
 #define TRACE_FLUSH()
 #endif
 
+// ---- packed fp32x2 arithmetic (Blackwell FFMA2 / FADD2: two lanes per issued instruction) ----
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
 // 32 score columns (one TMEM chunk held in registers) of one query row: p = exp2(c*s - mc) packed as bf16 pairs into
 // pk; running row sum / row max accumulated in `acc`.  MASKED (ragged last key block only) selects -inf for padded keys
 // with predicated selects - no per-element branches.
@@ -72,6 +92,27 @@ __device__ long long g_attn_trace[8];
 template <bool MASKED, bool DROP>
 __device__ __forceinline__ void softmax_chunk(const uint32_t (&v)[32], int ch, uint32_t (&pk)[16], float c, float mc,
                                               int kv_valid, SoftmaxAcc& acc, const DropoutCfg& dc, uint64_t grp0) {
+  if (!MASKED && !DROP) {
+    // hot path: packed scale-subtract and row sums (one FFMA2 / FADD2 per two elements: the step is power-capped, so
+    // issued instructions - not only stalls - are what the kernel pays for)
+    const uint64_t c2 = pack_f32x2(c, c), nmc2 = pack_f32x2(-mc, -mc);
+    uint64_t lacc = pack_f32x2(acc.l0, acc.l1);
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      const float s0 = __uint_as_float(v[i]), s1 = __uint_as_float(v[i + 1]), s2 = __uint_as_float(v[i + 2]), s3 = __uint_as_float(v[i + 3]);
+      acc.m0 = max3(acc.m0, s0, s1);
+      acc.m1 = max3(acc.m1, s2, s3);
+      float x0, x1, x2, x3;
+      unpack_f32x2(ffma2(pack_f32x2(s0, s1), c2, nmc2), x0, x1);
+      unpack_f32x2(ffma2(pack_f32x2(s2, s3), c2, nmc2), x2, x3);
+      const float p0 = fast_exp2(x0), p1 = fast_exp2(x1), p2 = fast_exp2(x2), p3 = fast_exp2(x3);
+      lacc = fadd2(lacc, fadd2(pack_f32x2(p0, p1), pack_f32x2(p2, p3)));
+      pk[i >> 1] = pack_bf16(p0, p1);
+      pk[(i >> 1) + 1] = pack_bf16(p2, p3);
+    }
+    unpack_f32x2(lacc, acc.l0, acc.l1);
+    return;
+  }
   uint32_t keep = 0;
 #pragma unroll
   for (int i = 0; i < 32; i += 4) {

@@ -181,3 +181,16 @@ def test_connector_gradients_vs_oracle(name, n_clips, golden_dir):
             prm.add_(0.01 * torch.randn_like(prm))
     feats2, _ = p(input_features=wave)
     assert (feats2 - feats).abs().max().item() > 0
+
+
+@pytest.mark.parametrize("M,N,ld,off,dtype", [(192000 // 8, 3840, 3840, 0, torch.bfloat16), (1000, 1280, 3840, 1280, torch.bfloat16),
+                                              (777, 50, 64, 3, torch.float32), (4097, 264, 264, 0, torch.bfloat16),
+                                              (33, 1280, 1280, 0, torch.float32), (5000, 8, 24, 8, torch.bfloat16)])
+def test_colsum_shapes(M, N, ld, off, dtype):
+    """Bias gradients: out[j] += sum_m x[m, j] on contiguous / strided, aligned / unaligned views (vectorised and scalar paths)."""
+    buf = torch.randn(M, ld, device="cuda").to(dtype)
+    x = buf[:, off:off + N]
+    out = torch.full((N,), 0.5, device="cuda")
+    ops.colsum(x, out)
+    ref = 0.5 + x.double().sum(0)
+    assert ((out.double() - ref).abs().max() / ref.abs().max()).item() < 1e-4
