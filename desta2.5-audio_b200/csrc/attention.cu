@@ -64,26 +64,6 @@ __device__ long long g_attn_trace[8];
 #define TRACE_FLUSH()
 #endif
 
-// ---- packed fp32x2 arithmetic (Blackwell FFMA2 / FADD2: two lanes per issued instruction) ----
-__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
-  uint64_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
-  uint64_t d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
-  uint64_t d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-
 // 32 score columns (one TMEM chunk held in registers) of one query row: p = exp2(c*s - mc) packed as bf16 pairs into
 // pk; running row sum / row max accumulated in `acc`.  MASKED (ragged last key block only) selects -inf for padded keys
 // with predicated selects - no per-element branches.
