@@ -18,11 +18,12 @@ namespace g2 {
 constexpr int BM = 128, BN = 256, BNH = 128, BK = 64, UMMA_K = 16;
 constexpr int A_BYTES = BM * BK * 2, B_BYTES = BNH * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;   // 32 KB
 constexpr int EPI_WARP0 = 4, EPI_WARPS = 8, THREADS = 384;
-// two epilogue flavours: bf16 outputs (two 2 KB boxes per warp, 5 pipeline stages) and fp32 outputs with optional
-// fp32 residual (two 4 KB boxes per warp, loaded AND stored by TMA; 4 pipeline stages)
+// two epilogue flavours: bf16 outputs (32 x 32 bf16 boxes) and fp32 outputs with optional fp32 residual (32 x 16 fp32
+// boxes, loaded AND stored by TMA); both stage through two 2 KB boxes per warp, which leaves room for a 5-stage
+// operand ring in either mode (the K = 5120 fc2 GEMM lost 10 % going from 4 to 3 stages)
 constexpr int EPI_BF16 = 0, EPI_F32 = 1;
-__host__ __device__ constexpr int stages_of(int mode) { return mode == EPI_BF16 ? 5 : 4; }
-__host__ __device__ constexpr int staging_of(int mode) { return mode == EPI_BF16 ? 2 * 2048 : 2 * 4096; }
+__host__ __device__ constexpr int stages_of(int mode) { return 5; }
+__host__ __device__ constexpr int staging_of(int mode) { return 2 * 2048; }
 constexpr int BAR_BYTES = 512;
 __host__ __device__ constexpr int smem_of(int mode) { return stages_of(mode) * STAGE_BYTES + EPI_WARPS * staging_of(mode) + 1024 + BAR_BYTES + EPI_WARPS * 512; }
 }  // namespace g2
@@ -226,10 +227,10 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         __syncwarp();
       }
       if (use_resid && lane == 0 && colbase < g.N && row0 < g.M) {
-        // residual box of chunk 0 (the buffer's previous store was issued >= 2 chunks ago)
+        // residual box of the first half-chunk (the buffer's previous store was issued >= 2 boxes ago)
         bulk_wait_read<1>();
-        mbar_arrive_expect_tx(&my_rbar[nchunk & 1], 4096);
-        tma_load_2d_plain(stg + (nchunk & 1) * 4096, &tmR, &my_rbar[nchunk & 1], colbase, row0);
+        mbar_arrive_expect_tx(&my_rbar[nchunk & 1], 2048);
+        tma_load_2d_plain(stg + (nchunk & 1) * 2048, &tmR, &my_rbar[nchunk & 1], colbase, row0);
       }
       mbar_wait_sleep(&acc_full[as], acc_phase);
       tcgen05_fence_after();
@@ -298,40 +299,46 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           }
           ++nchunk;
         } else {
-          // fp32: 32 rows x 32 floats (128-byte rows, SWIZZLE_128B).  The residual box was TMA-loaded into this very
-          // buffer; add in place, then TMA-store.  The next chunk's residual is requested before the math.
-          uint8_t* buf = stg + (nchunk & 1) * 4096;
-          const bool more = (c < 3) && (col0 + 32 < g.N);
-          if (use_resid) {
-            if (lane == 0 && more) {
-              bulk_wait_read<0>();                      // the other buffer's store (previous chunk) has been read
-              mbar_arrive_expect_tx(&my_rbar[(nchunk + 1) & 1], 4096);
-              tma_load_2d_plain(stg + ((nchunk + 1) & 1) * 4096, &tmR, &my_rbar[(nchunk + 1) & 1], col0 + 32, row0);
-            }
-            mbar_wait(&my_rbar[nchunk & 1], (nchunk >> 1) & 1);
-          } else {
-            if (lane == 0) bulk_wait_read<1>();
-            __syncwarp();
-          }
-          float4* rowp = reinterpret_cast<float4*>(buf + lane * 128);
-          const int sw = lane & 7;
+          // fp32: two boxes of 32 rows x 16 floats (64-byte rows, SWIZZLE_64B) per 32-column chunk.  The residual box was
+          // TMA-loaded into the very buffer; add in place, then TMA-store.  The next box's residual is requested first.
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 o4 = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          for (int h = 0; h < 2; ++h) {
+            const int colh = col0 + 16 * h;
+            if (colh >= g.N) break;                     // warp-uniform
+            uint8_t* buf = stg + (nchunk & 1) * 2048;
+            const bool more = h == 0 ? (colh + 16 < g.N) : ((c < 3) && (col0 + 32 < g.N));
             if (use_resid) {
-              const float4 r4 = rowp[j ^ sw];
-              o4.x += r4.x; o4.y += r4.y; o4.z += r4.z; o4.w += r4.w;
+              if (lane == 0 && more) {
+                bulk_wait_read<0>();                    // the other buffer's store (previous box) has been read
+                mbar_arrive_expect_tx(&my_rbar[(nchunk + 1) & 1], 2048);
+                tma_load_2d_plain(stg + ((nchunk + 1) & 1) * 2048, &tmR, &my_rbar[(nchunk + 1) & 1], colh + 16, row0);
+              }
+              mbar_wait(&my_rbar[nchunk & 1], (nchunk >> 1) & 1);
+            } else {
+              if (lane == 0) bulk_wait_read<1>();
+              __syncwarp();
             }
-            rowp[j ^ sw] = o4;
-            f[4 * j] = o4.x; f[4 * j + 1] = o4.y; f[4 * j + 2] = o4.z; f[4 * j + 3] = o4.w;
+            uint8_t* rowp = buf + lane * 64;
+            const int sw = (lane >> 1) & 3;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float4* q4 = reinterpret_cast<float4*>(rowp + ((j ^ sw) << 4));
+              float4 o4 = make_float4(f[16 * h + 4 * j], f[16 * h + 4 * j + 1], f[16 * h + 4 * j + 2], f[16 * h + 4 * j + 3]);
+              if (use_resid) {
+                const float4 r4 = *q4;
+                o4.x += r4.x; o4.y += r4.y; o4.z += r4.z; o4.w += r4.w;
+              }
+              *q4 = o4;
+              f[16 * h + 4 * j] = o4.x; f[16 * h + 4 * j + 1] = o4.y; f[16 * h + 4 * j + 2] = o4.z; f[16 * h + 4 * j + 3] = o4.w;
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmC, buf, colh, row0);
+              bulk_commit();
+            }
+            ++nchunk;
           }
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_2d(&tmC, buf, col0, row0);
-            bulk_commit();
-          }
-          ++nchunk;
           if (g.out_bf16 && row_ok) {                  // tap hand-off: direct bf16 copy (4 of 32 fc2 launches)
             __nv_bfloat16* o = g.out_bf16 + (size_t)row * g.ld_bf16 + col0;
             if (full_cols) {
@@ -366,8 +373,8 @@ int num_sms();
 static int make_f32_box_map(CUtensorMap* m, const float* base, int M, int N, int ld) {
   uint64_t dims[2] = {(uint64_t)N, (uint64_t)M};
   uint64_t strides[2] = {0, (uint64_t)ld * 4};
-  uint32_t box[2] = {32, 32};
-  return make_tmap(m, base, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+  uint32_t box[2] = {16, 32};
+  return make_tmap(m, base, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B);
 }
 
 int launch_gemm_2cta(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const desta_gemm_epilogue* ep,
