@@ -101,21 +101,38 @@ class TrainState:
         self.g_mix = e(N * Q, d, dt=f32)
         self.g_mixn = e(N * Q, d, dt=f32)
         self.g_x = e(R, d, dt=f32)
-        # gradient buffers (fp32, fused like the packed weights)
-        z = lambda *s: torch.zeros(*s, dtype=f32, device=device)  # noqa: E731
-        self.grads = dict(layer_weights=z(Q, K), prompts=z(K * Q, d), kv_w=z(L * 2 * d, d), kv_b=z(L * 2 * d),
-                          proj_ln_w=z(d), proj_ln_b=z(d), proj_w=z(dims.d_llm, d), proj_b=z(dims.d_llm))
-        self.lgrads = [dict(s_qkv_w=z(3 * d, d), s_qkv_b=z(3 * d), s_o_w=z(d, d), s_o_b=z(d), s_ln_w=z(d), s_ln_b=z(d),
-                            c_q_w=z(d, d), c_q_b=z(d), c_o_w=z(d, d), c_o_b=z(d), c_ln_w=z(d), c_ln_b=z(d),
-                            f1_w=z(dims.qf_ffn, d), f1_b=z(dims.qf_ffn), f2_w=z(d, dims.qf_ffn), f2_b=z(d),
-                            f_ln_w=z(d), f_ln_b=z(d)) for _ in range(L)]
+        # gradient buffers (fp32, fused like the packed weights): views of ONE arena, so that zeroing them and handing a
+        # private copy to autograd are single launches instead of one per tensor (165 parameters at the flagship size)
+        shapes = dict(layer_weights=(Q, K), prompts=(K * Q, d), kv_w=(L * 2 * d, d), kv_b=(L * 2 * d,),
+                      proj_ln_w=(d,), proj_ln_b=(d,), proj_w=(dims.d_llm, d), proj_b=(dims.d_llm,))
+        lshapes = dict(s_qkv_w=(3 * d, d), s_qkv_b=(3 * d,), s_o_w=(d, d), s_o_b=(d,), s_ln_w=(d,), s_ln_b=(d,),
+                       c_q_w=(d, d), c_q_b=(d,), c_o_w=(d, d), c_o_b=(d,), c_ln_w=(d,), c_ln_b=(d,),
+                       f1_w=(dims.qf_ffn, d), f1_b=(dims.qf_ffn,), f2_w=(d, dims.qf_ffn), f2_b=(d,), f_ln_w=(d,), f_ln_b=(d,))
+
+        def numel(shape):
+            n = 1
+            for v in shape:
+                n *= v
+            return (n + 3) // 4 * 4                     # keep every buffer 16-byte aligned
+
+        total = sum(numel(v) for v in shapes.values()) + L * sum(numel(v) for v in lshapes.values())
+        self.arena = torch.zeros(total, dtype=f32, device=device)
+        off = 0
+
+        def carve(shape):
+            nonlocal off
+            n = 1
+            for v in shape:
+                n *= v
+            t = self.arena[off: off + n].view(*shape)
+            off += numel(shape)
+            return t
+
+        self.grads = {k: carve(v) for k, v in shapes.items()}
+        self.lgrads = [{k: carve(v) for k, v in lshapes.items()} for _ in range(L)]
 
     def zero_grads(self):
-        for t in self.grads.values():
-            t.zero_()
-        for g in self.lgrads:
-            for t in g.values():
-                t.zero_()
+        self.arena.zero_()
 
 
 def _dense_res(a_bf, w, b, t, resid, drop):
@@ -291,10 +308,18 @@ class _ConnectorFn(torch.autograd.Function):
         st.zero_grads()
         g = grad_out.to(torch.float32).contiguous().view(N * p.dims.prompt_size, p.dims.d_llm)
         connector_backward(con, conT, p.dims, ws, st, g, ctx.plan)
+        # one private copy of the whole gradient arena; the per-parameter gradients are views of it (same offsets)
+        priv = st.arena.clone()
+        base = st.arena.data_ptr()
         by_name = grads_by_name(st, p.dims)
         grads = []
         for name, prm in p.connector.named_parameters():
-            grads.append(by_name[name].to(prm.dtype).reshape(prm.shape).clone() if prm.requires_grad else None)
+            if not prm.requires_grad:
+                grads.append(None)
+                continue
+            v = by_name[name]
+            gv = torch.as_strided(priv, v.shape, v.stride(), (v.data_ptr() - base) // 4).reshape(prm.shape)
+            grads.append(gv if prm.dtype == torch.float32 else gv.to(prm.dtype))
         return (None, None, *grads)
 
 
