@@ -54,6 +54,20 @@ def bench_attn():
         print(f"attn {name:9s} B={B} H={H} Tq={Tq} Tk={Tk}: {ms:.3f} ms  {4.0 * B * H * Tq * Tk * 64 / ms / 1e9:.0f} TFLOP/s", flush=True)
 
 
+def bench_attn_bwd():
+    for name, B, H, Tq, Tk, scale in [("qf_cross", 128, 20, 64, 1500, 0.125), ("qf_self", 128, 20, 64, 64, 0.125)]:
+        d = H * 64
+        q = (torch.randn(B * Tq, d, device="cuda") * 0.5).to(torch.bfloat16)
+        kv = (torch.randn(B * Tk, 2 * d, device="cuda") * 0.5).to(torch.bfloat16)
+        o, do = torch.empty_like(q), torch.randn_like(q)
+        lse = torch.empty(B * H * Tq, device="cuda")
+        ops.attention(q, kv[:, :d], kv[:, d:], o, B, H, Tq, Tk, scale, lse=lse)
+        dq, dkv = torch.empty_like(q), torch.empty_like(kv)
+        fn = lambda: ops.attention_bwd(q, kv[:, :d], kv[:, d:], o, do, lse, dq, dkv[:, :d], dkv[:, d:], B, H, Tq, Tk, scale)  # noqa: E731
+        ms = timeit(fn)
+        print(f"attn_bwd {name:9s} B={B} H={H} Tq={Tq} Tk={Tk}: {ms:.3f} ms  {10.0 * B * H * Tq * Tk * 64 / ms / 1e9:.0f} TFLOP/s", flush=True)
+
+
 def bench_mel():
     for N in (64, 256):
         wave = torch.clamp(0.1 * torch.randn(N, 480000, device="cuda"), -1, 1)
@@ -76,4 +90,4 @@ def bench_splice():
 if __name__ == "__main__":
     which = sys.argv[1:] or ["gemm", "attn", "mel", "splice"]
     for w in which:
-        {"gemm": bench_gemm, "attn": bench_attn, "mel": bench_mel, "splice": bench_splice}[w]()
+        {"gemm": bench_gemm, "attn": bench_attn, "attn_bwd": bench_attn_bwd, "mel": bench_mel, "splice": bench_splice}[w]()
