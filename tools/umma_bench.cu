@@ -8,7 +8,7 @@
 namespace desta { void set_error(const char*, ...) {} int check_launch(const char*) { return 0; } }
 using namespace desta;
 
-template <int STYLE, int N, bool TS>
+template <int STYLE, int N, bool TS, int AMN = 0, int BMN = 0>
 __global__ void __launch_bounds__(128) umma_bench(int iters, long long* out) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar;
@@ -22,9 +22,11 @@ __global__ void __launch_bounds__(128) umma_bench(int iters, long long* out) {
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t t0 = slot;
-  constexpr uint32_t idesc = umma_idesc_bf16(128, N, 0, 0);
-  const uint64_t adesc = umma_desc_sw128(smem_u32(smem), 16, 1024);
-  const uint64_t bdesc = umma_desc_sw128(smem_u32(smem) + 32768, 16, 1024);
+  constexpr uint32_t idesc = umma_idesc_bf16(128, N, AMN, BMN);
+  // K-major: 16 bf16 of K = 32 B inside the 128-byte row (+2);  MN-major: 16 K rows = two 8-row groups = 2048 B (+128)
+  const uint64_t adesc = AMN ? umma_desc_sw128(smem_u32(smem), 16384, 1024) : umma_desc_sw128(smem_u32(smem), 16, 1024);
+  const uint64_t bdesc = BMN ? umma_desc_sw128(smem_u32(smem) + 32768, 1024, 1024) : umma_desc_sw128(smem_u32(smem) + 32768, 16, 1024);
+  constexpr int AS = AMN ? 128 : 2, BS = BMN ? 128 : 2;
   if (STYLE == 0) {
     if (threadIdx.x == 0) {
       for (int i = 0; i < 8; ++i) umma_bf16_ss(t0, adesc, bdesc, idesc, 1);
@@ -33,8 +35,8 @@ __global__ void __launch_bounds__(128) umma_bench(int iters, long long* out) {
       for (int i = 0; i < iters; i += 4) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          if (TS) umma_bf16_ts(t0, t0 + 256 + 8 * k, bdesc + 2 * k, idesc, 1);
-          else umma_bf16_ss(t0, adesc + 2 * k, bdesc + 2 * k, idesc, 1);
+          if (TS) umma_bf16_ts(t0, t0 + 256 + 8 * k, bdesc + BS * k, idesc, 1);
+          else umma_bf16_ss(t0, adesc + AS * k, bdesc + BS * k, idesc, 1);
         }
       }
       umma_commit(&bar); mbar_wait(&bar, 1);
@@ -50,8 +52,8 @@ __global__ void __launch_bounds__(128) umma_bench(int iters, long long* out) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           if (elect_one()) {
-            if (TS) umma_bf16_ts(t0, t0 + 256 + 8 * k, bdesc + 2 * k, idesc, 1);
-            else umma_bf16_ss(t0, adesc + 2 * k, bdesc + 2 * k, idesc, 1);
+            if (TS) umma_bf16_ts(t0, t0 + 256 + 8 * k, bdesc + BS * k, idesc, 1);
+            else umma_bf16_ss(t0, adesc + AS * k, bdesc + BS * k, idesc, 1);
           }
         }
       }
@@ -65,11 +67,11 @@ __global__ void __launch_bounds__(128) umma_bench(int iters, long long* out) {
   if (warp == 0) { tcgen05_fence_after(); tmem_dealloc<512>(t0); }
 }
 
-template <int STYLE, int N, bool TS>
+template <int STYLE, int N, bool TS, int AMN = 0, int BMN = 0>
 void run(long long* d, const char* name) {
   const int iters = 1024;
-  cudaFuncSetAttribute(umma_bench<STYLE, N, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
-  umma_bench<STYLE, N, TS><<<148, 128, 65536>>>(iters, d);
+  cudaFuncSetAttribute(umma_bench<STYLE, N, TS, AMN, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+  umma_bench<STYLE, N, TS, AMN, BMN><<<148, 128, 65536>>>(iters, d);
   cudaError_t e = cudaDeviceSynchronize();
   long long h = 0; cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
   printf("style %d  128x%3dx16 %s  %-28s %7.1f cyc/mma  (math floor %d)%s\n", STYLE, N, TS ? "TS" : "SS", name, (double)h / iters,
@@ -82,5 +84,9 @@ int main() {
   run<0, 64, true>(d, "thread-0 branch");    run<1, 64, true>(d, "converged warp + elect");
   run<0, 128, false>(d, "thread-0 branch");  run<1, 128, false>(d, "converged warp + elect");
   run<0, 256, false>(d, "thread-0 branch");  run<1, 256, false>(d, "converged warp + elect");
+  run<1, 64, false, 0, 1>(d, "B MN-major");
+  run<1, 64, false, 1, 0>(d, "A MN-major");
+  run<1, 64, false, 1, 1>(d, "A and B MN-major");
+  run<1, 64, true, 0, 1>(d, "A TMEM, B MN-major");
   return 0;
 }
