@@ -375,7 +375,7 @@ def main():
                     help="single = one clip per prompt, S 128; multi = 4 clips per prompt with transcripts, S 512")
     ap.add_argument("--mode", default="forward", choices=["forward", "train"],
                     help="forward = BASELINE.json configs[1] (default); train = configs[4] step (connector fwd+bwd, grad all-reduce)")
-    ap.add_argument("--cpu-clips", type=int, default=2, help="clips in the bounded cpu_baseline sample")
+    ap.add_argument("--cpu-clips", type=int, default=8, help="clips in the bounded cpu_baseline sample (~10 s of CPU work on 16 cores)")
     ap.add_argument("--ref-clips", type=int, default=2, help="clips per step of the --impl reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
