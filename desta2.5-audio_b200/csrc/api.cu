@@ -69,6 +69,26 @@ int make_tmap(CUtensorMap* out, const void* base, CUtensorMapDataType dt, int el
   return DESTA_OK;
 }
 
+bool* device_once_flag(int slot) {
+  static bool flags[DESTA_MAX_DEVICES][8] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= DESTA_MAX_DEVICES) dev = 0;
+  return &flags[dev][slot & 7];
+}
+
+int num_sms() {
+  static int sms[DESTA_MAX_DEVICES] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= DESTA_MAX_DEVICES) dev = 0;
+  if (sms[dev] == 0) {
+    cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (sms[dev] <= 0) sms[dev] = 148;
+  }
+  return sms[dev];
+}
+
 int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
                       uint32_t box_rows, uint32_t box_cols) {
   uint64_t dims[2] = {cols, rows};

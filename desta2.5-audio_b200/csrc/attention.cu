@@ -412,7 +412,7 @@ extern "C" int desta_attention(const void* q, int ldq, const void* k, int ldk, c
   if (make_qkv_tmap(&tmQ, q, heads, Tq, ldq, batch, a.q_rows)) return DESTA_ERR_CUDA;
   if (make_qkv_tmap(&tmK, k, heads, Tk, ldk, batch, a.kv_rows)) return DESTA_ERR_CUDA;
   if (make_qkv_tmap(&tmV, v, heads, Tk, ldv, batch, a.kv_rows)) return DESTA_ERR_CUDA;
-  static bool attr_set = false;
+  bool& attr_set = *device_once_flag(2);
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);

@@ -653,7 +653,7 @@ extern "C" int desta_attention_bwd(const void* q, int ldq, const void* k, int ld
     CUtensorMap tmDK, tmDV;
     if (make_tmap3(&tmDK, dk, heads, Tk, lddk, batch, a.kv_rows)) return DESTA_ERR_CUDA;
     if (make_tmap3(&tmDV, dv, heads, Tk, lddv, batch, a.kv_rows)) return DESTA_ERR_CUDA;
-    static bool attr64 = false;
+    bool& attr64 = *device_once_flag(3);
     if (!attr64) {
       cudaError_t e = cudaFuncSetAttribute(attn_bwd_t64_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, t64::SMEM);
       if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_t64_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, t64::SMEM);
@@ -669,7 +669,7 @@ extern "C" int desta_attention_bwd(const void* q, int ldq, const void* k, int ld
   if (make_tmap3(&tmDO, dout, heads, Tq, lddo, batch, a.q_rows)) return DESTA_ERR_CUDA;
   if (make_tmap3(&tmK, k, heads, Tk, ldk, batch, a.kv_rows)) return DESTA_ERR_CUDA;
   if (make_tmap3(&tmV, v, heads, Tk, ldv, batch, a.kv_rows)) return DESTA_ERR_CUDA;
-  static bool attr_set = false;
+  bool& attr_set = *device_once_flag(4);
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM);

@@ -23,6 +23,12 @@ int make_tmap(CUtensorMap* out, const void* base, CUtensorMapDataType dt, int el
               const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz);
 int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
                       uint32_t box_rows, uint32_t box_cols);
+// Per-device one-time state (kernel attributes such as the dynamic shared-memory limit are per device): returns a
+// pointer to a flag for (current device, slot) that is false until the caller sets it.  The library keeps no other
+// mutable state, so one process may drive several GPUs.
+constexpr int DESTA_MAX_DEVICES = 64;
+bool* device_once_flag(int slot);
+int num_sms();
 
 // ---- dropout configuration as the kernels take it (by value); built from the ABI's desta_dropout (NULL -> off) ----
 struct DropoutCfg {

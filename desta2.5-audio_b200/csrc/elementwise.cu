@@ -103,7 +103,6 @@ layer_mix_kernel(const float* __restrict__ x, const float* __restrict__ lw, int 
   }
 }
 
-int num_sms();
 
 }  // namespace desta
 

@@ -5,7 +5,6 @@
 
 namespace desta {
 
-int num_sms();
 
 // ---- LayerNorm backward.  One warp per row (row kept in registers), statistics recomputed from the saved input.
 //      dx = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat));  dgamma += sum_rows dy*xhat;  dbeta += sum_rows dy.

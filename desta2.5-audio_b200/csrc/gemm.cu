@@ -270,23 +270,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 int launch_gemm_2cta(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const desta_gemm_epilogue* ep,
                      cudaStream_t stream);
 
-static int g_num_sms = 0;
-int num_sms() {
-  if (g_num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = 148;
-  }
-  return g_num_sms;
-}
 
 }  // namespace desta
 
 using namespace desta;
 
 static int launch_gemm(int mode, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g, cudaStream_t stream) {
-  static bool attr_set = false;
+  bool& attr_set = *device_once_flag(0);
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<MODE_TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_bf16_kernel<MODE_WGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);

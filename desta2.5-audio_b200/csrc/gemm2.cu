@@ -368,7 +368,6 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   }
 }
 
-int num_sms();
 
 static int make_f32_box_map(CUtensorMap* m, const float* base, int M, int N, int ld) {
   uint64_t dims[2] = {(uint64_t)N, (uint64_t)M};
@@ -405,7 +404,7 @@ int launch_gemm_2cta(const void* A, int lda, const void* W, int ldw, int M, int 
   g.bias = ep->bias; g.resid = ep->resid; g.ld_resid = ep->ld_resid;
   g.pos = ep->pos; g.pos_rows = ep->pos_rows > 0 ? ep->pos_rows : 1;
   g.scale = ep->scale; g.scale_cols = ep->scale_cols; g.gelu = ep->gelu;
-  static bool attr_set = false;
+  bool& attr_set = *device_once_flag(1);
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_2cta_kernel<EPI_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_of(EPI_BF16));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_bf16_tn_2cta_kernel<EPI_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_of(EPI_F32));

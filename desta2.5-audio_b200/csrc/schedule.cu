@@ -90,7 +90,6 @@ broadcast_prompts_kernel(const float* __restrict__ prompts, int taps, int N, int
   }
 }
 
-int num_sms();
 
 }  // namespace desta
 

@@ -80,7 +80,6 @@ splice_bwd_kernel(const uint4* __restrict__ grad_out, const desta_splice_desc* _
   }
 }
 
-int num_sms();
 
 }  // namespace desta
 

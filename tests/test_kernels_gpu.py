@@ -232,3 +232,24 @@ def test_splice_errors_and_empty():
     feats = torch.randn(1, 64, 64).cuda()
     with pytest.raises(ValueError):                                   # span leaves the sequence (reference raises too)
         ops.splice(ids, table, [(0, 30, 0, 0)], None, feats, 64)
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_one_process_two_devices():
+    """The library keeps no cross-device state (kernel attributes are set per device): the same process can run the
+    kernels on cuda:0 and cuda:1."""
+    outs = []
+    for dev in (0, 1, 0):
+        with torch.cuda.device(dev):
+            g = torch.Generator(device=f"cuda:{dev}").manual_seed(3)
+            a = torch.randn(512, 256, device=f"cuda:{dev}", generator=g).to(torch.bfloat16)
+            w = torch.randn(384, 256, device=f"cuda:{dev}", generator=g).to(torch.bfloat16)
+            out = torch.empty(512, 384, device=f"cuda:{dev}")
+            ops.gemm(a, w, None, out_f32=out)
+            q = torch.randn(2 * 200, 3 * 128, device=f"cuda:{dev}", generator=g).to(torch.bfloat16)
+            o = torch.empty(2 * 200, 128, device=f"cuda:{dev}", dtype=torch.bfloat16)
+            ops.attention(q[:, :128], q[:, 128:256], q[:, 256:], o, 2, 2, 200, 200, 0.125)
+            torch.cuda.synchronize()
+            outs.append((out.cpu(), o.float().cpu()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][0], outs[2][0])
+    assert torch.equal(outs[0][1], outs[1][1])
