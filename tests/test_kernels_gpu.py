@@ -253,3 +253,61 @@ def test_one_process_two_devices():
             outs.append((out.cpu(), o.float().cpu()))
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][0], outs[2][0])
     assert torch.equal(outs[0][1], outs[1][1])
+
+
+def _guarded(rows, cols, dtype, ld=None, guard_rows=64, fill=7.0):
+    """A [rows, cols] view (row stride ld) in the middle of a sentinel-filled buffer + a checker for the guard area."""
+    ld = ld or cols
+    buf = torch.full(((rows + 2 * guard_rows), ld), fill, dtype=dtype, device="cuda")
+    view = buf[guard_rows:guard_rows + rows, :cols]
+    def untouched():
+        ok = bool((buf[:guard_rows] == fill).all()) and bool((buf[guard_rows + rows:] == fill).all())
+        if ld > cols:
+            ok = ok and bool((buf[guard_rows:guard_rows + rows, cols:] == fill).all())
+        return ok
+    return view, untouched
+
+
+def test_no_writes_outside_the_outputs():
+    """TMA stores / vector stores must clip at ragged M, N, Tq, Tk (compute-sanitizer is not available on this pool, so the
+    bounds are checked with sentinel guards around every output)."""
+    g = torch.Generator(device="cuda").manual_seed(0)
+    # GEMM, bf16 output through 32 x 32 TMA boxes and fp32 + residual through 32 x 16 boxes, ragged M / N / K
+    for M, N, K in [(1000, 200, 72), (130, 264, 136), (257, 1288, 64)]:
+        a = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
+        w = torch.randn(N, K, device="cuda", generator=g).to(torch.bfloat16)
+        ob, chk_b = _guarded(M, N, torch.bfloat16, ld=N + 24)
+        ops.gemm(a, w, None, out_bf16=ob)
+        of, chk_f = _guarded(M, N, torch.float32, ld=N + 12)
+        r = torch.randn(M, N, device="cuda", generator=g)
+        ops.gemm(a, w, None, out_f32=of, resid=r)
+        torch.cuda.synchronize()
+        assert chk_b() and chk_f(), (M, N, K)
+        ref = a.float() @ w.float().t()
+        assert _rel(ob, ref) < 1e-2 and _rel(of, ref + r) < 1e-4
+    # attention forward (ragged last query tile / key block) and backward (TMA-stored dK / dV, ragged last key block)
+    for B, H, Tq, Tk in [(2, 2, 300, 300), (2, 2, 64, 300), (2, 2, 100, 200)]:
+        d = H * 64
+        q = torch.randn(B * Tq, d, device="cuda", generator=g).to(torch.bfloat16)
+        k = torch.randn(B * Tk, d, device="cuda", generator=g).to(torch.bfloat16)
+        v = torch.randn(B * Tk, d, device="cuda", generator=g).to(torch.bfloat16)
+        o, chk_o = _guarded(B * Tq, d, torch.bfloat16, ld=d + 64)
+        lse = torch.empty(B * H * Tq, device="cuda")
+        ops.attention(q, k, v, o, B, H, Tq, Tk, 0.125, lse=lse)
+        do = torch.randn(B * Tq, d, device="cuda", generator=g).to(torch.bfloat16)
+        dq, chk_q = _guarded(B * Tq, d, torch.bfloat16, ld=d + 64)
+        dk, chk_k = _guarded(B * Tk, d, torch.bfloat16, ld=d + 64)
+        dv, chk_v = _guarded(B * Tk, d, torch.bfloat16, ld=d + 64)
+        if Tq <= 128:                                   # the backward exists for Q-Former-sized query sets only
+            ops.attention_bwd(q, k, v, o, do, lse, dq, dk, dv, B, H, Tq, Tk, 0.125)
+        torch.cuda.synchronize()
+        assert chk_o() and chk_q() and chk_k() and chk_v(), (B, H, Tq, Tk)
+        assert torch.isfinite(o.float()).all()
+        if Tq <= 128:
+            assert torch.isfinite(dk.float()).all() and torch.isfinite(dv.float()).all() and torch.isfinite(dq.float()).all()
+    # LayerNorm
+    x = torch.randn(333, 384, device="cuda", generator=g)
+    y, chk_y = _guarded(333, 384, torch.bfloat16, ld=400)
+    ops.layernorm(x, torch.ones(384, device="cuda"), torch.zeros(384, device="cuda"), 1e-5, out_bf16=y)
+    torch.cuda.synchronize()
+    assert chk_y()
