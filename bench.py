@@ -216,7 +216,11 @@ def run_ours(args):
         perception.train()
         grad_emb = (0.01 * torch.randn(B_prompts, S_len, w["d_llm"], device=dev, generator=g)).to(torch.bfloat16)
         if world > 1:
-            bucket = GradBucket(list(perception.connector.parameters()))
+            if args.grad_sync == "overlap":
+                from desta_b200.dist import GradSync
+                perception.grad_sync = GradSync()       # all-reduce per Q-Former layer inside the backward
+            else:
+                bucket = GradBucket(list(perception.connector.parameters()))
 
     def train_step(ii, wv):
         # frozen encoder forward + Q-Former forward/backward; the LLM's gradient w.r.t. inputs_embeds is synthetic
@@ -377,6 +381,8 @@ def main():
                     help="forward = BASELINE.json configs[1] (default); train = configs[4] step (connector fwd+bwd, grad all-reduce)")
     ap.add_argument("--cpu-clips", type=int, default=8, help="clips in the bounded cpu_baseline sample (~10 s of CPU work on 16 cores)")
     ap.add_argument("--ref-clips", type=int, default=2, help="clips per step of the --impl reference arm")
+    ap.add_argument("--grad-sync", default="overlap", choices=["overlap", "bucket"],
+                    help="training on N > 1 GPUs: all-reduce overlapped with the backward (default) or one flat bucket after it")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -129,7 +129,12 @@ class TrainState:
             return t
 
         self.grads = {k: carve(v) for k, v in shapes.items()}
-        self.lgrads = [{k: carve(v) for k, v in lshapes.items()} for _ in range(L)]
+        self.global_slice = (0, off)                        # arena range of the non-layer gradients (complete last)
+        self.lgrads, self.layer_slices = [], []
+        for _ in range(L):
+            start = off
+            self.lgrads.append({k: carve(v) for k, v in lshapes.items()})
+            self.layer_slices.append((start, off))          # arena range of one Q-Former layer's gradients
 
     def zero_grads(self):
         self.arena.zero_()
@@ -177,8 +182,12 @@ def connector_forward_train(con, dims: PathDims, ws, st: TrainState, out_f32, pl
     return out_f32
 
 
-def connector_backward(con, conT: ConnectorTPack, dims: PathDims, ws, st: TrainState, grad_out, plan: DropPlan = NO_DROP):
-    """grad_out fp32 [N*Q, d_llm] -> fills st.grads / st.lgrads (+=; call st.zero_grads() first)."""
+def connector_backward(con, conT: ConnectorTPack, dims: PathDims, ws, st: TrainState, grad_out, plan: DropPlan = NO_DROP,
+                       on_ready=None):
+    """grad_out fp32 [N*Q, d_llm] -> fills st.grads / st.lgrads (+=; call st.zero_grads() first).
+    `on_ready(arena_slice)` is called as soon as a contiguous part of the gradient arena is final (one Q-Former layer at a
+    time, last layer first; the remaining tensors at the end) so that a data-parallel all-reduce can overlap the rest of
+    the backward (desta_b200.dist.GradSync)."""
     N, d, T, Q = ws.N, dims.d_model, dims.max_pos, dims.prompt_size
     K, H = len(dims.tap_layers), dims.n_heads
     B, R = K * N, K * N * Q
@@ -238,12 +247,18 @@ def connector_backward(con, conT: ConnectorTPack, dims: PathDims, ws, st: TrainS
         ops.colsum(st.g_qkv, g["s_qkv_b"])
         ops.gemm(st.g_qkv, LT["s_qkv"], None, out_f32=st.g_x, resid=st.g_f32_a)      # dx = dt1 + dqkv Wqkv
         dx = st.g_x
+        if on_ready is not None:
+            a0, a1 = st.layer_slices[l]
+            on_ready(st.arena[a0:a1])
     # ---- learned prompts: x0[k, n] = layer_prompts[k] for every clip n ----
     for k in range(K):
         ops.colsum(dx.view(K, N, Q * d)[k], G["prompts"].view(K, Q * d)[k])
     # ---- cross-attention K/V projections of all layers: one weight-gradient GEMM over all taps' rows ----
     ops.gemm_wgrad(st.dkv, ws.taps.view(K * N * T, d), G["kv_w"])
     ops.colsum(st.dkv, G["kv_b"])
+    if on_ready is not None:
+        a0, a1 = st.global_slice
+        on_ready(st.arena[a0:a1])
 
 
 def _drop_grad(st: TrainState, drop):
@@ -307,7 +322,10 @@ class _ConnectorFn(torch.autograd.Function):
         ws, st = p._workspace(N), p._train_state(N)
         st.zero_grads()
         g = grad_out.to(torch.float32).contiguous().view(N * p.dims.prompt_size, p.dims.d_llm)
-        connector_backward(con, conT, p.dims, ws, st, g, ctx.plan)
+        sync = getattr(p, "grad_sync", None)       # data-parallel all-reduce overlapped with the backward (dist.GradSync)
+        connector_backward(con, conT, p.dims, ws, st, g, ctx.plan, on_ready=sync.reduce if sync is not None else None)
+        if sync is not None:
+            sync.finish(st.arena)
         # one private copy of the whole gradient arena; the per-parameter gradients are views of it (same offsets)
         priv = st.arena.clone()
         base = st.arena.data_ptr()

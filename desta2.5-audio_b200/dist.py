@@ -75,6 +75,26 @@ class GradBucket:
             p.grad = v
 
 
+class GradSync:
+    """Gradient exchange overlapped with the connector backward.  Assign an instance to `perception.grad_sync`: the
+    backward then all-reduces each Q-Former layer's slice of the gradient arena as soon as it is final (asynchronously,
+    on NCCL's stream) while the remaining layers are still being differentiated, and `.grad`s come out already averaged
+    over the data-parallel group - the role DDP's bucketed hooks play for the reference (no further all-reduce needed)."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.works = []
+
+    def reduce(self, arena_slice: torch.Tensor):
+        self.works.append(dist.all_reduce(arena_slice, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def finish(self, arena: torch.Tensor):
+        for w in self.works:
+            w.wait()
+        self.works = []
+        arena.div_(dist.get_world_size(self.group))
+
+
 def allreduce_connector_grads(connector: torch.nn.Module, group=None, bucket: Optional[GradBucket] = None) -> GradBucket:
     bucket = bucket or GradBucket(list(connector.parameters()))
     bucket.allreduce(group)

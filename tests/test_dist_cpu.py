@@ -66,3 +66,33 @@ def test_gloo_world2_gather_and_allreduce():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, "ok"), (1, "ok")], res
+
+
+def _gradsync_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    from desta_b200.dist import GradSync
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    arena = torch.arange(1000, dtype=torch.float32) * (rank + 1)
+    sync = GradSync()
+    for a0, a1 in ((600, 1000), (300, 600), (0, 300)):          # slices become final back to front, like the backward
+        sync.reduce(arena[a0:a1])
+    sync.finish(arena)
+    q.put((rank, arena.clone()))
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_gradsync_overlapped_slices():
+    import torch
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29650
+    procs = [ctx.Process(target=_gradsync_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+    want = torch.arange(1000, dtype=torch.float32) * 1.5        # mean of 1x and 2x
+    assert torch.equal(res[0], want) and torch.equal(res[1], want)
