@@ -105,3 +105,30 @@ def test_flagship_splice_round_trip(flagship):
         t = trans[i].view(-1).cuda()
         expect[b, s + Q:s + Q + t.numel()] = table[t]
     assert torch.equal(emb.view(torch.int16), expect.view(torch.int16))
+
+
+def test_flagship_full_depth_vs_oracle():
+    """The whole flagship model - 32 encoder layers, 6 Q-Former layers, d_llm 4096 - on one clip against the CPU oracle
+    (a few seconds of fp32 ATen on the host cores): checks that the bf16-operand / fp32-residual arithmetic contract holds
+    the north_star tolerance (max|delta|/max|ref| <= 2e-2, cosine >= 0.999) after the error has accumulated over the
+    full depth, for every tap and for the connector output."""
+    cfg = CONFIGS["large_v3_llama"]
+    W = make_weights(cfg, seed=5, with_table=False)
+    waves = synth_waves(seed=7, kinds=("speechy_12s",))
+    mel = torch.from_numpy(o_mel.logmel(waves, cfg.n_mels))
+    with torch.no_grad():
+        taps_ref = o_enc.encoder_taps(W, cfg, mel)
+        feats_ref = o_qf.connector(W, cfg, taps_ref)
+    p = build_perception(cfg, W)
+    del W
+    wave = torch.from_numpy(np.stack([o_mel.pad_or_truncate(w) for w in waves])).cuda()
+    taps = [t.clone() for t in p.taps(wave)]
+    for k, (t, r) in enumerate(zip(taps, taps_ref)):
+        rel, cos = _rel(t, r), _cos(t, r)
+        print(f"tap {k} (after layer {cfg.tap_layers[k]}): rel {rel:.4f} cos {cos:.6f}")
+        assert rel <= 2e-2 and cos >= 0.999, f"tap {k}: rel {rel:.4f} cos {cos:.6f}"
+    with torch.no_grad():
+        feats, _ = p(input_features=wave)
+    rel, cos = _rel(feats, feats_ref), _cos(feats, feats_ref)
+    print(f"connector out: rel {rel:.4f} cos {cos:.6f}")
+    assert rel <= 2e-2 and cos >= 0.999, f"connector out: rel {rel:.4f} cos {cos:.6f}"
