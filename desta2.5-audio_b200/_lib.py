@@ -1,7 +1,7 @@
 """ctypes binding of libdesta_b200.so (C ABI in include/desta_b200.h).  Fails loudly when the library is absent."""
 import ctypes
 import os
-from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_uint32, c_uint64, c_void_p
+from ctypes import CFUNCTYPE, POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_uint32, c_uint64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DESTA_B200_LIB") or os.path.join(HERE, "libdesta_b200.so")   # override: A/B runs of two builds
@@ -45,6 +45,21 @@ class ConnectorWeights(Structure):
                 ("layers", POINTER(QfLayer))]
 
 
+class DropoutPlan(Structure):
+    _fields_ = [("p_hidden", c_float), ("p_attn", c_float), ("seed", c_uint64)]
+
+
+class QfLayerT(Structure):
+    _fields_ = [(n, c_void_p) for n in ("s_qkv", "s_o", "c_q", "c_o", "f1", "f2")]
+
+
+class ConnectorWeightsT(Structure):
+    _fields_ = [("proj", c_void_p), ("layers", POINTER(QfLayerT))]
+
+
+GRAD_READY_FN = CFUNCTYPE(None, c_void_p, c_size_t, c_size_t)
+
+
 class SpliceDesc(Structure):
     _fields_ = [("prompt", c_int32), ("start", c_int32), ("n_trans", c_int32), ("trans_off", c_int32)]
 
@@ -83,6 +98,12 @@ EXPORTS = {
     "desta_connector_workspace_bytes": (c_size_t, [POINTER(Dims), c_int]),
     "desta_connector_fwd": (c_int, [POINTER(Dims), POINTER(ConnectorWeights), c_void_p, c_int, c_void_p, c_size_t, c_void_p,
                                     c_void_p]),
+    "desta_connector_train_workspace_bytes": (c_size_t, [POINTER(Dims), c_int]),
+    "desta_connector_grad_floats": (c_size_t, [POINTER(Dims)]),
+    "desta_connector_train_fwd": (c_int, [POINTER(Dims), POINTER(ConnectorWeights), c_void_p, c_int, c_void_p, c_size_t,
+                                          POINTER(DropoutPlan), c_void_p, c_void_p]),
+    "desta_connector_bwd": (c_int, [POINTER(Dims), POINTER(ConnectorWeights), POINTER(ConnectorWeightsT), c_void_p, c_int, c_void_p,
+                                    c_size_t, POINTER(DropoutPlan), c_void_p, c_void_p, c_size_t, GRAD_READY_FN, c_void_p, c_void_p]),
     "desta_splice": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, POINTER(SpliceDesc), c_int, c_void_p, c_void_p, c_int,
                              c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
 }

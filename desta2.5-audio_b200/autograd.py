@@ -16,7 +16,10 @@ from typing import Dict, List
 
 import torch
 
+import ctypes
+
 from . import engine, ops
+from ._lib import ConnectorWeightsT, DropoutPlan, GRAD_READY_FN, QfLayerT, check, lib
 from .engine import CON, PathDims
 
 
@@ -46,6 +49,9 @@ class ConnectorTPack:
                 f2=_bf16_t(get(p + "output.dense.weight")),
             ))
         self.proj = _bf16_t(get("proj.1.weight"))
+        names = ("s_qkv", "s_o", "c_q", "c_o", "f1", "f2")
+        self._c_layers = (QfLayerT * dims.qf_layers)(*[QfLayerT(*[L[k].data_ptr() for k in names]) for L in self.layers])
+        self.c_weights = ConnectorWeightsT(self.proj.data_ptr(), self._c_layers)
 
 
 SITE_SELF_PROBS, SITE_SELF_OUT, SITE_CROSS_PROBS, SITE_CROSS_OUT, SITE_FFN_OUT = range(5)
@@ -65,20 +71,42 @@ class DropPlan:
         p = self.p_attn if which in (SITE_SELF_PROBS, SITE_CROSS_PROBS) else self.p_hidden
         return ops.make_dropout(p, self.seed, layer * 8 + which)
 
+    def c_struct(self) -> DropoutPlan:
+        return DropoutPlan(self.p_hidden, self.p_attn, self.seed & 0xFFFFFFFFFFFFFFFF)
+
 
 NO_DROP = DropPlan()
 
 
 class TrainState:
-    """Saved activations (per Q-Former layer) + gradient buffers for one batch size."""
+    """Gradient arena + (lazily) the saved activations of one batch size: one byte workspace for the native stage entry
+    points (desta_connector_train_fwd / desta_connector_bwd), or - when the per-op schedule runs (profiling) - the
+    individual activation buffers."""
 
-    def __init__(self, dims: PathDims, N: int, device):
+    _PY = ("layers", "x_out", "x_out_bf", "mix", "mix_bf", "dkv", "g_f32_a", "g_f32_b", "g_f32_c", "g_bf_a", "g_bf_b", "g_qkv",
+           "g_ff", "g_h1", "g_out_bf", "g_mix", "g_mixn", "g_x")
+
+    def __getattr__(self, name):
+        if name in TrainState._PY:                      # first use of the per-op schedule: allocate its buffers
+            self._alloc_py()
+            return self.__dict__[name]
+        raise AttributeError(name)
+
+    def native_ws(self) -> torch.Tensor:
+        if self._native_ws is None:
+            nbytes = lib().desta_connector_train_workspace_bytes(ctypes.byref(self._c_dims), self.N)
+            if nbytes == 0:
+                raise ValueError(f"unsupported dims for the native training schedule: {lib().desta_last_error().decode()}")
+            self._native_ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        return self._native_ws
+
+    def _alloc_py(self):
+        dims, N, device = self.dims, self.N, self.device
         d, Q, T = dims.d_model, dims.prompt_size, dims.max_pos
         K, L, H = len(dims.tap_layers), dims.qf_layers, dims.n_heads
         R, B = K * N * Q, K * N
         bf, f32 = torch.bfloat16, torch.float32
         e = lambda *s, dt=bf: torch.empty(*s, dtype=dt, device=device)  # noqa: E731
-        self.N = N
         self.layers = [dict(x_bf=e(R, d), x_f32=e(R, d, dt=f32), qkv=e(R, 3 * d), lse_s=e(B * H * Q, dt=f32), ao_s=e(R, d),
                             t1=e(R, d, dt=f32), a_bf=e(R, d), a_f32=e(R, d, dt=f32), q_c=e(R, d), lse_c=e(B * H * Q, dt=f32),
                             ao_c=e(R, d), t2=e(R, d, dt=f32), c_bf=e(R, d), c_f32=e(R, d, dt=f32), h1=e(R, dims.qf_ffn),
@@ -101,6 +129,14 @@ class TrainState:
         self.g_mix = e(N * Q, d, dt=f32)
         self.g_mixn = e(N * Q, d, dt=f32)
         self.g_x = e(R, d, dt=f32)
+
+    def __init__(self, dims: PathDims, N: int, device):
+        d, Q, T = dims.d_model, dims.prompt_size, dims.max_pos
+        K, L, H = len(dims.tap_layers), dims.qf_layers, dims.n_heads
+        f32 = torch.float32
+        self.dims, self.N, self.device = dims, N, device
+        self._c_dims = dims.c_struct()
+        self._native_ws = None
         # gradient buffers (fp32, fused like the packed weights): views of ONE arena, so that zeroing them and handing a
         # private copy to autograd are single launches instead of one per tensor (165 parameters at the flagship size)
         shapes = dict(layer_weights=(Q, K), prompts=(K * Q, d), kv_w=(L * 2 * d, d), kv_b=(L * 2 * d,),
@@ -116,6 +152,8 @@ class TrainState:
             return (n + 3) // 4 * 4                     # keep every buffer 16-byte aligned
 
         total = sum(numel(v) for v in shapes.values()) + L * sum(numel(v) for v in lshapes.values())
+        native_total = lib().desta_connector_grad_floats(ctypes.byref(self._c_dims))
+        assert native_total in (0, total), (native_total, total)     # the C schedule carves the same layout
         self.arena = torch.zeros(total, dtype=f32, device=device)
         off = 0
 
@@ -270,6 +308,28 @@ def _drop_grad(st: TrainState, drop):
     return st.g_f32_c
 
 
+def connector_forward_train_native(con, dims: PathDims, ws, st: TrainState, out_f32, plan: DropPlan = NO_DROP):
+    """The same schedule as connector_forward_train as ONE call (desta_connector_train_fwd)."""
+    wsb = st.native_ws()
+    cplan = plan.c_struct()
+    ops.STATS["launches"] += 2 + 13 * dims.qf_layers + 3
+    check(lib().desta_connector_train_fwd(ctypes.byref(st._c_dims), ctypes.byref(con.c_weights), ops._p(ws.taps), ws.N, ops._p(wsb),
+                                          wsb.numel(), ctypes.byref(cplan), ops._p(out_f32), ops._stream()), "desta_connector_train_fwd")
+    return out_f32
+
+
+def connector_backward_native(con, conT: ConnectorTPack, dims: PathDims, ws, st: TrainState, grad_out, plan: DropPlan = NO_DROP,
+                              on_ready=None):
+    """The same schedule as connector_backward as ONE call (desta_connector_bwd); `on_ready` as there."""
+    wsb = st.native_ws()
+    cplan = plan.c_struct()
+    cb = GRAD_READY_FN(lambda _user, first, count: on_ready(st.arena[first:first + count])) if on_ready is not None else GRAD_READY_FN()
+    ops.STATS["launches"] += 6 + 26 * dims.qf_layers + len(dims.tap_layers) + 2
+    check(lib().desta_connector_bwd(ctypes.byref(st._c_dims), ctypes.byref(con.c_weights), ctypes.byref(conT.c_weights), ops._p(ws.taps),
+                                    ws.N, ops._p(wsb), wsb.numel(), ctypes.byref(cplan), ops._p(grad_out), ops._p(st.arena),
+                                    st.arena.numel(), cb, None, ops._stream()), "desta_connector_bwd")
+
+
 def param_order(connector) -> List[str]:
     return [n for n, _ in connector.named_parameters()]
 
@@ -310,7 +370,9 @@ class _ConnectorFn(torch.autograd.Function):
         st = perception._train_state(N)
         out = torch.empty(N * perception.dims.prompt_size, perception.dims.d_llm, dtype=torch.float32, device=ws.h.device)
         plan = perception._drop_plan()
-        connector_forward_train(con, perception.dims, ws, st, out, plan)
+        native = engine._native_enabled()
+        (connector_forward_train_native if native else connector_forward_train)(con, perception.dims, ws, st, out, plan)
+        ctx.native = native
         ctx.perception, ctx.N, ctx.plan = perception, N, plan
         return out.view(N, perception.dims.prompt_size, perception.dims.d_llm)
 
@@ -323,7 +385,8 @@ class _ConnectorFn(torch.autograd.Function):
         st.zero_grads()
         g = grad_out.to(torch.float32).contiguous().view(N * p.dims.prompt_size, p.dims.d_llm)
         sync = getattr(p, "grad_sync", None)       # data-parallel all-reduce overlapped with the backward (dist.GradSync)
-        connector_backward(con, conT, p.dims, ws, st, g, ctx.plan, on_ready=sync.reduce if sync is not None else None)
+        (connector_backward_native if ctx.native else connector_backward)(
+            con, conT, p.dims, ws, st, g, ctx.plan, on_ready=sync.reduce if sync is not None else None)
         if sync is not None:
             sync.finish(st.arena)
         # one private copy of the whole gradient arena; the per-parameter gradients are views of it (same offsets)

@@ -180,3 +180,255 @@ extern "C" int desta_connector_fwd(const desta_dims* dims, const desta_connector
   RUN(gemm(ws.mix_bf, d, w->proj_w, d, N * Q, dims->d_llm, d, w->proj_b, nullptr, 0, out, dims->d_llm, nullptr, 0, nullptr, 0, 1.f, 0, 0, stream));
   return DESTA_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Connector training: forward with saved activations + hand-scheduled backward (row a6).  Same launches, same order as
+// the host-side per-op schedule in desta_b200/autograd.py (kept as the reference for this schedule; tested bit-identical).
+// ---------------------------------------------------------------------------------------------------------------------
+namespace desta {
+
+struct TrainLayer {
+  __nv_bfloat16 *x_bf, *qkv, *ao_s, *a_bf, *q_c, *ao_c, *c_bf, *h1, *f;
+  float *x_f32, *lse_s, *t1, *a_f32, *lse_c, *t2, *c_f32, *t3;
+};
+struct TrainWs {
+  __nv_bfloat16 *kv, *x_out_bf, *mix_bf, *dkv, *g_bf_a, *g_bf_b, *g_qkv, *g_ff, *g_h1, *g_out_bf;
+  float *x_out, *mix, *g_f32_a, *g_f32_b, *g_f32_c, *g_mix, *g_mixn, *g_x;
+  TrainLayer layer[32];
+  size_t bytes;
+};
+static TrainWs carve_train(const desta_dims* d, int N, void* ws) {
+  Carver c{(uint8_t*)ws, 0};
+  const size_t D = d->d_model, K = d->n_taps, Q = d->prompt_size, T = d->max_pos, H = d->n_heads, F = d->qf_ffn, L = d->qf_layers;
+  const size_t R = K * N * Q, B = K * N, NQ = (size_t)N * Q;
+  TrainWs w;
+  w.kv = (__nv_bfloat16*)c.take(K * N * T * L * 2 * D * 2);
+  for (size_t l = 0; l < L; ++l) {
+    TrainLayer& S = w.layer[l];
+    S.x_bf = (__nv_bfloat16*)c.take(R * D * 2);   S.x_f32 = (float*)c.take(R * D * 4);
+    S.qkv = (__nv_bfloat16*)c.take(R * 3 * D * 2); S.lse_s = (float*)c.take(B * H * Q * 4);
+    S.ao_s = (__nv_bfloat16*)c.take(R * D * 2);    S.t1 = (float*)c.take(R * D * 4);
+    S.a_bf = (__nv_bfloat16*)c.take(R * D * 2);    S.a_f32 = (float*)c.take(R * D * 4);
+    S.q_c = (__nv_bfloat16*)c.take(R * D * 2);     S.lse_c = (float*)c.take(B * H * Q * 4);
+    S.ao_c = (__nv_bfloat16*)c.take(R * D * 2);    S.t2 = (float*)c.take(R * D * 4);
+    S.c_bf = (__nv_bfloat16*)c.take(R * D * 2);    S.c_f32 = (float*)c.take(R * D * 4);
+    S.h1 = (__nv_bfloat16*)c.take(R * F * 2);      S.f = (__nv_bfloat16*)c.take(R * F * 2);
+    S.t3 = (float*)c.take(R * D * 4);
+  }
+  w.x_out = (float*)c.take(R * D * 4);    w.x_out_bf = (__nv_bfloat16*)c.take(R * D * 2);
+  w.mix = (float*)c.take(NQ * D * 4);     w.mix_bf = (__nv_bfloat16*)c.take(NQ * D * 2);
+  w.dkv = (__nv_bfloat16*)c.take(K * N * T * L * 2 * D * 2);
+  w.g_f32_a = (float*)c.take(R * D * 4);  w.g_f32_b = (float*)c.take(R * D * 4);  w.g_f32_c = (float*)c.take(R * D * 4);
+  w.g_bf_a = (__nv_bfloat16*)c.take(R * D * 2); w.g_bf_b = (__nv_bfloat16*)c.take(R * D * 2);
+  w.g_qkv = (__nv_bfloat16*)c.take(R * 3 * D * 2);
+  w.g_ff = (__nv_bfloat16*)c.take(R * F * 2);   w.g_h1 = (__nv_bfloat16*)c.take(R * F * 2);
+  w.g_out_bf = (__nv_bfloat16*)c.take(NQ * (size_t)d->d_llm * 2);
+  w.g_mix = (float*)c.take(NQ * D * 4);   w.g_mixn = (float*)c.take(NQ * D * 4);
+  w.g_x = (float*)c.take(R * D * 4);
+  w.bytes = c.off;
+  return w;
+}
+
+// gradient arena (floats), same order / padding as desta_b200/autograd.py TrainState
+struct GradLayer { float *s_qkv_w, *s_qkv_b, *s_o_w, *s_o_b, *s_ln_w, *s_ln_b, *c_q_w, *c_q_b, *c_o_w, *c_o_b, *c_ln_w, *c_ln_b,
+                         *f1_w, *f1_b, *f2_w, *f2_b, *f_ln_w, *f_ln_b; size_t first, count; };
+struct GradArena { float *layer_weights, *prompts, *kv_w, *kv_b, *proj_ln_w, *proj_ln_b, *proj_w, *proj_b; size_t global_count;
+                   GradLayer layer[32]; size_t floats; };
+static GradArena carve_grads(const desta_dims* d, float* base) {
+  size_t off = 0;
+  auto take = [&](size_t n) { float* p = base ? base + off : nullptr; off += (n + 3) / 4 * 4; return p; };
+  const size_t D = d->d_model, K = d->n_taps, Q = d->prompt_size, F = d->qf_ffn, L = d->qf_layers, DL = d->d_llm;
+  GradArena g;
+  g.layer_weights = take(Q * K); g.prompts = take(K * Q * D); g.kv_w = take(L * 2 * D * D); g.kv_b = take(L * 2 * D);
+  g.proj_ln_w = take(D); g.proj_ln_b = take(D); g.proj_w = take(DL * D); g.proj_b = take(DL);
+  g.global_count = off;
+  for (size_t l = 0; l < L; ++l) {
+    GradLayer& x = g.layer[l];
+    x.first = off;
+    x.s_qkv_w = take(3 * D * D); x.s_qkv_b = take(3 * D); x.s_o_w = take(D * D); x.s_o_b = take(D); x.s_ln_w = take(D); x.s_ln_b = take(D);
+    x.c_q_w = take(D * D); x.c_q_b = take(D); x.c_o_w = take(D * D); x.c_o_b = take(D); x.c_ln_w = take(D); x.c_ln_b = take(D);
+    x.f1_w = take(F * D); x.f1_b = take(F); x.f2_w = take(D * F); x.f2_b = take(D); x.f_ln_w = take(D); x.f_ln_b = take(D);
+    x.count = off - x.first;
+  }
+  g.floats = off;
+  return g;
+}
+
+static bool site(const desta_dropout_plan* plan, int layer, int which, desta_dropout* out) {
+  if (!plan) return false;
+  const float p = (which == 0 || which == 2) ? plan->p_attn : plan->p_hidden;
+  long thr = lroundf(p * 65536.0f);
+  if (thr <= 0) return false;
+  if (thr > 65535) thr = 65535;
+  out->thr16 = (uint32_t)thr;
+  out->scale = (float)(1.0 / (1.0 - (double)thr / 65536.0));
+  out->seed = plan->seed;
+  out->site = (uint32_t)(layer * 8 + which);
+  return true;
+}
+
+// t = dropout(a W^T + b) + resid  (BertSelfOutput / BertOutput before their LayerNorm)
+static int dense_res(const void* a, int lda, const void* W, int M, int N, int K, const float* bias, float* t, const float* resid,
+                     const desta_dropout_plan* plan, int layer, int which, void* stream) {
+  desta_dropout dr;
+  if (!site(plan, layer, which, &dr)) return gemm(a, lda, W, K, M, N, K, bias, nullptr, 0, t, N, resid, N, nullptr, 0, 1.f, 0, 0, stream);
+  int rc = gemm(a, lda, W, K, M, N, K, bias, nullptr, 0, t, N, nullptr, 0, nullptr, 0, 1.f, 0, 0, stream);
+  if (rc) return rc;
+  return desta_dropout_add(t, N, resid, N, M, N, &dr, t, N, nullptr, 0, stream);
+}
+
+}  // namespace desta
+
+extern "C" size_t desta_connector_train_workspace_bytes(const desta_dims* dims, int N) {
+  if (check_dims(dims, "desta_connector_train_workspace_bytes") || N <= 0 || dims->qf_layers > 32) return 0;
+  return carve_train(dims, N, nullptr).bytes;
+}
+
+extern "C" size_t desta_connector_grad_floats(const desta_dims* dims) {
+  if (check_dims(dims, "desta_connector_grad_floats") || dims->qf_layers > 32) return 0;
+  return carve_grads(dims, nullptr).floats;
+}
+
+extern "C" int desta_connector_train_fwd(const desta_dims* dims, const desta_connector_weights* w, const void* taps, int N,
+                                         void* workspace, size_t workspace_bytes, const desta_dropout_plan* plan, float* out,
+                                         void* stream) {
+  RUN(check_dims(dims, "desta_connector_train_fwd"));
+  if (!w || !w->layers || !taps || !workspace || !out || dims->qf_layers > 32) { set_error("desta_connector_train_fwd: bad argument"); return DESTA_ERR_ARG; }
+  if (N <= 0) return DESTA_OK;
+  TrainWs ws = carve_train(dims, N, workspace);
+  if (workspace_bytes < ws.bytes) { set_error("desta_connector_train_fwd: workspace too small (%zu < %zu)", workspace_bytes, ws.bytes); return DESTA_ERR_ARG; }
+  const int d = dims->d_model, T = dims->max_pos, Q = dims->prompt_size, K = dims->n_taps, H = dims->n_heads, F = dims->qf_ffn;
+  const int B = K * N, R = B * Q, ldkv = dims->qf_layers * 2 * d, L = dims->qf_layers;
+  const float scale = 1.0f / sqrtf((float)(d / H));
+  RUN(gemm(taps, d, w->kv_w, d, K * N * T, ldkv, d, w->kv_b, ws.kv, ldkv, nullptr, 0, nullptr, 0, nullptr, 0, 1.f, 0, 0, stream));
+  {
+    const size_t total = (size_t)B * (Q * d / 4);
+    size_t blocks = (total + 255) / 256;
+    const size_t cap = (size_t)num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    broadcast_prompts_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(w->prompts, K, N, Q * d, ws.layer[0].x_f32, ws.layer[0].x_bf);
+    RUN(check_launch("broadcast_prompts_kernel"));
+  }
+  for (int l = 0; l < L; ++l) {
+    const desta_qf_layer& P = w->layers[l];
+    TrainLayer& S = ws.layer[l];
+    desta_dropout dr;
+    RUN(gemm(S.x_bf, d, P.s_qkv_w, d, R, 3 * d, d, P.s_qkv_b, S.qkv, 3 * d, nullptr, 0, nullptr, 0, nullptr, 0, 1.f, 0, 0, stream));
+    RUN(desta_attention(S.qkv, 3 * d, S.qkv + d, 3 * d, S.qkv + 2 * d, 3 * d, S.ao_s, d, B, H, Q, Q, scale, S.lse_s,
+                        site(plan, l, 0, &dr) ? &dr : nullptr, stream));
+    RUN(dense_res(S.ao_s, d, P.s_o_w, R, d, d, P.s_o_b, S.t1, S.x_f32, plan, l, 1, stream));
+    RUN(desta_layernorm(S.t1, d, P.s_ln_w, P.s_ln_b, 1e-12f, R, d, S.a_bf, d, S.a_f32, d, stream));
+    RUN(gemm(S.a_bf, d, P.c_q_w, d, R, d, d, P.c_q_b, S.q_c, d, nullptr, 0, nullptr, 0, nullptr, 0, 1.f, 0, 0, stream));
+    const __nv_bfloat16* kl = ws.kv + (size_t)l * 2 * d;
+    RUN(desta_attention(S.q_c, d, kl, ldkv, kl + d, ldkv, S.ao_c, d, B, H, Q, T, scale, S.lse_c, site(plan, l, 2, &dr) ? &dr : nullptr, stream));
+    RUN(dense_res(S.ao_c, d, P.c_o_w, R, d, d, P.c_o_b, S.t2, S.a_f32, plan, l, 3, stream));
+    RUN(desta_layernorm(S.t2, d, P.c_ln_w, P.c_ln_b, 1e-12f, R, d, S.c_bf, d, S.c_f32, d, stream));
+    RUN(gemm(S.c_bf, d, P.f1_w, d, R, F, d, P.f1_b, S.h1, F, nullptr, 0, nullptr, 0, nullptr, 0, 1.f, 0, 0, stream));   // pre-activation kept
+    RUN(desta_gelu_fwd(S.h1, S.f, (size_t)R * F, stream));
+    RUN(dense_res(S.f, F, P.f2_w, R, d, F, P.f2_b, S.t3, S.c_f32, plan, l, 4, stream));
+    __nv_bfloat16* nx_bf = l + 1 < L ? ws.layer[l + 1].x_bf : ws.x_out_bf;
+    float* nx_f32 = l + 1 < L ? ws.layer[l + 1].x_f32 : ws.x_out;
+    RUN(desta_layernorm(S.t3, d, P.f_ln_w, P.f_ln_b, 1e-12f, R, d, nx_bf, d, nx_f32, d, stream));
+  }
+  RUN(desta_layer_mix(ws.x_out, w->layer_weights, K, N, Q, d, ws.mix, stream));
+  RUN(desta_layernorm(ws.mix, d, w->proj_ln_w, w->proj_ln_b, 1e-5f, N * Q, d, ws.mix_bf, d, nullptr, 0, stream));
+  RUN(gemm(ws.mix_bf, d, w->proj_w, d, N * Q, dims->d_llm, d, w->proj_b, nullptr, 0, out, dims->d_llm, nullptr, 0, nullptr, 0, 1.f, 0, 0, stream));
+  return DESTA_OK;
+}
+
+extern "C" int desta_connector_bwd(const desta_dims* dims, const desta_connector_weights* w, const desta_connector_weights_t* wt,
+                                   const void* taps, int N, void* workspace, size_t workspace_bytes, const desta_dropout_plan* plan,
+                                   const float* grad_out, float* grad_arena, size_t arena_floats, desta_grad_ready_fn on_ready,
+                                   void* user, void* stream) {
+  RUN(check_dims(dims, "desta_connector_bwd"));
+  if (!w || !w->layers || !wt || !wt->layers || !taps || !workspace || !grad_out || !grad_arena || dims->qf_layers > 32) {
+    set_error("desta_connector_bwd: bad argument");
+    return DESTA_ERR_ARG;
+  }
+  if (N <= 0) return DESTA_OK;
+  TrainWs ws = carve_train(dims, N, workspace);
+  if (workspace_bytes < ws.bytes) { set_error("desta_connector_bwd: workspace too small (%zu < %zu)", workspace_bytes, ws.bytes); return DESTA_ERR_ARG; }
+  GradArena G = carve_grads(dims, grad_arena);
+  if (arena_floats < G.floats) { set_error("desta_connector_bwd: gradient arena too small (%zu < %zu floats)", arena_floats, G.floats); return DESTA_ERR_ARG; }
+  const int d = dims->d_model, T = dims->max_pos, Q = dims->prompt_size, K = dims->n_taps, H = dims->n_heads, F = dims->qf_ffn;
+  const int B = K * N, R = B * Q, ldkv = dims->qf_layers * 2 * d, L = dims->qf_layers, DL = dims->d_llm, NQ = N * Q;
+  const float scale = 1.0f / sqrtf((float)(d / H));
+  // masks g_f32_a into (g_f32_c fp32, g_bf_a bf16) for a dropped dense branch; returns the fp32 gradient of its bias
+  auto drop_grad = [&](int l, int which, const float** gd) -> int {
+    desta_dropout dr;
+    *gd = ws.g_f32_a;
+    if (!site(plan, l, which, &dr)) return DESTA_OK;
+    *gd = ws.g_f32_c;
+    return desta_dropout_add(ws.g_f32_a, d, nullptr, 0, R, d, &dr, ws.g_f32_c, d, ws.g_bf_a, d, stream);
+  };
+  auto dgrad = [&](const void* a, int lda, const void* Wt, int M, int Nn, int Kk, void* out_bf16, float* out_f32, const float* resid) {
+    return gemm(a, lda, Wt, Kk, M, Nn, Kk, nullptr, out_bf16, Nn, out_f32, Nn, resid, Nn, nullptr, 0, 1.f, 0, 0, stream);
+  };
+  // ---- proj: out = LN(mix) Wp^T + bp ----
+  RUN(desta_cast_f32_bf16(grad_out, ws.g_out_bf, (size_t)NQ * DL, stream));
+  RUN(desta_gemm_bf16_wgrad(ws.g_out_bf, DL, ws.mix_bf, d, NQ, DL, d, G.proj_w, d, stream));
+  RUN(desta_colsum(grad_out, 0, DL, NQ, DL, G.proj_b, stream));
+  RUN(dgrad(ws.g_out_bf, DL, wt->proj, NQ, d, DL, nullptr, ws.g_mixn, nullptr));
+  RUN(desta_layernorm_bwd(ws.g_mixn, d, ws.mix, d, w->proj_ln_w, 1e-5f, NQ, d, ws.g_mix, d, nullptr, 0, G.proj_ln_w, G.proj_ln_b, stream));
+  // ---- layer mix ----
+  RUN(desta_layer_mix_bwd(ws.g_mix, ws.x_out, w->layer_weights, K, N, Q, d, ws.g_x, G.layer_weights, stream));
+  const float* dx = ws.g_x;
+  for (int l = L - 1; l >= 0; --l) {
+    const desta_qf_layer& P = w->layers[l];
+    const desta_qf_layer_t& PT = wt->layers[l];
+    TrainLayer& S = ws.layer[l];
+    GradLayer& g = G.layer[l];
+    const float* gd;
+    desta_dropout dr;
+    // x' = LN(t3)
+    RUN(desta_layernorm_bwd(dx, d, S.t3, d, P.f_ln_w, 1e-12f, R, d, ws.g_f32_a, d, ws.g_bf_a, d, g.f_ln_w, g.f_ln_b, stream));
+    // t3 = dropout(f W2^T + b2) + c
+    RUN(drop_grad(l, 4, &gd));
+    RUN(desta_gemm_bf16_wgrad(ws.g_bf_a, d, S.f, F, R, d, F, g.f2_w, F, stream));
+    RUN(desta_colsum(gd, 0, d, R, d, g.f2_b, stream));
+    RUN(dgrad(ws.g_bf_a, d, PT.f2, R, F, d, ws.g_ff, nullptr, nullptr));                       // df
+    RUN(desta_gelu_bwd(ws.g_ff, S.h1, ws.g_h1, (size_t)R * F, stream));                          // dh1
+    // h1 = c W1^T + b1
+    RUN(desta_gemm_bf16_wgrad(ws.g_h1, F, S.c_bf, d, R, F, d, g.f1_w, d, stream));
+    RUN(desta_colsum(ws.g_h1, 1, F, R, F, g.f1_b, stream));
+    RUN(dgrad(ws.g_h1, F, PT.f1, R, d, F, nullptr, ws.g_f32_b, ws.g_f32_a));                    // dc = dt3 + dh1 W1
+    // c = LN(t2)
+    RUN(desta_layernorm_bwd(ws.g_f32_b, d, S.t2, d, P.c_ln_w, 1e-12f, R, d, ws.g_f32_a, d, ws.g_bf_a, d, g.c_ln_w, g.c_ln_b, stream));
+    // t2 = dropout(ao_c Wco^T + b) + a
+    RUN(drop_grad(l, 3, &gd));
+    RUN(desta_gemm_bf16_wgrad(ws.g_bf_a, d, S.ao_c, d, R, d, d, g.c_o_w, d, stream));
+    RUN(desta_colsum(gd, 0, d, R, d, g.c_o_b, stream));
+    RUN(dgrad(ws.g_bf_a, d, PT.c_o, R, d, d, ws.g_bf_b, nullptr, nullptr));                     // d(ao_c)
+    const __nv_bfloat16* kl = ws.kv + (size_t)l * 2 * d;
+    __nv_bfloat16* dkl = ws.dkv + (size_t)l * 2 * d;
+    RUN(desta_attention_bwd(S.q_c, d, kl, ldkv, kl + d, ldkv, S.ao_c, d, ws.g_bf_b, d, S.lse_c, ws.g_qkv, 3 * d, dkl, ldkv, dkl + d, ldkv,
+                            B, H, Q, T, scale, site(plan, l, 2, &dr) ? &dr : nullptr, stream));
+    // q_c = a Wq^T + bq   (dq_c = first d columns of g_qkv)
+    RUN(desta_gemm_bf16_wgrad(ws.g_qkv, 3 * d, S.a_bf, d, R, d, d, g.c_q_w, d, stream));
+    RUN(desta_colsum(ws.g_qkv, 1, 3 * d, R, d, g.c_q_b, stream));
+    RUN(dgrad(ws.g_qkv, 3 * d, PT.c_q, R, d, d, nullptr, ws.g_f32_b, ws.g_f32_a));              // da = dt2 + dq_c Wq
+    // a = LN(t1)
+    RUN(desta_layernorm_bwd(ws.g_f32_b, d, S.t1, d, P.s_ln_w, 1e-12f, R, d, ws.g_f32_a, d, ws.g_bf_a, d, g.s_ln_w, g.s_ln_b, stream));
+    // t1 = dropout(ao_s Wso^T + b) + x
+    RUN(drop_grad(l, 1, &gd));
+    RUN(desta_gemm_bf16_wgrad(ws.g_bf_a, d, S.ao_s, d, R, d, d, g.s_o_w, d, stream));
+    RUN(desta_colsum(gd, 0, d, R, d, g.s_o_b, stream));
+    RUN(dgrad(ws.g_bf_a, d, PT.s_o, R, d, d, ws.g_bf_b, nullptr, nullptr));                     // d(ao_s)
+    RUN(desta_attention_bwd(S.qkv, 3 * d, S.qkv + d, 3 * d, S.qkv + 2 * d, 3 * d, S.ao_s, d, ws.g_bf_b, d, S.lse_s, ws.g_qkv, 3 * d,
+                            ws.g_qkv + d, 3 * d, ws.g_qkv + 2 * d, 3 * d, B, H, Q, Q, scale, site(plan, l, 0, &dr) ? &dr : nullptr, stream));
+    // qkv = x Wqkv^T + b
+    RUN(desta_gemm_bf16_wgrad(ws.g_qkv, 3 * d, S.x_bf, d, R, 3 * d, d, g.s_qkv_w, d, stream));
+    RUN(desta_colsum(ws.g_qkv, 1, 3 * d, R, 3 * d, g.s_qkv_b, stream));
+    RUN(dgrad(ws.g_qkv, 3 * d, PT.s_qkv, R, d, 3 * d, nullptr, ws.g_x, ws.g_f32_a));            // dx = dt1 + dqkv Wqkv
+    dx = ws.g_x;
+    if (on_ready) on_ready(user, g.first, g.count);
+  }
+  // ---- learned prompts: x0[k, n] = layer_prompts[k] for every clip n ----
+  for (int k = 0; k < K; ++k)
+    RUN(desta_colsum(dx + (size_t)k * N * Q * d, 0, Q * d, N, Q * d, G.prompts + (size_t)k * Q * d, stream));
+  // ---- cross-attention K/V projections of all layers: one weight-gradient GEMM over all taps' rows ----
+  RUN(desta_gemm_bf16_wgrad(ws.dkv, ldkv, taps, d, K * N * T, ldkv, d, G.kv_w, d, stream));
+  RUN(desta_colsum(ws.dkv, 1, ldkv, K * N * T, ldkv, G.kv_b, stream));
+  if (on_ready) on_ready(user, 0, G.global_count);
+  return DESTA_OK;
+}

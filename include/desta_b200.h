@@ -187,6 +187,34 @@ size_t desta_connector_workspace_bytes(const desta_dims* dims, int N);
 int desta_connector_fwd(const desta_dims* dims, const desta_connector_weights* w, const void* taps, int N, void* workspace,
                         size_t workspace_bytes, float* out, void* stream);
 
+/* ---- (3b) connector training as two stage-level calls: the forward that keeps the activations the backward needs,
+ *      and the backward that fills ONE fp32 gradient arena (row a6: autograd of modeling_desta25.py:587-606 over
+ *      $TF/models/bert/modeling_bert.py; only the connector is trainable, :1456-1463, so taps get no gradient).
+ *      Arena layout (every tensor padded to a multiple of 4 floats): layer_weights [Q,taps], prompts [taps*Q,d],
+ *      kv_w [L*2d,d], kv_b [L*2d], proj_ln_w [d], proj_ln_b [d], proj_w [d_llm,d], proj_b [d_llm]; then per Q-Former
+ *      layer: s_qkv_w [3d,d], s_qkv_b, s_o_w [d,d], s_o_b, s_ln_w, s_ln_b, c_q_w [d,d], c_q_b, c_o_w [d,d], c_o_b, c_ln_w,
+ *      c_ln_b, f1_w [ffn,d], f1_b, f2_w [d,ffn], f2_b, f_ln_w, f_ln_b  (= the fused layouts of desta_connector_weights).
+ *      Dropout: p_hidden / p_attn = 0 in eval mode; site = layer * 8 + {0 self probs, 1 self out, 2 cross probs,
+ *      3 cross out, 4 FFN out}; the backward regenerates the masks from the same seed. ---- */
+typedef struct desta_dropout_plan { float p_hidden, p_attn; uint64_t seed; } desta_dropout_plan;
+typedef struct desta_qf_layer_t {            /* transposed bf16 weights [in,out] for the data-gradient GEMMs */
+  const void *s_qkv, *s_o, *c_q, *c_o, *f1, *f2;
+} desta_qf_layer_t;
+typedef struct desta_connector_weights_t { const void* proj; const desta_qf_layer_t* layers; } desta_connector_weights_t;
+size_t desta_connector_train_workspace_bytes(const desta_dims* dims, int N);
+size_t desta_connector_grad_floats(const desta_dims* dims);
+int desta_connector_train_fwd(const desta_dims* dims, const desta_connector_weights* w, const void* taps, int N, void* workspace,
+                              size_t workspace_bytes, const desta_dropout_plan* plan, float* out, void* stream);
+/* grad_arena must be zeroed by the caller (gradients are accumulated).  on_ready(user, first_float, n_floats) - optional -
+ * is called on the host right after the launches that complete a contiguous arena range (one Q-Former layer at a time,
+ * last layer first; the leading non-layer range at the end), so that a data-parallel all-reduce can be enqueued behind
+ * them while the rest of the backward is still being issued. */
+typedef void (*desta_grad_ready_fn)(void* user, size_t first_float, size_t n_floats);
+int desta_connector_bwd(const desta_dims* dims, const desta_connector_weights* w, const desta_connector_weights_t* wt,
+                        const void* taps, int N, void* workspace, size_t workspace_bytes, const desta_dropout_plan* plan,
+                        const float* grad_out, float* grad_arena, size_t arena_floats, desta_grad_ready_fn on_ready,
+                        void* user, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
