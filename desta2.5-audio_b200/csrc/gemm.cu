@@ -38,8 +38,11 @@ struct GemmArgs {
   const float* pos; int pos_rows;
   float scale; int scale_cols;
   int gelu;
-  int splits;      // split-K factor (MODE_WGRAD); > 1 => fp32 atomic accumulation into out_f32
-  int atomic;
+  // work items (MODE_WGRAD): the first n_full tiles are one item each (whole reduction; dW += acc by plain
+  // read-modify-write through `resid`); the remaining tiles - the partial last wave of the persistent grid, or every tile
+  // of a small output - are split `splits` ways along the reduction and accumulate with fp32 atomics
+  int n_full;
+  int splits;
 };
 
 constexpr int MODE_TN = 0, MODE_WGRAD = 1;
@@ -59,9 +62,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = (g.M + BM - 1) / BM, n_tiles = (g.N + BN - 1) / BN;
-  const int num_tiles = m_tiles * n_tiles * g.splits;          // work items = (tile, k-split)
+  const int num_tiles = g.n_full + (m_tiles * n_tiles - g.n_full) * g.splits;          // work items
   const int k_blocks_total = (g.K + BK - 1) / BK;
   const int kb_per = (k_blocks_total + g.splits - 1) / g.splits;
+  // item -> (tile, k-block range, split?)
+  auto decode = [&](int item, int& tile, int& kb0, int& kb1) {
+    if (item < g.n_full) { tile = item; kb0 = 0; kb1 = k_blocks_total; return false; }
+    const int j = item - g.n_full;
+    tile = g.n_full + j / g.splits;
+    const int split = j - (j / g.splits) * g.splits;
+    kb0 = split * kb_per;
+    kb1 = min(k_blocks_total, kb0 + kb_per);
+    return g.splits > 1;
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -84,9 +97,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     {
       int stage = 0; uint32_t phase = 0;
       for (int item = blockIdx.x; item < num_tiles; item += gridDim.x) {
-        const int tile = item / g.splits, split = item - tile * g.splits;
+        int tile, kb0, kb1;
+        decode(item, tile, kb0, kb1);
         const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
-        const int kb0 = split * kb_per, kb1 = min(k_blocks_total, kb0 + kb_per);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait_sleep(&empty[stage], phase ^ 1);
           if (elect_one()) {
@@ -114,8 +127,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int stage = 0; uint32_t phase = 0;
       int local = 0;
       for (int item = blockIdx.x; item < num_tiles; item += gridDim.x, ++local) {
-        const int split = item % g.splits;
-        const int kb0 = split * kb_per, kb1 = min(k_blocks_total, kb0 + kb_per);
+        int tile_unused, kb0, kb1;
+        decode(item, tile_unused, kb0, kb1);
         const int as = local & 1;
         const uint32_t acc_phase = (local >> 1) & 1;
         mbar_wait(&acc_empty[as], acc_phase ^ 1);
@@ -156,7 +169,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int half = (warp - EPI_WARP0) >> 2;  // column half handled by this warp
     int local = 0;
     for (int item = blockIdx.x; item < num_tiles; item += gridDim.x, ++local) {
-      const int tile = item / g.splits;
+      int tile, kb0_unused, kb1_unused;
+      const bool atomic = decode(item, tile, kb0_unused, kb1_unused);
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
       const int as = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
@@ -213,7 +227,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int j = 0; j < 32; ++j) if (col0 + j < g.N) f[j] += __ldg(pos_row + col0 + j);
           }
         }
-        if (g.resid) {
+        if (g.resid && !atomic) {
           const float* r = g.resid + (size_t)row * g.ld_resid + col0;
           if (full_cols) {
 #pragma unroll
@@ -226,7 +240,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int j = 0; j < 32; ++j) if (col0 + j < g.N) f[j] += r[j];
           }
         }
-        if (g.out_f32 && g.atomic) {
+        if (g.out_f32 && atomic) {
           float* o = g.out_f32 + (size_t)row * g.ld_f32 + col0;
 #pragma unroll
           for (int j = 0; j < 32; ++j) if (col0 + j < g.N) atomicAdd(o + j, f[j]);
@@ -284,7 +298,7 @@ static int launch_gemm(int mode, const CUtensorMap& tmA, const CUtensorMap& tmB,
     attr_set = true;
   }
   const int m_tiles = (g.M + BM - 1) / BM, n_tiles = (g.N + BN - 1) / BN;
-  const int items = m_tiles * n_tiles * g.splits;
+  const int items = g.n_full + (m_tiles * n_tiles - g.n_full) * g.splits;
   const int grid = items < num_sms() ? items : num_sms();
   if (mode == MODE_TN) gemm_bf16_kernel<MODE_TN><<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(tmA, tmB, g);
   else gemm_bf16_kernel<MODE_WGRAD><<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(tmA, tmB, g);
@@ -317,7 +331,7 @@ extern "C" int desta_gemm_bf16(const void* A, int lda, const void* W, int ldw, i
   g.bias = ep->bias; g.resid = ep->resid; g.ld_resid = ep->ld_resid;
   g.pos = ep->pos; g.pos_rows = ep->pos_rows > 0 ? ep->pos_rows : 1;
   g.scale = ep->scale; g.scale_cols = ep->scale_cols; g.gelu = ep->gelu;
-  g.splits = 1; g.atomic = 0;
+  g.splits = 1; g.n_full = 0;
   return launch_gemm(MODE_TN, tmA, tmB, g, (cudaStream_t)stream);
 }
 
@@ -340,17 +354,23 @@ extern "C" int desta_gemm_bf16_wgrad(const void* dY, int ldy, const void* X, int
   g.pos_rows = 1; g.scale = 1.f;
   const int tiles = ((Nout + BM - 1) / BM) * ((Kin + BN - 1) / BN);
   const int kblocks = (Mred + BK - 1) / BK;
+  // The persistent grid runs one CTA per SM.  Full waves of tiles are processed whole; the tiles of the partial last wave
+  // (all tiles of a small output) are split along the reduction so that every SM gets a share of them: the K/V-projection
+  // weight gradient has 600 tiles = 4.05 waves on 148 SMs, and its 8 tail tiles would otherwise cost a whole fifth round.
+  const int sms = num_sms();
+  const int n_full = (tiles / sms) * sms;
+  const int tail = tiles - n_full;
   int splits = 1;
-  if (tiles < num_sms()) {                       // small outputs: spread the long reduction over the idle SMs
-    splits = num_sms() / tiles;
+  if (tail > 0) {
+    splits = sms / tail;
     const int max_splits = kblocks / 8 > 0 ? kblocks / 8 : 1;    // keep >= 8 k-blocks per split
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
+    const int kb_per = (kblocks + splits - 1) / splits;
+    splits = (kblocks + kb_per - 1) / kb_per;                    // no empty split
   }
-  const int kb_per = (kblocks + splits - 1) / splits;
-  splits = (kblocks + kb_per - 1) / kb_per;      // no empty split
+  g.n_full = splits > 1 ? n_full : tiles;
   g.splits = splits;
-  if (splits > 1) g.atomic = 1;                  // dW += partial (fp32 atomics)
-  else { g.resid = dW; g.ld_resid = ldw; }       // dW += acc (plain read-modify-write, one writer per element)
+  g.resid = dW; g.ld_resid = ldw;                                // whole-reduction items: dW += acc (one writer per element)
   return launch_gemm(MODE_WGRAD, tmA, tmB, g, (cudaStream_t)stream);
 }
