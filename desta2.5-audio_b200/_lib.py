@@ -64,12 +64,24 @@ class SpliceDesc(Structure):
     _fields_ = [("prompt", c_int32), ("start", c_int32), ("n_trans", c_int32), ("trans_off", c_int32)]
 
 
+class ResamplePlan(Structure):
+    _fields_ = [("L", c_int32), ("M", c_int32), ("P", c_int32), ("reserved", c_int32)]
+
+
+class PcmClip(Structure):
+    _fields_ = [("pcm", c_void_p), ("n_frames", c_int64), ("n_out", c_int64), ("out_row", c_int64)]
+
+
 EXPORTS = {
     "desta_version": (c_int, []),
     "desta_last_error": (c_char_p, []),
     "desta_logmel_plan_bytes": (c_size_t, [c_int]),
     "desta_logmel_plan_build": (c_int, [c_int, c_void_p, c_size_t]),
     "desta_logmel": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "desta_resample_plan_bytes": (c_size_t, [c_int, c_int, POINTER(ResamplePlan)]),
+    "desta_resample_plan_build": (c_int, [c_int, c_int, c_void_p, c_size_t]),
+    "desta_decode_resample": (c_int, [c_void_p, c_int, c_int, c_int, POINTER(ResamplePlan), c_void_p, c_void_p, c_int64, c_int64,
+                                      c_void_p]),
     "desta_gemm_bf16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, POINTER(GemmEpilogue), c_void_p]),
     "desta_layernorm": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_float, c_int, c_int, c_void_p, c_int, c_void_p,
                                 c_int, c_void_p]),

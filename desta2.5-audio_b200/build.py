@@ -9,7 +9,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdesta_b200.so")
 STAMP = os.path.join(HERE, "csrc", ".build_stamp")
-SOURCES = ["api.cu", "schedule.cu", "gemm.cu", "gemm2.cu", "attention.cu", "attention_bwd.cu", "elementwise.cu", "elementwise_bwd.cu", "logmel.cu", "splice.cu"]
+SOURCES = ["api.cu", "schedule.cu", "gemm.cu", "gemm2.cu", "attention.cu", "attention_bwd.cu", "elementwise.cu", "elementwise_bwd.cu", "logmel.cu", "splice.cu", "resample.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 

@@ -4,7 +4,7 @@ import ctypes
 import numpy as np
 import torch
 
-from ._lib import Dropout, GemmEpilogue, SpliceDesc, check, lib
+from ._lib import Dropout, GemmEpilogue, PcmClip, ResamplePlan, SpliceDesc, check, lib
 
 N_SAMPLES = 480000
 N_FRAMES = 3000
@@ -299,6 +299,52 @@ def logmel(wave, n_mels, *, n_valid=None, want_bf16_tm=False):
     with _op("logmel", 2, nbytes, "byte"):
         check(lib().desta_logmel(_p(wave), _p(n_valid), N, n_mels, _p(plan), _p(out), _p(out_tm), _p(cmax), _stream()), "desta_logmel")
     return out, out_tm
+
+
+_resample_plans = {}
+
+
+def resample_plan(sr_in, sr_out, device):
+    """(ResamplePlan, device coefficient table [L, P] f32) for one rate pair, built once per device."""
+    key = (int(sr_in), int(sr_out), str(device))
+    if key not in _resample_plans:
+        plan = ResamplePlan()
+        nbytes = lib().desta_resample_plan_bytes(int(sr_in), int(sr_out), ctypes.byref(plan))
+        if nbytes == 0:
+            raise ValueError(f"unsupported sample rates {sr_in} -> {sr_out}")
+        if nbytes > (256 << 20):
+            raise ValueError(f"sample rates {sr_in} -> {sr_out} reduce to {plan.L}/{plan.M}: coefficient table of {nbytes} bytes")
+        host = np.zeros(nbytes // 4, dtype=np.float32)
+        check(lib().desta_resample_plan_build(int(sr_in), int(sr_out), host.ctypes.data_as(ctypes.c_void_p), nbytes),
+              "desta_resample_plan_build")
+        _resample_plans[key] = (plan, torch.from_numpy(host).to(device))
+    return _resample_plans[key]
+
+
+def decode_resample(pcm, clips, fmt, channels, sr_in, sr_out, out):
+    """pcm: uint8 CUDA tensor holding the raw interleaved frames of every clip; clips: list of (byte offset into pcm,
+    n_frames, out_row).  Writes out[out_row, :] (f32, zero-padded / truncated to out.shape[1]); returns the valid lengths."""
+    _cuda(pcm, torch.uint8), _cuda(out, torch.float32)
+    assert out.dim() == 2 and out.stride(1) == 1
+    plan, taps = resample_plan(sr_in, sr_out, out.device)
+    n = len(clips)
+    host = (PcmClip * max(n, 1))()
+    lengths = []
+    for i, (off, n_frames, row) in enumerate(clips):
+        if not 0 <= row < out.shape[0]:
+            raise ValueError(f"clip {i}: output row {row} outside [0, {out.shape[0]})")
+        n_out = -(-int(n_frames) * plan.L // plan.M)
+        host[i] = PcmClip(pcm.data_ptr() + int(off), int(n_frames), n_out, int(row))
+        lengths.append(min(n_out, out.shape[1]))
+    if n == 0:
+        return lengths
+    dev = torch.frombuffer(bytearray(bytes(host)), dtype=torch.int64).to(out.device)
+    frames = sum(c[1] for c in clips)
+    nbytes = frames * channels * (1, 2, 3, 4, 4, 8)[fmt] + n * out.shape[1] * 4
+    with _op("decode_resample", 1, nbytes, "byte"):
+        check(lib().desta_decode_resample(_p(dev), n, int(fmt), int(channels), ctypes.byref(plan), _p(taps), _p(out), out.stride(0),
+                                          out.shape[1], _stream()), "desta_decode_resample")
+    return lengths
 
 
 def splice(input_ids, table, descs, trans_ids, feats, Q, out=None):

@@ -6,6 +6,7 @@
     model = DeSTA25AudioModel.from_pretrained(...).cuda()
     desta_b200.install(model)          # perception + splice now run on libdesta_b200.so
 """
+import sys
 import types
 
 from .perception import WhisperPerceptionB200
@@ -13,7 +14,10 @@ from .processor import WaveformProcessor
 from .splice import prepare_inputs_for_llm
 
 
-def install(model, wrap_processor: bool = True):
+def install(model, wrap_processor: bool = True, patch_audio: bool = False):
+    """patch_audio=True also rebinds the `AudioSegment` name that `generate()` uses (modeling_desta25.py:13, :1553-1557) to
+    desta_b200.audio.AudioSegment, so RIFF/WAVE files are decoded, down-mixed and resampled to 16 kHz on the GPU.  It is
+    opt-in because it is module-wide and because other containers (flac, mp3 ...) need the reference's libsndfile path."""
     if getattr(model.config, "connector_mode", "qformer_1") != "qformer_1":
         raise NotImplementedError("desta_b200 covers connector_mode='qformer_1' (ORCA modifies LLM decoding: out of scope)")
     ref_perception = model.perception
@@ -27,6 +31,12 @@ def install(model, wrap_processor: bool = True):
     if hasattr(model.perception.whisper, "generate"):
         # ASR pass of generate() (:1582-1601): encoder through the same kernels, shared with the perception call
         model.perception.wrap_whisper_generate()
+    if patch_audio:
+        from .audio import AudioSegment
+        mod = sys.modules.get(type(model).__module__)
+        if mod is None or not hasattr(mod, "AudioSegment"):
+            raise RuntimeError(f"{type(model).__module__} has no AudioSegment to replace")
+        mod.AudioSegment = AudioSegment
     if wrap_processor and getattr(model, "processor", None) is not None and not isinstance(model.processor, WaveformProcessor):
         model.processor = WaveformProcessor(model.processor)
     return model

@@ -41,6 +41,22 @@ def pad_or_truncate_batch(raw_speech, out=None, lengths=None):
     return out[:n], lengths[:n]
 
 
+def _device_batch(raw_speech):
+    """Clips decoded by desta_b200.audio.AudioSegment carry their device tensor: pad / truncate there (no second H2D copy)."""
+    if not isinstance(raw_speech, (list, tuple)) or not raw_speech:
+        return None
+    devs = [getattr(c, "device_tensor", None) for c in raw_speech]
+    if any(d is None for d in devs):
+        return None
+    wave = torch.zeros(len(devs), N_SAMPLES, dtype=torch.float32, device=devs[0].device)
+    lengths = torch.zeros(len(devs), dtype=torch.int32)
+    for i, d in enumerate(devs):
+        m = min(d.shape[0], N_SAMPLES)
+        wave[i, :m] = d[:m]
+        lengths[i] = m
+    return wave, lengths
+
+
 class _Features(dict):
     def __getattr__(self, k):
         try:
@@ -66,6 +82,9 @@ class WaveformProcessor:
                 f"The model corresponding to this feature extractor: WhisperFeatureExtractor was trained using a"
                 f" sampling rate of {self.sampling_rate}. Please make sure that the provided `raw_speech` input"
                 f" was sampled with {self.sampling_rate} and not {sampling_rate}.")
+        on_device = _device_batch(raw_speech) if return_tensors == "pt" else None
+        if on_device is not None:
+            return _Features(input_features=on_device[0], num_samples=on_device[1])
         wave, lengths = pad_or_truncate_batch(raw_speech)
         feats = torch.from_numpy(wave) if return_tensors == "pt" else wave
         return _Features(input_features=feats, num_samples=torch.from_numpy(lengths) if return_tensors == "pt" else lengths)

@@ -138,6 +138,40 @@ int desta_splice(const int64_t* input_ids, const void* table, int64_t vocab, con
 int desta_splice_bwd(const void* grad_out, const desta_splice_desc* descs_dev, int n_desc, int Q, int S, int d, float* dfeats,
                      void* stream);
 
+/* ---- (0) PCM decode + resample to 16 kHz (scope row n3): replaces the sample conversion, channel average and
+ *      librosa.core.resample call of AudioSegment.__init__ / .from_file (desta/utils/audio.py:147-166, 221-243, 305-315;
+ *      called with target_sr=16000, channel_selector="average" at modeling_desta25.py:1553-1557 and
+ *      trainer/data/simple_dataset.py:145-149), fused with the right-pad / truncate to 30 s of the feature extractor.
+ *      The host only parses the container header and hands over the raw interleaved PCM bytes.
+ *      out[c, n] = sum_k x_c[k] g(n M/L - k) for n < n_out_c, 0 for n_out_c <= n < out_len, where x_c = channel mean of the
+ *      float32-converted frames (soundfile scaling: s16 / 2^15, s24 / 2^23, s32 / 2^31, u8 (v-128)/2^7, floats as they are)
+ *      and g is a Kaiser-windowed sinc with the band edges of the resampler the reference uses (librosa's default
+ *      res_type "soxr_hq": pass band to 0.913 of the lower Nyquist, stop band from 1.0, ~120 dB).  sr_in == sr_out gives
+ *      L = M = P = 1 and the call reduces to conversion + down-mix + padding, bit-exact with the reference. ---- */
+#define DESTA_PCM_U8 0
+#define DESTA_PCM_S16 1
+#define DESTA_PCM_S24 2
+#define DESTA_PCM_S32 3
+#define DESTA_PCM_F32 4
+#define DESTA_PCM_F64 5
+typedef struct desta_resample_plan {
+  int32_t L, M;          /* sr_out / sr_in reduced: output n sits at input time n M / L */
+  int32_t P;             /* taps per output sample (even, or 1 for the identity plan) */
+  int32_t reserved;
+} desta_resample_plan;
+typedef struct desta_pcm_clip {
+  const void* pcm;       /* device pointer to interleaved frames, little-endian, `channels` samples per frame */
+  int64_t n_frames;
+  int64_t n_out;         /* ceil(n_frames L / M) as librosa fixes the length (audio.py:164); the kernel clamps it to out_len */
+  int64_t out_row;       /* row of `out` this clip is written to (clips of one batch may be grouped by format) */
+} desta_pcm_clip;
+/* Fills *plan; returns the byte size of the coefficient table (L rows of P floats, row r = output residue n mod L). */
+size_t desta_resample_plan_bytes(int sr_in, int sr_out, desta_resample_plan* plan);
+int desta_resample_plan_build(int sr_in, int sr_out, float* host_taps, size_t bytes);
+/* clips_dev[n_clips] (device array) share one format / channel count / rate; out [rows, out_stride] f32, row = out_row. */
+int desta_decode_resample(const desta_pcm_clip* clips_dev, int n_clips, int fmt, int channels, const desta_resample_plan* plan,
+                          const float* taps_dev, float* out, int64_t out_stride, int64_t out_len, void* stream);
+
 /* ---- (2)/(3) stage-level entry points: the whole encoder / connector forward as ONE call (native schedule over the
  *      building blocks above; nothing is allocated - the caller passes a workspace of desta_*_workspace_bytes()).
  *      desta_encoder_fwd replaces WhisperPerception.forward_whisper's conv stem + layer loop with taps

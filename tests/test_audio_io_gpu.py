@@ -1,0 +1,156 @@
+"""GPU parity of the decode + resample kernel (scope row n3) against oracle/audio_io.py, through the C ABI.
+Tolerances: conversion / down-mix / identity rate bit-exact; resampled samples |delta| <= 2e-5 against the float64 oracle
+(fp32 accumulation of 180-540 taps on samples in [-1, 1])."""
+import numpy as np
+import pytest
+import torch
+
+import __graft_entry__
+import wavutil as W
+from oracle import audio_io as A
+
+pytestmark = pytest.mark.gpu
+
+TOL = 2e-5
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    __graft_entry__.build()
+
+
+def _signal(n, ch, seed):
+    rng = np.random.default_rng(seed)
+    t = np.arange(n)
+    x = 0.3 * np.sin(2 * np.pi * 0.013 * t)[:, None] + 0.2 * rng.standard_normal((n, ch)) + 0.1 * np.sin(2 * np.pi * 0.31 * t)[:, None]
+    return np.clip(x, -1, 0.999)
+
+
+def _run(raw, kind, ch, sr, n_frames, out_len, target=16000):
+    from desta_b200 import ops
+    pcm = torch.from_numpy(np.frombuffer(raw, np.uint8).copy()).cuda() if len(raw) else torch.zeros(16, dtype=torch.uint8, device="cuda")
+    out = torch.full((1, out_len), 7.0, dtype=torch.float32, device="cuda")       # sentinel: every sample must be written
+    lengths = ops.decode_resample(pcm, [(0, n_frames, 0)], kind, ch, sr, target, out)
+    return out[0].cpu().numpy(), lengths[0]
+
+
+@pytest.mark.parametrize("sr", [8000, 11025, 22050, 24000, 32000, 44100, 48000, 96000])
+def test_resample_matches_oracle(sr):
+    n = 30011
+    x = _signal(n, 1, sr)
+    raw = W.encode(x, W.F32)
+    ref = A.resample(A.decode_frames(raw, A.FMT_F32, 1)[:, 0], sr, 16000)
+    got, m = _run(raw, W.F32, 1, sr, n, len(ref) + 100)
+    assert m == len(ref)
+    assert np.abs(got[:m] - ref).max() <= TOL
+    assert not got[m:].any()                                     # zero padding up to the row length
+
+
+@pytest.mark.parametrize("kind", [W.U8, W.S16, W.S24, W.S32, W.F32, W.F64])
+@pytest.mark.parametrize("ch", [1, 2, 5])
+def test_decode_and_downmix_bit_exact_at_the_model_rate(kind, ch):
+    n = 5003
+    raw = W.encode(_signal(n, ch, kind + ch), kind)
+    ref = A.downmix_average(A.decode_frames(raw, kind, ch)).astype(np.float32)
+    got, m = _run(raw, kind, ch, 16000, n, 6000)
+    assert m == n and np.array_equal(got[:n], ref) and not got[n:].any()
+
+
+@pytest.mark.parametrize("kind,ch,sr", [(W.S16, 2, 44100), (W.S24, 1, 22050), (W.U8, 2, 8000), (W.F64, 3, 32000), (W.S32, 2, 24000)])
+def test_decode_downmix_resample_fused(kind, ch, sr):
+    n = 20000
+    raw = W.encode(_signal(n, ch, sr + kind), kind)
+    ref = A.resample(A.downmix_average(A.decode_frames(raw, kind, ch)), sr, 16000)
+    got, m = _run(raw, kind, ch, sr, n, len(ref))
+    assert m == len(ref) and np.abs(got - ref).max() <= TOL
+
+
+def test_truncation_short_and_empty_clips():
+    sr = 22050
+    x = _signal(40000, 1, 5)
+    raw = W.encode(x, W.S16)
+    ref = A.resample(A.decode_frames(raw, A.FMT_S16, 1)[:, 0], sr, 16000)
+    got, m = _run(raw, W.S16, 1, sr, 40000, 10000)               # longer than the row: first out_len samples, as the
+    assert m == 10000 and np.abs(got - ref[:10000]).max() <= TOL  # feature extractor truncates (feature_extraction_whisper.py:296-320)
+    for n in (1, 2, 3, 100):                                     # clips shorter than the filter
+        ref = A.resample(A.decode_frames(raw[:2 * n], A.FMT_S16, 1)[:, 0], sr, 16000)
+        got, m = _run(raw[:2 * n], W.S16, 1, sr, n, 300)
+        assert m == len(ref) and np.abs(got[:m] - ref).max() <= TOL and not got[m:].any()
+    got, m = _run(b"", W.S16, 1, sr, 0, 300)
+    assert m == 0 and not got.any()
+
+
+def test_full_length_clip_linearity_and_passband_tone():
+    """30 s at 44.1 kHz (the size the path runs at): properties instead of an element-wise oracle pass."""
+    sr, n = 44100, 44100 * 30
+    t = np.arange(n) / sr
+    a = (0.4 * np.sin(2 * np.pi * 3000.0 * t)).astype(np.float32)
+    b = (0.3 * np.random.default_rng(2).standard_normal(n)).astype(np.float32)
+    ya, m = _run(a.tobytes(), W.F32, 1, sr, n, 480000)
+    yb, _ = _run(b.tobytes(), W.F32, 1, sr, n, 480000)
+    yab, _ = _run((a + b).astype(np.float32).tobytes(), W.F32, 1, sr, n, 480000)
+    assert m == 480000
+    assert np.abs(yab - (ya + yb)).max() <= 1e-5                 # linear
+    to = np.arange(480000) / 16000
+    assert np.abs(ya - 0.4 * np.sin(2 * np.pi * 3000.0 * to))[400:-400].max() <= 2e-5      # pass-band tone re-sampled exactly
+    # spot window against the oracle: a segment starting at input sample lo = 441 * c maps to output 160 * c exactly
+    c = 1500
+    lo = 441 * c
+    ref = A.resample(b[lo:lo + 8000], sr, 16000)
+    keep = slice(600, len(ref) - 600)                            # outputs whose taps lie wholly inside the segment
+    assert np.abs(yb[160 * c:160 * c + len(ref)][keep] - ref[keep]).max() <= TOL
+
+
+def test_load_waveforms_mixed_batch_and_audio_segment(tmp_path):
+    from desta_b200 import audio
+    from desta_b200.processor import WaveformProcessor
+    specs = [(W.S16, 1, 16000, 9000), (W.S16, 2, 44100, 30000), (W.F32, 1, 22050, 12345), (W.S16, 1, 16000, 4000),
+             (W.S24, 2, 48000, 20000), (W.S16, 2, 44100, 777)]
+    paths, refs = [], []
+    for i, (kind, ch, sr, n) in enumerate(specs):
+        data = W.wav_bytes(_signal(n, ch, 100 + i), sr, kind, extensible=(i == 4), extra_chunks=(i % 2 == 1))
+        p = tmp_path / f"c{i}.wav"
+        p.write_bytes(data)
+        paths.append(str(p))
+        refs.append(A.load(data)[0])
+    wave, lengths = audio.load_waveforms(paths, n_samples=20000)
+    wave = wave.cpu().numpy()
+    for i, ref in enumerate(refs):
+        m = min(len(ref), 20000)
+        assert int(lengths[i]) == m
+        tol = 0.0 if specs[i][2] == 16000 else TOL
+        assert np.abs(wave[i, :m] - ref[:m]).max() <= tol and not wave[i, m:].any()
+    # AudioSegment mirror: same call as modeling_desta25.py:1553-1557
+    seg = audio.AudioSegment.from_file(paths[1], target_sr=16000, channel_selector="average")
+    assert seg.sample_rate == 16000 and seg.num_samples == len(refs[1]) and seg.samples.dtype == np.float32
+    assert np.abs(seg.samples - refs[1]).max() <= TOL
+    # offset / duration select frames before resampling (audio.py:310-315)
+    data = open(paths[2], "rb").read()
+    kind, ch, sr, off, n = A.parse_wav(data)
+    first, count = int(0.1 * sr), int(0.25 * sr)
+    ref = A.resample(A.decode_frames(data[off + first * 4:off + (first + count) * 4], kind, ch)[:, 0], sr, 16000)
+    seg2 = audio.AudioSegment.from_file(paths[2], target_sr=16000, offset=0.1, duration=0.25, channel_selector="average")
+    assert seg2.num_samples == len(ref) and np.abs(seg2.samples - ref).max() <= TOL
+    # target_sr=None keeps the file's rate (conversion + down-mix only)
+    seg3 = audio.AudioSegment.from_file(paths[4], channel_selector="average")
+    kind, ch, sr, off, n = A.parse_wav(open(paths[4], "rb").read())
+    assert seg3.sample_rate == 48000 and seg3.num_samples == n
+    with pytest.raises(NotImplementedError):
+        audio.AudioSegment.from_file(paths[1], target_sr=16000)            # stereo kept as stereo: not on the model path
+    # the processor shim assembles device-resident clips without a host round trip
+    feats = WaveformProcessor()([seg.samples, seg2.samples], sampling_rate=16000, return_tensors="pt")
+    assert feats.input_features.is_cuda and feats.input_features.shape == (2, 480000)
+    assert torch.equal(feats.input_features[0, :seg.num_samples], seg.device_samples) and not feats.input_features[0, seg.num_samples:].any()
+    assert feats.num_samples.tolist() == [seg.num_samples, seg2.num_samples]
+
+
+def test_bad_arguments_fail_loudly():
+    from desta_b200 import ops
+    pcm = torch.zeros(64, dtype=torch.uint8, device="cuda")
+    out = torch.zeros(1, 100, device="cuda")
+    with pytest.raises(ValueError):
+        ops.decode_resample(pcm, [(0, 10, 3)], W.S16, 1, 22050, 16000, out)          # row outside the buffer
+    with pytest.raises(Exception):
+        ops.decode_resample(pcm, [(0, 10, 0)], 9, 1, 22050, 16000, out)              # unknown sample format
+    with pytest.raises(Exception):
+        ops.decode_resample(pcm, [(0, 10, 0)], W.S16, 0, 22050, 16000, out)          # zero channels

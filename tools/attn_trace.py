@@ -8,7 +8,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "desta2.5-audio_b200", "csrc")
 OUT = os.path.join(ROOT, "tools", "_bin", "libdesta_trace.so")
-SOURCES = ["api.cu", "schedule.cu", "gemm.cu", "gemm2.cu", "attention.cu", "attention_bwd.cu", "elementwise.cu", "elementwise_bwd.cu", "logmel.cu", "splice.cu"]
+SOURCES = ["api.cu", "schedule.cu", "gemm.cu", "gemm2.cu", "attention.cu", "attention_bwd.cu", "elementwise.cu", "elementwise_bwd.cu", "logmel.cu", "splice.cu", "resample.cu"]
 
 
 def build():

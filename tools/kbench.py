@@ -87,7 +87,22 @@ def bench_splice():
         print(f"splice B={B} S={S} d={d}: {ms:.4f} ms  {nbytes / ms / 1e6:.0f} GB/s", flush=True)
 
 
+def bench_resample():
+    import numpy as np
+    N = 64
+    for sr, ch in ((22050, 1), (32000, 1), (44100, 2), (48000, 2), (16000, 2)):
+        n = sr * 30
+        pcm = torch.randint(-20000, 20000, (N, n * ch), dtype=torch.int16, device="cuda").view(torch.uint8).reshape(-1)
+        clips = [(i * n * ch * 2, n, i) for i in range(N)]
+        out = torch.empty(N, 480000, device="cuda")
+        ms = timeit(lambda: ops.decode_resample(pcm, clips, 1, ch, sr, 16000, out))
+        plan, _ = ops.resample_plan(sr, 16000, out.device)
+        nbytes = N * (n * ch * 2 + 480000 * 4)
+        print(f"decode_resample {sr} Hz x{ch}ch s16 -> 16 kHz, N={N}: {ms:.3f} ms  {nbytes / ms / 1e6:.0f} GB/s algorithmic, "
+              f"{2.0 * N * 480000 * plan.P / ms / 1e9:.2f} TFLOP/s fp32 (P={plan.P})", flush=True)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["gemm", "attn", "mel", "splice"]
     for w in which:
-        {"gemm": bench_gemm, "attn": bench_attn, "attn_bwd": bench_attn_bwd, "mel": bench_mel, "splice": bench_splice}[w]()
+        {"gemm": bench_gemm, "attn": bench_attn, "attn_bwd": bench_attn_bwd, "mel": bench_mel, "splice": bench_splice, "resample": bench_resample}[w]()
