@@ -321,12 +321,15 @@ def resample_plan(sr_in, sr_out, device):
     return _resample_plans[key]
 
 
-def decode_resample(pcm, clips, fmt, channels, sr_in, sr_out, out):
+def decode_resample(pcm, clips, fmt, channels, sr_in, sr_out, out, general_kernel=False):
     """pcm: uint8 CUDA tensor holding the raw interleaved frames of every clip; clips: list of (byte offset into pcm,
-    n_frames, out_row).  Writes out[out_row, :] (f32, zero-padded / truncated to out.shape[1]); returns the valid lengths."""
+    n_frames, out_row).  Writes out[out_row, :] (f32, zero-padded / truncated to out.shape[1]); returns the valid lengths.
+    general_kernel=True forces the any-ratio kernel where the tiled one would run (test hook)."""
     _cuda(pcm, torch.uint8), _cuda(out, torch.float32)
     assert out.dim() == 2 and out.stride(1) == 1
     plan, taps = resample_plan(sr_in, sr_out, out.device)
+    if general_kernel:
+        plan = ResamplePlan(plan.L, plan.M, plan.P, 1)
     n = len(clips)
     host = (PcmClip * max(n, 1))()
     lengths = []

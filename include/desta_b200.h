@@ -157,7 +157,7 @@ int desta_splice_bwd(const void* grad_out, const desta_splice_desc* descs_dev, i
 typedef struct desta_resample_plan {
   int32_t L, M;          /* sr_out / sr_in reduced: output n sits at input time n M / L */
   int32_t P;             /* taps per output sample (even, or 1 for the identity plan) */
-  int32_t reserved;
+  int32_t reserved;      /* flags; bit 0: force the general (any-ratio) kernel - the tests use it to cover both */
 } desta_resample_plan;
 typedef struct desta_pcm_clip {
   const void* pcm;       /* device pointer to interleaved frames, little-endian, `channels` samples per frame */

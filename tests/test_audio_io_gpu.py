@@ -26,42 +26,47 @@ def _signal(n, ch, seed):
     return np.clip(x, -1, 0.999)
 
 
-def _run(raw, kind, ch, sr, n_frames, out_len, target=16000):
+def _run(raw, kind, ch, sr, n_frames, out_len, target=16000, general=False):
     from desta_b200 import ops
     pcm = torch.from_numpy(np.frombuffer(raw, np.uint8).copy()).cuda() if len(raw) else torch.zeros(16, dtype=torch.uint8, device="cuda")
     out = torch.full((1, out_len), 7.0, dtype=torch.float32, device="cuda")       # sentinel: every sample must be written
-    lengths = ops.decode_resample(pcm, [(0, n_frames, 0)], kind, ch, sr, target, out)
+    lengths = ops.decode_resample(pcm, [(0, n_frames, 0)], kind, ch, sr, target, out, general_kernel=general)
     return out[0].cpu().numpy(), lengths[0]
 
 
-@pytest.mark.parametrize("sr", [8000, 11025, 22050, 24000, 32000, 44100, 48000, 96000])
-def test_resample_matches_oracle(sr):
+@pytest.mark.parametrize("general", [False, True], ids=["tiled", "general"])
+@pytest.mark.parametrize("sr", [8000, 11025, 12000, 22050, 24000, 32000, 44100, 48000, 88200, 96000, 16001, 37800])
+def test_resample_matches_oracle(sr, general):
     n = 30011
     x = _signal(n, 1, sr)
     raw = W.encode(x, W.F32)
     ref = A.resample(A.decode_frames(raw, A.FMT_F32, 1)[:, 0], sr, 16000)
-    got, m = _run(raw, W.F32, 1, sr, n, len(ref) + 100)
+    got, m = _run(raw, W.F32, 1, sr, n, len(ref) + 100, general=general)
     assert m == len(ref)
     assert np.abs(got[:m] - ref).max() <= TOL
     assert not got[m:].any()                                     # zero padding up to the row length
 
 
+@pytest.mark.parametrize("general", [False, True], ids=["copy", "general"])
 @pytest.mark.parametrize("kind", [W.U8, W.S16, W.S24, W.S32, W.F32, W.F64])
-@pytest.mark.parametrize("ch", [1, 2, 5])
-def test_decode_and_downmix_bit_exact_at_the_model_rate(kind, ch):
+@pytest.mark.parametrize("ch", [1, 2, 4, 5])
+def test_decode_and_downmix_bit_exact_at_the_model_rate(kind, ch, general):
     n = 5003
     raw = W.encode(_signal(n, ch, kind + ch), kind)
     ref = A.downmix_average(A.decode_frames(raw, kind, ch)).astype(np.float32)
-    got, m = _run(raw, kind, ch, 16000, n, 6000)
-    assert m == n and np.array_equal(got[:n], ref) and not got[n:].any()
+    for out_len in (6000, 6001, 4001):                           # padded, odd row length (scalar stores), truncated
+        got, m = _run(raw, kind, ch, 16000, n, out_len, general=general)
+        k = min(n, out_len)
+        assert m == k and np.array_equal(got[:k], ref[:k]) and not got[k:].any()
 
 
+@pytest.mark.parametrize("general", [False, True], ids=["tiled", "general"])
 @pytest.mark.parametrize("kind,ch,sr", [(W.S16, 2, 44100), (W.S24, 1, 22050), (W.U8, 2, 8000), (W.F64, 3, 32000), (W.S32, 2, 24000)])
-def test_decode_downmix_resample_fused(kind, ch, sr):
+def test_decode_downmix_resample_fused(kind, ch, sr, general):
     n = 20000
     raw = W.encode(_signal(n, ch, sr + kind), kind)
     ref = A.resample(A.downmix_average(A.decode_frames(raw, kind, ch)), sr, 16000)
-    got, m = _run(raw, kind, ch, sr, n, len(ref))
+    got, m = _run(raw, kind, ch, sr, n, len(ref), general=general)
     assert m == len(ref) and np.abs(got - ref).max() <= TOL
 
 
@@ -74,8 +79,17 @@ def test_truncation_short_and_empty_clips():
     assert m == 10000 and np.abs(got - ref[:10000]).max() <= TOL  # feature extractor truncates (feature_extraction_whisper.py:296-320)
     for n in (1, 2, 3, 100):                                     # clips shorter than the filter
         ref = A.resample(A.decode_frames(raw[:2 * n], A.FMT_S16, 1)[:, 0], sr, 16000)
-        got, m = _run(raw[:2 * n], W.S16, 1, sr, n, 300)
-        assert m == len(ref) and np.abs(got[:m] - ref).max() <= TOL and not got[m:].any()
+        for general in (False, True):
+            got, m = _run(raw[:2 * n], W.S16, 1, sr, n, 300, general=general)
+            assert m == len(ref) and np.abs(got[:m] - ref).max() <= TOL and not got[m:].any()
+    # odd row length / unaligned row start: the scalar store path of the tiled kernel
+    from desta_b200 import ops
+    pcm = torch.from_numpy(np.frombuffer(raw, np.uint8).copy()).cuda()
+    buf = torch.full((3, 1003), 7.0, device="cuda")
+    ref = A.resample(A.decode_frames(raw[:4000], A.FMT_S16, 1)[:, 0], 32000, 16000)
+    ops.decode_resample(pcm, [(0, 2000, 1)], W.S16, 1, 32000, 16000, buf)
+    got = buf.cpu().numpy()
+    assert np.abs(got[1, :1000] - ref).max() <= TOL and not got[1, 1000:].any() and (got[0] == 7).all() and (got[2] == 7).all()
     got, m = _run(b"", W.S16, 1, sr, 0, 300)
     assert m == 0 and not got.any()
 
