@@ -140,6 +140,32 @@ def cpu_reference_rate(workload, n_clips, steps=1, warmup=0, threads=None):
     return 30.0 * n_clips / dt, dt, threads
 
 
+def decode_resample_rates(n, dev):
+    """Scope row n3, outside the timed regions: raw PCM of n 30 s clips (resident in HBM) -> padded 16 kHz waveform buffer
+    of the log-mel kernel.  Reported beside the headline so a non-16 kHz corpus can be costed against ms_per_step."""
+    from desta_b200 import ops
+    res = {"unit": "ms per %d clips of 30 s (s16 PCM -> [N,480000] f32)" % n}
+    try:
+        for name, sr, ch in (("16k_mono", 16000, 1), ("22k05_mono", 22050, 1), ("44k1_stereo", 44100, 2)):
+            frames = sr * 30
+            pcm = torch.randint(-20000, 20000, (n * frames * ch,), dtype=torch.int16, device=dev).view(torch.uint8)
+            clips = [(i * frames * ch * 2, frames, i) for i in range(n)]
+            out = torch.empty(n, 480000, device=dev)
+            for _ in range(2):
+                ops.decode_resample(pcm, clips, 1, ch, sr, 16000, out)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                ops.decode_resample(pcm, clips, 1, ch, sr, 16000, out)
+            e1.record()
+            torch.cuda.synchronize()
+            res[name] = round(e0.elapsed_time(e1) / 5, 3)
+            del pcm, out
+    except Exception as e:      # reported, never hidden: the headline above does not depend on this row
+        res["error"] = repr(e)
+    return res
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -361,6 +387,8 @@ def run_ours(args):
         "step_tensor_frac": round(flops_clip * n / step_s / 1e12 / tf_sust, 4),
         "kernels": fam,
     }
+    if rank == 0 and world == 1:
+        line["upstream_n3"] = decode_resample_rates(n, dev)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         rate, dt, threads = cpu_reference_rate(args.workload, args.cpu_clips)
         line["cpu_baseline"] = {"value": rate, "unit": "audio-s/s", "cores": threads, "kind": "port",

@@ -158,6 +158,27 @@ def test_load_waveforms_mixed_batch_and_audio_segment(tmp_path):
     assert feats.num_samples.tolist() == [seg.num_samples, seg2.num_samples]
 
 
+@pytest.mark.parametrize("ch", [1, 2])
+def test_unaligned_clip_start_takes_the_scalar_path(ch):
+    """Clips inside a caller's buffer may start at any sample-aligned byte: the vector loads of the copy kernel need 16."""
+    from desta_b200 import ops
+    n = 4001
+    raw = W.encode(_signal(n, ch, 77 + ch), W.S16)
+    ref = A.downmix_average(A.decode_frames(raw, A.FMT_S16, ch)).astype(np.float32)
+    for off in (0, 2 * ch, 6 * ch, 16):
+        buf = np.zeros(off + len(raw) + 16, np.uint8)
+        buf[off:off + len(raw)] = np.frombuffer(raw, np.uint8)
+        pcm = torch.from_numpy(buf).cuda()
+        out = torch.full((1, 4100), 7.0, device="cuda")
+        ops.decode_resample(pcm, [(off, n, 0)], W.S16, ch, 16000, 16000, out)
+        got = out[0].cpu().numpy()
+        assert np.array_equal(got[:n], ref) and not got[n:].any(), off
+        ref22 = A.resample(ref, 22050, 16000)
+        out = torch.full((1, len(ref22)), 7.0, device="cuda")
+        ops.decode_resample(pcm, [(off, n, 0)], W.S16, ch, 22050, 16000, out)
+        assert np.abs(out[0].cpu().numpy() - ref22).max() <= TOL, off
+
+
 def test_bad_arguments_fail_loudly():
     from desta_b200 import ops
     pcm = torch.zeros(64, dtype=torch.uint8, device="cuda")
