@@ -38,6 +38,7 @@ class WhisperPerceptionB200(nn.Module):
         self._ws = {}
         self._train = {}
         self._enc_cache = None      # (input clone, N): encoder state of the last whisper.generate() call, see share_encoder
+        self._graph = None          # (CUDAGraph, static input, static output, N, parameter versions), see capture_graph
 
     # ---- reference-compatible constructor: wrap an existing reference WhisperPerception ----
     @classmethod
@@ -131,12 +132,61 @@ class WhisperPerceptionB200(nn.Module):
 
     @torch.no_grad()
     def forward_features(self, input_features: torch.Tensor) -> torch.Tensor:
+        g = self._graph_for(input_features)
+        if g is not None and self._enc_cache is None:
+            graph, wave, out, _, _ = g
+            wave.copy_(input_features, non_blocking=True)
+            graph.replay()
+            ops.STATS["graph_kernels"] = ops.STATS.get("graph_kernels", 0) + self._graph_kernels
+            return out.clone()
         _, con = self._packs()
         N = input_features.size(0)
         ws = self._run_encoder(input_features)
         out = torch.empty(N * self.dims.prompt_size, self.dims.d_llm, dtype=torch.float32, device=ws.h.device)
         engine.connector_forward(con, self.dims, ws, out)
         return out.view(N, self.dims.prompt_size, self.dims.d_llm)
+
+    # ---- CUDA-graph replay of the whole waveform -> audio-feature path (inference, fixed batch size) ----
+    @torch.no_grad()
+    def capture_graph(self, n_clips: int):
+        """Capture log-mel + encoder + connector for `n_clips` padded waveforms into one CUDA graph.  The ~300 kernel launches
+        of a step are then issued by a single cudaGraphLaunch: at small batches (8 clips: ~70 us of kernel time per launch)
+        the launch path is no longer on the critical path.  Everything the step touches is static - weights packed once,
+        caller-owned workspace, TMA descriptors passed by value as kernel parameters - so the capture needs no special
+        handling beyond one eager warm-up (kernel attributes, plans and workspaces are created there).
+        Returns the static output tensor; `forward_features` replays the graph whenever it sees a waveform batch of this
+        size on this device (eval mode only: train-mode dropout draws a fresh seed per step on the host)."""
+        dev = self._device()
+        wave = torch.zeros(n_clips, ops.N_SAMPLES, dtype=torch.float32, device=dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        self._graph = None
+        with torch.cuda.stream(side):
+            self.forward_features(wave)                           # warm-up: allocations, attributes, plans
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        l0 = ops.STATS["launches"]
+        with torch.cuda.graph(graph):
+            out = self.forward_features(wave)
+        self._graph_kernels = ops.STATS["launches"] - l0          # kernels recorded into the graph (not launched yet)
+        ops.STATS["launches"] = l0
+        # the graph holds raw pointers into the workspace and the packed weights: keep them alive with it (the module itself
+        # only keeps ONE batch size resident and re-packs the connector after every optimizer step)
+        self._graph_keepalive = (self._workspace(n_clips), self._enc_pack, self._con_pack)
+        self._graph = (graph, wave, out, n_clips, tuple(p._version for p in self.connector.parameters()))
+        return out
+
+    def _graph_for(self, input_features):
+        g = getattr(self, "_graph", None)
+        if g is None or torch.cuda.is_current_stream_capturing() or ops._PROFILE is not None:
+            return None                                           # per-kernel profiling needs the eager launches
+        graph, wave, out, n, versions = g
+        if (input_features.dim() != 2 or input_features.shape != wave.shape or input_features.device != wave.device
+                or input_features.dtype != torch.float32 or self.connector.training
+                or versions != tuple(p._version for p in self.connector.parameters())):
+            return None                                           # other shapes / updated weights run eagerly
+        return g
 
     def taps(self, input_features: torch.Tensor):
         """The four tapped hidden states (bf16 [N, 1500, d]) — exposed for parity tests."""

@@ -112,3 +112,39 @@ def test_native_schedule_equals_per_op_schedule(name):
                                  ctypes.c_void_p(small.data_ptr()), 16, ctypes.c_void_p(ws.taps.data_ptr()),
                                  ctypes.c_void_p(ws.h.data_ptr()), None)
     assert rc == -1 and b"workspace too small" in lib().desta_last_error()
+
+
+@pytest.mark.parametrize("name", ["micro", "debug"])
+def test_cuda_graph_replay_equals_eager(name):
+    """capture_graph(): the whole waveform -> audio-feature path replayed as one CUDA graph gives bit-identical features,
+    keeps doing so for new inputs, and steps aside for other batch sizes, train mode and updated connector weights."""
+    cfg = CONFIGS[name]
+    W = make_weights(cfg, seed=11, with_table=False)
+    waves = synth_waves(seed=7, kinds=KINDS)
+    p = build_perception(cfg, W)
+    wave_a = torch.from_numpy(np.stack([o_mel.pad_or_truncate(w) for w in waves[:3]])).cuda()
+    wave_b = torch.from_numpy(np.stack([o_mel.pad_or_truncate(w) for w in waves[3:6]])).cuda()
+    with torch.no_grad():
+        eager_a = p.forward_features(wave_a).clone()
+        eager_b = p.forward_features(wave_b).clone()
+        eager_2 = p.forward_features(wave_a[:2]).clone()
+    p.capture_graph(3)
+    from desta_b200 import ops
+    l0 = ops.STATS["launches"]
+    with torch.no_grad():
+        got_a = p.forward_features(wave_a)
+        got_b = p.forward_features(wave_b)
+        got_a2, _ = p(input_features=wave_a)
+    assert ops.STATS["launches"] == l0, "replays must not launch kernels one by one"
+    assert torch.equal(got_a, eager_a), "graph replay differs from eager (first input)"
+    assert torch.equal(got_b, eager_b), "graph replay differs from eager (second input)"
+    assert torch.equal(got_a2, eager_a), "module call did not replay"
+    with torch.no_grad():
+        assert torch.equal(p.forward_features(wave_a[:2]), eager_2), "other batch size must take the eager path"
+    assert ops.STATS["launches"] > l0
+    with torch.no_grad():                                                  # weights change -> the stale graph is not used
+        p.connector.layer_weights[0] += 1.5                                # (a uniform shift would cancel in the softmax)
+        l1 = ops.STATS["launches"]
+        changed = p.forward_features(wave_a)
+    assert ops.STATS["launches"] > l1, "stale graph replayed after a weight update"
+    assert not torch.equal(changed, eager_a)
