@@ -142,6 +142,11 @@ def test_cuda_graph_replay_equals_eager(name):
     with torch.no_grad():
         assert torch.equal(p.forward_features(wave_a[:2]), eager_2), "other batch size must take the eager path"
     assert ops.STATS["launches"] > l0
+    # the eager call replaced the module's resident workspace; the graph must still own the one it was captured with
+    junk = [torch.full((1 << 20,), float(i), device="cuda") for i in range(64)]
+    with torch.no_grad():
+        assert torch.equal(p.forward_features(wave_b), eager_b), "graph buffers were recycled under the graph"
+    del junk
     with torch.no_grad():                                                  # weights change -> the stale graph is not used
         p.connector.layer_weights[0] += 1.5                                # (a uniform shift would cancel in the softmax)
         l1 = ops.STATS["launches"]
