@@ -179,6 +179,37 @@ def test_unaligned_clip_start_takes_the_scalar_path(ch):
         assert np.abs(out[0].cpu().numpy() - ref22).max() <= TOL, off
 
 
+def test_pcm_stager_double_buffer(tmp_path):
+    """File batches through the pinned PCM double buffer: every batch equals the oracle, slots are reused safely."""
+    from desta_b200.staging import PcmStager, stage_files
+    specs = [(W.S16, 1, 16000, 7000), (W.S16, 2, 44100, 9000), (W.F32, 1, 22050, 5000), (W.S24, 2, 48000, 8000),
+             (W.S16, 1, 32000, 6000), (W.U8, 1, 8000, 3000), (W.S16, 1, 16000, 100)]
+    paths, refs = [], []
+    for i, (kind, ch, sr, n) in enumerate(specs):
+        data = W.wav_bytes(_signal(n, ch, 300 + i), sr, kind, extra_chunks=(i % 2 == 0))
+        p = tmp_path / f"s{i}.wav"
+        p.write_bytes(data)
+        paths.append(str(p))
+        refs.append(A.load(data)[0])
+    batches = [paths[0:3], paths[3:5], paths[5:7], paths[1:4]]
+    order = [[0, 1, 2], [3, 4], [5, 6], [1, 2, 3]]
+    stager = PcmStager(3, "cuda", slot_bytes=1 << 20)
+    seen = 0
+    for (wave, lens), idx in zip(stage_files(stager, batches), order):
+        got = wave.cpu().numpy()
+        assert wave.shape == (len(idx), 480000)
+        for r, i in enumerate(idx):
+            m = len(refs[i])
+            tol = 0.0 if specs[i][2] == 16000 else TOL
+            assert int(lens[r]) == m and np.abs(got[r, :m] - refs[i]).max() <= tol and not got[r, m:].any()
+        seen += 1
+    assert seen == 4 and stager.h2d_bytes > 0
+    with pytest.raises(ValueError):
+        PcmStager(1, "cuda", slot_bytes=1 << 20).fill(0, paths[:2])                  # more clips than the slot holds
+    with pytest.raises(ValueError):
+        PcmStager(3, "cuda", slot_bytes=1024).fill(0, paths[:1])                     # payload larger than the slot
+
+
 def test_bad_arguments_fail_loudly():
     from desta_b200 import ops
     pcm = torch.zeros(64, dtype=torch.uint8, device="cuda")

@@ -50,3 +50,27 @@ def test_stager_host_side_without_cuda():
     assert st.host_len[1][:3].tolist() == [min(len(w), 480000) for w in waves[3:6]]
     with pytest.raises(ValueError):
         st.fill(0, waves[:5])
+
+
+def test_pcm_stager_host_side_without_cuda(tmp_path):
+    """PcmStager.fill only touches the host: header walk + payload straight into the slot, 16-byte aligned clip starts."""
+    import wavutil as W
+    from desta_b200.staging import PcmStager
+    rng = np.random.default_rng(0)
+    paths, payloads = [], []
+    for i, (kind, ch, sr, n) in enumerate([(W.S16, 1, 16000, 1001), (W.S24, 2, 44100, 333), (W.F32, 1, 22050, 10)]):
+        x = np.clip(0.3 * rng.standard_normal((n, ch)), -1, 0.999)
+        data = W.wav_bytes(x, sr, kind, extra_chunks=(i == 1))
+        p = tmp_path / f"h{i}.wav"
+        p.write_bytes(data)
+        paths.append(str(p))
+        payloads.append(W.encode(x, kind))
+    st = PcmStager(4, "cpu", slot_bytes=1 << 16, pin=False)
+    assert st.fill(0, paths) == 3
+    for (fmt, ch, sr, off, frames), raw in zip(st.clips[0], payloads):
+        assert off % 16 == 0 and bytes(st._host_np[0][off:off + len(raw)]) == raw and frames * ch * (1, 2, 3, 4, 4, 8)[fmt] == len(raw)
+    assert [c[2] for c in st.clips[0]] == [16000, 44100, 22050]
+    bad = tmp_path / "bad.wav"
+    bad.write_bytes(b"RIFFxxxxWAVE")
+    with pytest.raises(Exception, match="could not be decoded"):
+        st.fill(1, [str(bad)])
