@@ -148,7 +148,7 @@ def test_cuda_graph_replay_equals_eager(name):
         assert torch.equal(p.forward_features(wave_b), eager_b), "graph buffers were recycled under the graph"
     del junk
     with torch.no_grad():                                                  # weights change -> the stale graph is not used
-        p.connector.layer_weights[0] += 1.5                                # (a uniform shift would cancel in the softmax)
+        p.connector.layer_weights[:, 0] += 1.5                             # one tap up (a uniform shift cancels in the softmax)
         l1 = ops.STATS["launches"]
         changed = p.forward_features(wave_a)
     assert ops.STATS["launches"] > l1, "stale graph replayed after a weight update"
