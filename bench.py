@@ -355,7 +355,7 @@ def run_ours(args):
           "calls": sum(prof[k]["calls"] for k in ("gemm", "gemm_wgrad") if k in prof)}
     # DRAM traffic of the same kernel from the committed ncu capture of this command (per launch, like `achieved`)
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r1d_gemm_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r1f_gemm_traffic.json")
     if os.path.exists(tpath) and not train and args.workload == "large_v3_llama" and n == 64:
         traffic = json.load(open(tpath))["dram_bytes_per_launch_avg"]
     gemm_tflops = gm["work"] / (gm["ms"] * 1e-3) / 1e12
