@@ -90,7 +90,7 @@ def bench_splice():
 def bench_resample():
     import numpy as np
     N = 64
-    for sr, ch in ((22050, 1), (24000, 1), (32000, 1), (44100, 2), (48000, 2), (8000, 1), (16000, 2)):
+    for sr, ch in ((22050, 1), (24000, 1), (32000, 1), (44100, 2), (44100, 1), (48000, 2), (8000, 1), (16000, 2)):
         n = sr * 30
         pcm = torch.randint(-20000, 20000, (N, n * ch), dtype=torch.int16, device="cuda").view(torch.uint8).reshape(-1)
         clips = [(i * n * ch * 2, n, i) for i in range(N)]
