@@ -1,5 +1,5 @@
 // Memory-bound helpers around the tensor-core kernels: LayerNorm, conv-stem im2col, Q-Former layer mix.
-// One warp per row, 128-bit coalesced loads/stores; grids sized from the row count (>= several waves at flagship sizes).
+// One warp per row, 128-bit coalesced loads/stores; LayerNorm runs persistent warps with a one-row prefetch.
 #include "common.cuh"
 #include "desta_b200.h"
 
@@ -11,53 +11,74 @@ __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ gamma, const float* __restrict__ beta,
                  float eps, int M, int D, __nv_bfloat16* __restrict__ out_bf16, int ld_bf16, float* __restrict__ out_f32,
                  int ld_f32) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= M) return;
+  // Persistent warps: one row at a time per warp, held in registers; the loads of the warp's NEXT row are issued before the
+  // statistics of the current one, so every warp always has a full row of HBM reads in flight.
+  const int lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= M) return;
   const int nv = D >> 2;                     // float4 per row
-  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)warp * ldx);
-  float4 v[MAXV];
-  float s = 0.f;
-#pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    const int idx = lane + 32 * i;
-    if (idx < nv) {
-      v[i] = xr[idx];
-      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-    }
-  }
-#pragma unroll
-  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  const float mean = s / (float)D;
-  float ss = 0.f;
-#pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    const int idx = lane + 32 * i;
-    if (idx < nv) {
-      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
-      ss += (a * a + b * b) + (c * c + d * d);
-    }
-  }
-#pragma unroll
-  for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-  const float rstd = rsqrtf(ss / (float)D + eps);
   const float4* g4 = reinterpret_cast<const float4*>(gamma);
   const float4* b4 = reinterpret_cast<const float4*>(beta);
+  float4 v[MAXV], nx[MAXV];
+  {
+    const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * ldx);
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    const int idx = lane + 32 * i;
-    if (idx < nv) {
-      const float4 g = __ldg(g4 + idx), b = __ldg(b4 + idx);
-      float4 y;
-      y.x = (v[i].x - mean) * rstd * g.x + b.x;
-      y.y = (v[i].y - mean) * rstd * g.y + b.y;
-      y.z = (v[i].z - mean) * rstd * g.z + b.z;
-      y.w = (v[i].w - mean) * rstd * g.w + b.w;
-      if (out_f32) reinterpret_cast<float4*>(out_f32 + (size_t)warp * ld_f32)[idx] = y;
-      if (out_bf16) {
-        uint2 u;
-        u.x = pack_bf16(y.x, y.y);
-        u.y = pack_bf16(y.z, y.w);
-        reinterpret_cast<uint2*>(out_bf16 + (size_t)warp * ld_bf16)[idx] = u;
+    for (int i = 0; i < MAXV; ++i) {
+      const int idx = lane + 32 * i;
+      if (idx < nv) nx[i] = xr[idx];
+    }
+  }
+  for (; row < M; row += nwarps) {
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) v[i] = nx[i];
+    const int next = row + nwarps;
+    if (next < M) {
+      const float4* xr = reinterpret_cast<const float4*>(x + (size_t)next * ldx);
+#pragma unroll
+      for (int i = 0; i < MAXV; ++i) {
+        const int idx = lane + 32 * i;
+        if (idx < nv) nx[i] = xr[idx];
+      }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int idx = lane + 32 * i;
+      if (idx < nv) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / (float)D;
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int idx = lane + 32 * i;
+      if (idx < nv) {
+        const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+        ss += (a * a + b * b) + (c * c + d * d);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float rstd = rsqrtf(ss / (float)D + eps);
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int idx = lane + 32 * i;
+      if (idx < nv) {
+        const float4 g = __ldg(g4 + idx), b = __ldg(b4 + idx);
+        float4 y;
+        y.x = (v[i].x - mean) * rstd * g.x + b.x;
+        y.y = (v[i].y - mean) * rstd * g.y + b.y;
+        y.z = (v[i].z - mean) * rstd * g.z + b.z;
+        y.w = (v[i].w - mean) * rstd * g.w + b.w;
+        if (out_f32) reinterpret_cast<float4*>(out_f32 + (size_t)row * ld_f32)[idx] = y;
+        if (out_bf16) {
+          uint2 u;
+          u.x = pack_bf16(y.x, y.y);
+          u.y = pack_bf16(y.z, y.w);
+          reinterpret_cast<uint2*>(out_bf16 + (size_t)row * ld_bf16)[idx] = u;
+        }
       }
     }
   }
@@ -117,7 +138,9 @@ extern "C" int desta_layernorm(const float* x, int ldx, const float* gamma, cons
     return DESTA_ERR_ARG;
   }
   const int threads = 256, rows_per_block = threads / 32;
-  const int grid = (M + rows_per_block - 1) / rows_per_block;
+  int grid = (M + rows_per_block - 1) / rows_per_block;
+  const int cap = num_sms() * 2;             // persistent: two 8-warp CTAs per SM (128 registers), each warp walks rows with a one-row prefetch
+  if (grid > cap) grid = cap;
   cudaStream_t s = (cudaStream_t)stream;
   if (D <= 512)
     layernorm_kernel<4><<<grid, threads, 0, s>>>(x, ldx, gamma, beta, eps, M, D, (__nv_bfloat16*)out_bf16, ld_bf16, out_f32, ld_f32);
