@@ -382,7 +382,7 @@ def run_ours(args):
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "gemm_bf16_tn_2cta_kernel (per launch, averaged over the GEMM launches of one step)",
                      "achieved": round(gemm_tflops, 1), "peak": tf_sust, "unit": "TFLOP/s",
-                     "frac": round(gemm_tflops / tf_sust, 4), "traffic": traffic,
+                     "frac": round(gemm_tflops / tf_sust, 4), "frac_of_burst_peak": round(gemm_tflops / tf_burst, 4), "traffic": traffic,
                      "algorithmic_bytes": round(gm["bytes"] / max(gm["calls"], 1)), "launches_per_step": gm["calls"],
                      "avg_launch_ms": round(gm["ms"] / max(gm["calls"], 1), 4), "flop_per_launch": round(gm["work"] / max(gm["calls"], 1)),
                      "peak_kind": f"{peak_kind} sustained bf16 (cuBLAS under the power cap; burst {tf_burst})",
