@@ -135,3 +135,25 @@ def test_reference_assets_parse():
         y, _ = A.load(data[:off + min(n, 4000) * ch * (1, 2, 3, 4, 4, 8)[kind]])
         assert y.dtype == np.float32 and np.isfinite(y).all() and np.abs(y).max() <= 1.0 + 1e-3
     assert (A.FMT_F32, 16000) in seen and (A.FMT_S16, 22050) in seen and (A.FMT_S16, 32000) in seen
+
+
+@pytest.mark.parametrize("sr", [8000, 22050, 24000, 32000, 44100, 48000])
+def test_oracle_agrees_with_an_independent_resampler_on_band_limited_input(sr):
+    """torchaudio's Kaiser-windowed sinc resampler (its documented "kaiser_best" parameters: an independent third-party
+    design with another window, width and roll-off) and the oracle must produce the same samples wherever the input has no
+    energy above 0.8 of the lower Nyquist frequency: both are then ideal band-limited interpolators.  Same output length
+    (ceil(n * 16000 / sr)), same time alignment, values within 2e-5."""
+    torch = pytest.importorskip("torch")
+    ta = pytest.importorskip("torchaudio")
+    rng = np.random.default_rng(sr)
+    n = sr // 2
+    t = np.arange(n) / sr
+    low = min(sr, 16000) / 2
+    x = np.zeros(n)
+    for _ in range(40):
+        x += rng.uniform(0.01, 0.05) * np.sin(2 * np.pi * rng.uniform(50, 0.8 * low) * t + rng.uniform(0, 6.28))
+    y = A.resample(x, sr, 16000)
+    yt = ta.functional.resample(torch.from_numpy(x).float(), sr, 16000, lowpass_filter_width=64, rolloff=0.9475937167399596,
+                                resampling_method="sinc_interp_kaiser", beta=14.769656459379492).numpy()
+    assert len(yt) == len(y)
+    assert np.abs(y - yt)[300:-300].max() < 2e-5
