@@ -13,8 +13,8 @@ golden vectors for it, so this file restates the *published specification* - an 
 band edges, realised as a Kaiser-windowed sinc - and the tests pin it against what any implementation of that
 specification must reproduce: pass-band sinusoids map to the analytically resampled sinusoid, stop-band sinusoids vanish,
 scipy.signal.resample_poly with the same prototype agrees, torchaudio's independent Kaiser-sinc resampler ("kaiser_best"
-parameters) agrees to 1e-5 on band-limited input (same length, same alignment), the identity rate is exact.  Inside the transition band
-(7.3-8 kHz for a 16 kHz target) a different filter realisation may differ from soxr by design.
+parameters) agrees to 1e-5 on band-limited input (same length, same alignment), the identity rate is exact.  Inside the
+transition band (7.3-8 kHz for a 16 kHz target) a different filter realisation may differ from soxr by design.
 
 The decode and down-mix steps (everything a 16 kHz file goes through) ARE pinned: stdlib `wave` / scipy read the same
 bytes and the scaling rules below are libsndfile's documented float conversion, which tests/golden fixtures already use.
