@@ -59,3 +59,28 @@ def test_pad_or_truncate_properties(kinds, seed):
     # idempotent: padding the padded batch changes nothing
     out2, lengths2 = pad_or_truncate_batch(out) if len(clips) else (out, lengths)
     assert np.array_equal(out2, out)
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.integers(0, 5), st.integers(1, 4), st.sampled_from([8000, 16000, 22050, 44100, 48000]), st.integers(0, 300),
+       st.booleans(), st.lists(st.integers(0, 23), min_size=0, max_size=3), st.integers(0, 40))
+def test_wav_header_walk_product_equals_oracle(kind, ch, sr, frames, extensible, junk_sizes, cut):
+    """RIFF chunk walk of the product (desta_b200.audio.read_wav_info, file based) against the oracle (bytes based) on
+    random layouts: unknown chunks of odd and even sizes before `fmt ` and `data`, EXTENSIBLE headers, truncated payloads."""
+    import io
+    import struct
+
+    import wavutil as W
+    from desta_b200 import audio
+    from oracle import audio_io as A
+    x = np.zeros((frames, ch))
+    data = W.wav_bytes(x, sr, kind, extensible=extensible and kind != W.U8)
+    # splice junk chunks in front of the fmt chunk (12-byte RIFF header first)
+    junk = b"".join(b"JUNK" + struct.pack("<I", n) + bytes(n) + (b"\x00" if n & 1 else b"") for n in junk_sizes)
+    data = data[:12] + junk + data[12:]
+    if cut and cut < len(data) - 60:
+        data = data[:len(data) - cut]                       # payload cut short
+    ref = A.parse_wav(data)
+    info = audio.read_wav_info(io.BytesIO(data), len(data))
+    assert (info.fmt, info.channels, info.sample_rate, info.data_offset, info.n_frames) == ref
+    assert ref[0] == kind and ref[1] == ch and ref[2] == sr and ref[4] <= frames
