@@ -29,3 +29,32 @@ def test_install_keeps_reference_checkpoint_layout():
     # the product path has no CPU fallback: calling it without CUDA must fail loudly, not silently run elsewhere
     with pytest.raises((AssertionError, RuntimeError)):
         model.perception(input_features=torch.zeros(1, cfg.n_mels, 3000))
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="reference tree not present on this machine")
+def test_install_patch_audio_rebinds_the_name_generate_uses():
+    """install(model, patch_audio=True) swaps the module-level `AudioSegment` that generate() calls
+    (modeling_desta25.py:13, :1553-1557) for the GPU decode + resample mirror; the default install leaves it alone."""
+    import sys
+
+    import desta_b200
+    from desta_b200 import audio
+    from oracle.configs import CONFIGS
+    from oracle.refshim import load_reference
+    cfg = CONFIGS["micro"]
+    ref = load_reference(cfg)
+    rcfg = ref.DeSTA25Config(llm_model_id="llama-micro", encoder_model_id=cfg.encoder_model_id,
+                             qformer_num_hidden_layers=cfg.qf_layers, prompt_size=cfg.prompt_size)
+    mod = sys.modules[ref.DeSTA25AudioModel.__module__]
+    original = mod.AudioSegment
+    try:
+        model = ref.DeSTA25AudioModel(rcfg)
+        desta_b200.install(model)
+        assert mod.AudioSegment is original
+        model2 = ref.DeSTA25AudioModel(rcfg)
+        desta_b200.install(model2, patch_audio=True)
+        assert mod.AudioSegment is audio.AudioSegment
+        # same call shape as the reference's: classmethod from_file(path, target_sr=..., channel_selector=...) -> .samples
+        assert callable(mod.AudioSegment.from_file) and hasattr(mod.AudioSegment, "samples")
+    finally:
+        mod.AudioSegment = original
