@@ -50,8 +50,12 @@ def read_wav_info(f, file_size):
         body = pos + 8
         if tag == b"fmt ":
             raw = f.read(min(size, 40))
+            if len(raw) < 16:
+                raise ValueError("truncated fmt chunk")
             code, ch, sr, _rate, _align, bits = struct.unpack("<HHIIHH", raw[:16])
-            if code == 0xFFFE and len(raw) >= 26:          # WAVE_FORMAT_EXTENSIBLE: the sub-format GUID starts with the real code
+            if code == 0xFFFE:                             # WAVE_FORMAT_EXTENSIBLE: the sub-format GUID starts with the real code
+                if len(raw) < 26:
+                    raise ValueError("truncated extensible fmt chunk")
                 code = struct.unpack("<H", raw[24:26])[0]
             fmt = (code, ch, sr, bits)
         elif tag == b"data":
@@ -119,15 +123,21 @@ def load_waveforms(paths, device="cuda", target_sr=16000, n_samples=N_SAMPLES, o
 
 class DeviceWave(np.ndarray):
     """Host copy of a waveform that remembers the device tensor it came from, so that the processor shim
-    (desta_b200.processor.WaveformProcessor) can assemble the batch without a second host -> device copy."""
+    (desta_b200.processor.WaveformProcessor) can assemble the batch without a second host -> device copy.
+
+    Only the object `AudioSegment.samples` returns carries the tensor: anything derived from it (`w * 0.5`, `w[::-1]`,
+    `np.clip(w, ...)`, slices, copies) is a plain host array again as far as the processor is concerned, and the carrier
+    itself is read-only, so the two copies cannot drift apart silently - a caller that edits the samples gets its edited
+    host array uploaded like any other."""
 
     def __new__(cls, host, device_tensor):
         obj = np.asarray(host).view(cls)
         obj.device_tensor = device_tensor
+        obj.flags.writeable = False
         return obj
 
     def __array_finalize__(self, obj):
-        self.device_tensor = getattr(obj, "device_tensor", None) if obj is not None and getattr(obj, "shape", None) == self.shape else None
+        self.device_tensor = None
 
 
 class AudioSegment:

@@ -92,6 +92,17 @@ class TrainState:
             return self.__dict__[name]
         raise AttributeError(name)
 
+    @property
+    def pinned(self):
+        return self._pin is not None and self._pin() is not None
+
+    def pin(self, token):
+        import weakref
+        self._pin = weakref.ref(token)
+
+    def unpin(self):
+        self._pin = None
+
     def native_ws(self) -> torch.Tensor:
         if self._native_ws is None:
             nbytes = lib().desta_connector_train_workspace_bytes(ctypes.byref(self._c_dims), self.N)
@@ -137,6 +148,8 @@ class TrainState:
         self.dims, self.N, self.device = dims, N, device
         self._c_dims = dims.c_struct()
         self._native_ws = None
+        self.generation = 0         # bumped by every training forward that overwrites the saved activations
+        self._pin = None            # weakref to the token of the autograd graph that still needs them (see _ConnectorFn)
         # gradient buffers (fp32, fused like the packed weights): views of ONE arena, so that zeroing them and handing a
         # private copy to autograd are single launches instead of one per tensor (165 parameters at the flagship size)
         shapes = dict(layer_weights=(Q, K), prompts=(K * Q, d), kv_w=(L * 2 * d, d), kv_b=(L * 2 * d,),
@@ -362,31 +375,54 @@ def grads_by_name(st: TrainState, dims: PathDims) -> Dict[str, torch.Tensor]:
     return out
 
 
+class _GraphToken:
+    """Lives as long as the autograd node of one training forward; the workspaces it pins are not reused meanwhile."""
+
+
 class _ConnectorFn(torch.autograd.Function):
+    """Differentiable connector.  The activations the backward needs (taps, K/V, per-layer states, dropout plan) live in
+    the perception module's Workspace / TrainState, not in autograd saved tensors, so autograd's version counters cannot
+    protect them.  Two guards do instead: (1) from this forward until the end of its backward both objects are PINNED - a
+    second forward before the backward (two grad-enabled forwards in one loss, an eval / generate call in between) gets
+    fresh buffers instead of overwriting these; (2) both carry a generation counter that every overwriting forward bumps;
+    the backward raises if it no longer matches what the forward stamped (e.g. a second backward through a retained graph
+    after the buffers were released and reused) rather than returning wrong gradients."""
+
     @staticmethod
-    def forward(ctx, perception, N, *params):
+    def forward(ctx, perception, ws, st, *params):
+        N = ws.N
         enc, con = perception._packs()
-        ws = perception._workspace(N)
-        st = perception._train_state(N)
         out = torch.empty(N * perception.dims.prompt_size, perception.dims.d_llm, dtype=torch.float32, device=ws.h.device)
         plan = perception._drop_plan()
         native = engine._native_enabled()
-        (connector_forward_train_native if native else connector_forward_train)(con, perception.dims, ws, st, out, plan)
+        st.generation += 1
+        with ops.device_guard(ws.h.device):
+            (connector_forward_train_native if native else connector_forward_train)(con, perception.dims, ws, st, out, plan)
         ctx.native = native
         ctx.perception, ctx.N, ctx.plan = perception, N, plan
+        ctx.ws, ctx.st, ctx.stamp = ws, st, (ws.generation, st.generation)
+        ctx.token = _GraphToken()
+        ws.pin(ctx.token)
+        st.pin(ctx.token)
         return out.view(N, perception.dims.prompt_size, perception.dims.d_llm)
 
     @staticmethod
     def backward(ctx, grad_out):
         p, N = ctx.perception, ctx.N
+        ws, st = ctx.ws, ctx.st
+        if (ws.generation, st.generation) != ctx.stamp:
+            raise RuntimeError(
+                "desta_b200: the activations saved by this connector forward were overwritten by a later forward "
+                f"(stamp {ctx.stamp}, now {(ws.generation, st.generation)}); a graph can be differentiated again only while no "
+                "other forward of the same batch size has run since its first backward")
         _, con = p._packs()
         conT = p._t_pack()
-        ws, st = p._workspace(N), p._train_state(N)
         st.zero_grads()
         g = grad_out.to(torch.float32).contiguous().view(N * p.dims.prompt_size, p.dims.d_llm)
         sync = getattr(p, "grad_sync", None)       # data-parallel all-reduce overlapped with the backward (dist.GradSync)
-        (connector_backward_native if ctx.native else connector_backward)(
-            con, conT, p.dims, ws, st, g, ctx.plan, on_ready=sync.reduce if sync is not None else None)
+        with ops.device_guard(ws.h.device):
+            (connector_backward_native if ctx.native else connector_backward)(
+                con, conT, p.dims, ws, st, g, ctx.plan, on_ready=sync.reduce if sync is not None else None)
         if sync is not None:
             sync.finish(st.arena)
         # one private copy of the whole gradient arena; the per-parameter gradients are views of it (same offsets)
@@ -401,15 +437,16 @@ class _ConnectorFn(torch.autograd.Function):
             v = by_name[name]
             gv = torch.as_strided(priv, v.shape, v.stride(), (v.data_ptr() - base) // 4).reshape(prm.shape)
             grads.append(gv if prm.dtype == torch.float32 else gv.to(prm.dtype))
-        return (None, None, *grads)
+        ws.unpin()                                 # the buffers may serve the next step (same objects, no reallocation)
+        st.unpin()
+        return (None, None, None, *grads)
 
 
 def connector_training_forward(perception, input_features):
     """Frozen encoder forward (no graph) + differentiable connector."""
     N = input_features.size(0)
     with torch.no_grad():
-        enc, _ = perception._packs()
-        ws = perception._workspace(N)
-        engine.encoder_forward(enc, perception.dims, ws, perception.mel_time_major(input_features))
+        ws = perception._run_encoder(input_features)      # bumps ws.generation; never a pinned workspace
+    st = perception._train_state(N)
     params = [prm for _, prm in perception.connector.named_parameters()]
-    return _ConnectorFn.apply(perception, N, *params)
+    return _ConnectorFn.apply(perception, ws, st, *params)

@@ -179,3 +179,48 @@ extern "C" int desta_layer_mix(const float* x, const float* layer_weights, int t
   layer_mix_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, layer_weights, taps, N * Q, Q, D / 4, out);
   return check_launch("layer_mix_kernel");
 }
+
+// ---- per-row content hash (scope row n2, see desta_b200.h) ----
+namespace desta {
+__device__ __forceinline__ uint64_t mix64(uint32_t w, uint64_t i) {
+  uint64_t z = ((uint64_t)w | (i << 32)) + 0x9E3779B97F4A7C15ull * (i + 1);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+constexpr int RH_CHUNK = 8192;      // 32-bit words per block
+__global__ void __launch_bounds__(256)
+row_hash_kernel(const uint8_t* __restrict__ rows, int64_t words, int64_t stride_bytes, unsigned long long* __restrict__ out) {
+  const uint32_t* r = reinterpret_cast<const uint32_t*>(rows + (size_t)blockIdx.y * stride_bytes);
+  const int64_t i0 = (int64_t)blockIdx.x * RH_CHUNK;
+  const int64_t i1 = i0 + RH_CHUNK < words ? i0 + RH_CHUNK : words;
+  uint64_t acc = 0;
+  for (int64_t i = i0 + threadIdx.x; i < i1; i += blockDim.x) acc += mix64(__ldg(r + i), (uint64_t)i);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ uint64_t part[8];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint64_t t = 0;
+    for (int w = 0; w < 8; ++w) t += part[w];
+    atomicAdd(out + blockIdx.y, (unsigned long long)t);
+  }
+}
+}  // namespace desta
+
+extern "C" int desta_row_hash(const void* rows, int64_t n_rows, int64_t row_bytes, int64_t row_stride_bytes, uint64_t* out,
+                              void* stream) {
+  using namespace desta;
+  if (n_rows <= 0) return DESTA_OK;
+  if (!rows || !out || row_bytes <= 0 || (row_bytes & 3) || (row_stride_bytes & 3) || ((uintptr_t)rows & 3) || n_rows > 65535) {
+    set_error("desta_row_hash: rows must be 4-byte aligned multiples of 4 bytes, n_rows <= 65535");
+    return DESTA_ERR_ARG;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  if (cudaMemsetAsync(out, 0, (size_t)n_rows * 8, s) != cudaSuccess) return check_launch("desta_row_hash memset");
+  const int64_t words = row_bytes / 4;
+  const dim3 grid((unsigned)((words + RH_CHUNK - 1) / RH_CHUNK), (unsigned)n_rows);
+  row_hash_kernel<<<grid, 256, 0, s>>>((const uint8_t*)rows, words, row_stride_bytes, (unsigned long long*)out);
+  return check_launch("row_hash_kernel");
+}

@@ -13,11 +13,24 @@ namespace desta {
 // Each warp owns output rows; the 32 lanes scan the clip descriptors (staged in shared memory) to find the LAST clip
 // whose span [start, start + Q + T_i) covers the row - "later clips win", exactly the reference's loop order - so no
 // row-map pass and no scratch buffer are needed: ONE launch.
+// A token id outside [0, vocab) makes the reference's embedding lookup raise (IndexError on the CPU, a device-side assert on
+// CUDA; modeling_desta25.py:981,1009).  The kernel stays memory-safe (the row is read from a clamped id) and REPORTS it:
+// err_word[0] counts offending rows, err_word[1] keeps one offending id; the host raises from that word (ops.splice).
+__device__ __forceinline__ int64_t checked_id(int64_t id, int64_t vocab, int64_t* err_word, int lane) {
+  if (id >= 0 && id < vocab) return id;
+  if (err_word && lane == 0) {
+    atomicAdd(reinterpret_cast<unsigned long long*>(err_word), 1ull);
+    err_word[1] = id;
+  }
+  return id < 0 ? 0 : vocab - 1;
+}
+
 template <bool FEAT_F32>
 __global__ void __launch_bounds__(256)
 splice_rows_kernel(const int64_t* __restrict__ input_ids, const uint4* __restrict__ table, int64_t vocab,
                    const desta_splice_desc* __restrict__ descs, int n_desc, const int64_t* __restrict__ trans_ids,
-                   const void* __restrict__ feats, int Q, int S, int d8, int rows, uint4* __restrict__ out) {
+                   const void* __restrict__ feats, int Q, int S, int d8, int rows, uint4* __restrict__ out,
+                   int64_t* __restrict__ err_word) {
   extern __shared__ desta_splice_desc s_desc[];
   for (int i = threadIdx.x; i < n_desc; i += blockDim.x) s_desc[i] = descs[i];
   __syncthreads();
@@ -35,15 +48,11 @@ splice_rows_kernel(const int64_t* __restrict__ input_ids, const uint4* __restric
     uint4* o = out + (size_t)row * d8;
     const uint4* src = nullptr;
     if (hit < 0) {
-      int64_t id = input_ids[row];
-      id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
-      src = table + (size_t)id * d8;
+      src = table + (size_t)checked_id(input_ids[row], vocab, err_word, lane) * d8;
     } else {
       const int j = pos - s_desc[hit].start;
       if (j >= Q) {
-        int64_t id = trans_ids[s_desc[hit].trans_off + (j - Q)];
-        id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
-        src = table + (size_t)id * d8;
+        src = table + (size_t)checked_id(trans_ids[s_desc[hit].trans_off + (j - Q)], vocab, err_word, lane) * d8;
       } else if (!FEAT_F32) {
         src = reinterpret_cast<const uint4*>(feats) + ((size_t)hit * Q + j) * d8;
       } else {
@@ -88,7 +97,7 @@ using namespace desta;
 extern "C" int desta_splice(const int64_t* input_ids, const void* table, int64_t vocab, const desta_splice_desc* descs_dev,
                             const desta_splice_desc* descs_host, int n_desc, const int64_t* trans_ids,
                             const void* audio_feats, int feat_dtype, int Q, void* out, int B, int S, int d,
-                            int32_t* row_map, void* stream) {
+                            int64_t* err_word, void* stream) {
   if (!input_ids || !table || !out) { set_error("desta_splice: null pointer"); return DESTA_ERR_ARG; }
   if (B <= 0 || S <= 0) return DESTA_OK;
   if (d % 8) { set_error("desta_splice: hidden size must be a multiple of 8 (got %d)", d); return DESTA_ERR_ARG; }
@@ -106,7 +115,6 @@ extern "C" int desta_splice(const int64_t* input_ids, const void* table, int64_t
   }
   cudaStream_t s = (cudaStream_t)stream;
   const int rows = B * S;
-  (void)row_map;
   int grid = (rows + 7) / 8;
   const int cap = num_sms() * 8;
   if (grid > cap) grid = cap;
@@ -118,10 +126,10 @@ extern "C" int desta_splice(const int64_t* input_ids, const void* table, int64_t
   }
   if (feat_dtype == 0)
     splice_rows_kernel<true><<<grid, 256, sm, s>>>(input_ids, (const uint4*)table, vocab, descs_dev, n_desc, trans_ids, audio_feats, Q,
-                                                   S, d / 8, rows, (uint4*)out);
+                                                   S, d / 8, rows, (uint4*)out, err_word);
   else
     splice_rows_kernel<false><<<grid, 256, sm, s>>>(input_ids, (const uint4*)table, vocab, descs_dev, n_desc, trans_ids, audio_feats, Q,
-                                                    S, d / 8, rows, (uint4*)out);
+                                                    S, d / 8, rows, (uint4*)out, err_word);
   return check_launch("splice kernels");
 }
 

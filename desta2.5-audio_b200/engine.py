@@ -159,6 +159,20 @@ class Workspace:
         self._c_dims = dims.c_struct()
         self._enc_ws = None
         self._con_ws = None
+        self.generation = 0         # bumped by every forward that overwrites the buffers (checked by the training backward)
+        self._pin = None            # weakref to the token of the training graph that still needs these buffers
+        self.h_valid = False
+
+    @property
+    def pinned(self):
+        return self._pin is not None and self._pin() is not None
+
+    def pin(self, token):
+        import weakref
+        self._pin = weakref.ref(token)
+
+    def unpin(self):
+        self._pin = None
 
     def native_ws(self, which: str) -> torch.Tensor:
         attr = "_enc_ws" if which == "encoder" else "_con_ws"
@@ -211,17 +225,33 @@ def _native_enabled():
     return ops._PROFILE is None        # the per-family CUDA-event profile of bench.py needs the per-op schedule
 
 
-def encoder_forward(enc: EncoderPack, dims: PathDims, ws: Workspace, mel_tm: torch.Tensor):
-    """mel_tm: bf16 time-major log-mel [N, 3000, n_mels] -> ws.taps[k] (bf16 [N*1500, d]) and ws.h.  One call of the
-    native schedule desta_encoder_fwd (same launches, same order as encoder_forward_ops below)."""
+def encoder_forward(enc: EncoderPack, dims: PathDims, ws: Workspace, mel_tm: torch.Tensor, taps=None, h=None):
+    """mel_tm: bf16 time-major log-mel [n, 3000, n_mels] -> taps[k] (bf16 [n*1500, d]) and h (fp32 [n*1500, d]).  One call
+    of the native schedule desta_encoder_fwd (same launches, same order as encoder_forward_ops below).
+    By default n == ws.N and the outputs are ws.taps / ws.h.  A SUBSET run (scope row n2: only the clips whose encoder
+    state is not cached) passes n < ws.N clips with its own compact `taps` [K, n*1500, d] / `h` [n*1500, d] and borrows
+    the byte workspace of the full batch."""
+    n = mel_tm.shape[0]
+    taps = ws.taps if taps is None else taps
+    h = ws.h if h is None else h
+    ops._cuda(mel_tm, torch.bfloat16), ops._cuda(taps, torch.bfloat16), ops._cuda(h, torch.float32)
+    assert mel_tm.is_contiguous() and mel_tm.shape == (n, 2 * dims.max_pos, dims.n_mels) and 0 < n <= ws.N
+    assert taps.is_contiguous() and taps.shape == (len(dims.tap_layers), n * dims.max_pos, dims.d_model)
+    assert h.is_contiguous() and h.shape == (n * dims.max_pos, dims.d_model)
+    ops.STATS["encoder_clips"] = ops.STATS.get("encoder_clips", 0) + n
     if not _native_enabled():
+        if n != ws.N or taps is not ws.taps or h is not ws.h:          # per-op schedule: buffers are sized per batch
+            sub = Workspace(dims, n, ws.device)
+            encoder_forward_ops(enc, dims, sub, mel_tm)
+            taps.copy_(sub.taps)
+            h.copy_(sub.h)
+            return
         return encoder_forward_ops(enc, dims, ws, mel_tm)
-    ops._cuda(mel_tm, torch.bfloat16)
-    assert mel_tm.is_contiguous() and mel_tm.shape == (ws.N, 2 * dims.max_pos, dims.n_mels)
     wsb = ws.native_ws("encoder")
     ops.STATS["launches"] += 4 + 7 * dims.n_layers
-    check(lib().desta_encoder_fwd(ctypes.byref(ws._c_dims), ctypes.byref(enc.c_weights), ops._p(mel_tm), ws.N, ops._p(wsb), wsb.numel(),
-                                  ops._p(ws.taps), ops._p(ws.h), ops._stream()), "desta_encoder_fwd")
+    with ops.device_guard(ops._dev(mel_tm, taps, h, wsb, enc.pos)):
+        check(lib().desta_encoder_fwd(ctypes.byref(ws._c_dims), ctypes.byref(enc.c_weights), ops._p(mel_tm), n, ops._p(wsb), wsb.numel(),
+                                      ops._p(taps), ops._p(h), ops._stream()), "desta_encoder_fwd")
 
 
 def connector_forward(con: ConnectorPack, dims: PathDims, ws: Workspace, out_f32: torch.Tensor):
@@ -232,8 +262,9 @@ def connector_forward(con: ConnectorPack, dims: PathDims, ws: Workspace, out_f32
     assert out_f32.is_contiguous() and out_f32.shape == (ws.N * dims.prompt_size, dims.d_llm)
     wsb = ws.native_ws("connector")
     ops.STATS["launches"] += 2 + 11 * dims.qf_layers + 3
-    check(lib().desta_connector_fwd(ctypes.byref(ws._c_dims), ctypes.byref(con.c_weights), ops._p(ws.taps), ws.N, ops._p(wsb),
-                                    wsb.numel(), ops._p(out_f32), ops._stream()), "desta_connector_fwd")
+    with ops.device_guard(ops._dev(ws.taps, wsb, out_f32, con.proj_b)):
+        check(lib().desta_connector_fwd(ctypes.byref(ws._c_dims), ctypes.byref(con.c_weights), ops._p(ws.taps), ws.N, ops._p(wsb),
+                                        wsb.numel(), ops._p(out_f32), ops._stream()), "desta_connector_fwd")
     return out_f32
 
 

@@ -35,12 +35,33 @@ def stop_profile():
     return out
 
 
+def _dev(*tensors):
+    """The one CUDA device all tensor arguments of a call live on (None entries are skipped)."""
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        assert t.is_cuda, "desta_b200 ops run on CUDA tensors only (no CPU fallback)"
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise ValueError(f"desta_b200: tensor arguments on different devices ({dev} and {t.device})")
+    return dev
+
+
 class _op:
-    def __init__(self, family, launches, work=0.0, unit="flop", nbytes=0.0):
+    """Accounting + DEVICE GUARD of one C-ABI call: the library launches on the CURRENT device (cudaGetDevice: kernel
+    attributes, SM count, the launch itself), so the call is made with the tensors' device current and on that device's
+    current stream - a model moved to cuda:1 without torch.cuda.set_device(1) must not launch on cuda:0."""
+
+    def __init__(self, family, launches, work=0.0, unit="flop", nbytes=0.0, dev=None):
         self.family, self.launches, self.work, self.unit = family, launches, work, unit
         self.nbytes = nbytes if unit == "flop" else work      # algorithmic DRAM bytes of the launch
+        self.guard = torch.cuda.device(dev) if dev is not None and dev.index is not None else None
 
     def __enter__(self):
+        if self.guard is not None:
+            self.guard.__enter__()
         STATS["launches"] += self.launches
         if _PROFILE is not None:
             self.e0 = torch.cuda.Event(enable_timing=True)
@@ -51,10 +72,18 @@ class _op:
         if _PROFILE is not None and exc[0] is None:
             self.e1.record()
             _PROFILE.append((self.family, self.work, self.unit, self.e0, self.e1, self.nbytes))
+        if self.guard is not None:
+            self.guard.__exit__(*exc)
         return False
 
 
+def device_guard(dev):
+    """Guard for the stage-level native calls (engine / autograd): same rule as `_op`."""
+    return torch.cuda.device(dev)
+
+
 def _stream():
+    # evaluated inside the `_op` guard: the current device IS the tensors' device here
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
@@ -100,7 +129,7 @@ def gemm(a, w, bias=None, *, out_bf16=None, out_f32=None, resid=None, pos=None, 
     # algorithmic bytes: A and W read once, every output written once, the residual read once
     nbytes = 2.0 * (M * K + N * K) + M * N * ((4 if out_f32 is not None else 0) + (2 if out_bf16 is not None else 0)
                                               + (4 if resid is not None else 0))
-    with _op("gemm", 1, 2.0 * M * N * K, nbytes=nbytes):
+    with _op("gemm", 1, 2.0 * M * N * K, nbytes=nbytes, dev=_dev(a, w, bias, out_f32, out_bf16, resid, pos)):
         check(lib().desta_gemm_bf16(_p(a), a.stride(0), _p(w), w.stride(0), M, N, K, ctypes.byref(ep), _stream()), "desta_gemm_bf16")
 
 
@@ -109,7 +138,7 @@ def layernorm(x, gamma, beta, eps, *, out_bf16=None, out_f32=None):
     M, D = x.shape
     assert x.stride(1) == 1
     nbytes = M * D * (4 + (2 if out_bf16 is not None else 0) + (4 if out_f32 is not None else 0))
-    with _op("layernorm", 1, nbytes, "byte"):
+    with _op("layernorm", 1, nbytes, "byte", dev=_dev(x, gamma, beta, out_bf16, out_f32)):
         check(lib().desta_layernorm(_p(x), x.stride(0), _p(gamma), _p(beta), float(eps), M, D,
                                     _p(out_bf16), out_bf16.stride(0) if out_bf16 is not None else 0,
                                     _p(out_f32), out_f32.stride(0) if out_f32 is not None else 0, _stream()), "desta_layernorm")
@@ -134,7 +163,7 @@ def attention(q, k, v, out, batch, heads, Tq, Tk, scale, lse=None, drop=None):
         _cuda(t, torch.bfloat16)
         assert t.stride(1) == 1
     assert q.shape[0] == batch * Tq and k.shape[0] == batch * Tk and v.shape[0] == batch * Tk and out.shape[0] == batch * Tq
-    with _op("attention", 1, 4.0 * batch * heads * Tq * Tk * 64):
+    with _op("attention", 1, 4.0 * batch * heads * Tq * Tk * 64, dev=_dev(q, k, v, out, lse)):
         check(lib().desta_attention(_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(out), out.stride(0),
                                     batch, heads, Tq, Tk, float(scale), _p(lse), _dp(drop), _stream()), "desta_attention")
 
@@ -144,7 +173,7 @@ def attention_bwd(q, k, v, o, dout, lse, dq, dk, dv, batch, heads, Tq, Tk, scale
         _cuda(t, torch.bfloat16)
         assert t.stride(1) == 1
     _cuda(lse, torch.float32)
-    with _op("attention_bwd", 1, 10.0 * batch * heads * Tq * Tk * 64):
+    with _op("attention_bwd", 1, 10.0 * batch * heads * Tq * Tk * 64, dev=_dev(q, k, v, o, dout, lse, dq, dk, dv)):
         check(lib().desta_attention_bwd(_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(o), o.stride(0),
                                         _p(dout), dout.stride(0), _p(lse), _p(dq), dq.stride(0), _p(dk), dk.stride(0),
                                         _p(dv), dv.stride(0), batch, heads, Tq, Tk, float(scale), _dp(drop), _stream()),
@@ -160,7 +189,7 @@ def dropout_add(x, resid, drop, *, out_f32=None, out_bf16=None):
         _cuda(resid, torch.float32)
         assert resid.shape == (M, N) and resid.stride(1) == 1
     nbytes = M * N * (4 + (4 if resid is not None else 0) + (4 if out_f32 is not None else 0) + (2 if out_bf16 is not None else 0))
-    with _op("dropout", 1, nbytes, "byte"):
+    with _op("dropout", 1, nbytes, "byte", dev=_dev(x, resid, out_f32, out_bf16)):
         check(lib().desta_dropout_add(_p(x), x.stride(0), _p(resid), resid.stride(0) if resid is not None else 0, M, N, _dp(drop),
                                       _p(out_f32), out_f32.stride(0) if out_f32 is not None else 0,
                                       _p(out_bf16), out_bf16.stride(0) if out_bf16 is not None else 0, _stream()),
@@ -170,7 +199,7 @@ def dropout_add(x, resid, drop, *, out_f32=None, out_bf16=None):
 def dropout_mask(drop, rows, cols, device):
     """Test hook: the keep mask (bool [rows, cols]) the kernels generate for `drop` over a [rows, cols] grid."""
     mask = torch.empty(rows, cols, dtype=torch.uint8, device=device)
-    with _op("dropout", 1, rows * cols, "byte"):
+    with _op("dropout", 1, rows * cols, "byte", dev=_dev(mask)):
         check(lib().desta_dropout_mask(_dp(drop), rows, cols, _p(mask), _stream()), "desta_dropout_mask")
     return mask.bool()
 
@@ -181,7 +210,7 @@ def gemm_wgrad(dy, x, dw):
     M, Nout = dy.shape
     M2, Kin = x.shape
     assert M == M2 and dw.shape == (Nout, Kin) and dy.stride(1) == 1 and x.stride(1) == 1 and dw.stride(1) == 1
-    with _op("gemm_wgrad", 1, 2.0 * M * Nout * Kin, nbytes=2.0 * M * (Nout + Kin) + 8.0 * Nout * Kin):
+    with _op("gemm_wgrad", 1, 2.0 * M * Nout * Kin, nbytes=2.0 * M * (Nout + Kin) + 8.0 * Nout * Kin, dev=_dev(dy, x, dw)):
         check(lib().desta_gemm_bf16_wgrad(_p(dy), dy.stride(0), _p(x), x.stride(0), M, Nout, Kin, _p(dw), dw.stride(0), _stream()),
               "desta_gemm_bf16_wgrad")
 
@@ -189,7 +218,7 @@ def gemm_wgrad(dy, x, dw):
 def layernorm_bwd(dy, x, gamma, eps, dgamma, dbeta, *, dx_f32=None, dx_bf16=None):
     _cuda(dy, torch.float32), _cuda(x, torch.float32)
     M, D = x.shape
-    with _op("layernorm_bwd", 1, M * D * 12, "byte"):
+    with _op("layernorm_bwd", 1, M * D * 12, "byte", dev=_dev(dy, x, gamma, dgamma, dbeta, dx_f32, dx_bf16)):
         check(lib().desta_layernorm_bwd(_p(dy), dy.stride(0), _p(x), x.stride(0), _p(gamma), float(eps), M, D,
                                         _p(dx_f32), dx_f32.stride(0) if dx_f32 is not None else 0,
                                         _p(dx_bf16), dx_bf16.stride(0) if dx_bf16 is not None else 0,
@@ -199,7 +228,7 @@ def layernorm_bwd(dy, x, gamma, eps, dgamma, dbeta, *, dx_f32=None, dx_bf16=None
 def gelu_fwd(h, y):
     _cuda(h, torch.bfloat16), _cuda(y, torch.bfloat16)
     assert h.is_contiguous() and y.is_contiguous()
-    with _op("gelu", 1, h.numel() * 4, "byte"):
+    with _op("gelu", 1, h.numel() * 4, "byte", dev=_dev(h, y)):
         check(lib().desta_gelu_fwd(_p(h), _p(y), h.numel(), _stream()), "desta_gelu_fwd")
 
 
@@ -207,7 +236,7 @@ def gelu_bwd(dy, h, dh):
     for t in (dy, h, dh):
         _cuda(t, torch.bfloat16)
         assert t.is_contiguous()
-    with _op("gelu", 1, h.numel() * 6, "byte"):
+    with _op("gelu", 1, h.numel() * 6, "byte", dev=_dev(dy, h, dh)):
         check(lib().desta_gelu_bwd(_p(dy), _p(h), _p(dh), h.numel(), _stream()), "desta_gelu_bwd")
 
 
@@ -217,7 +246,7 @@ def colsum(x, out):
     _cuda(out, torch.float32)
     M, N = x.shape
     assert out.numel() == N
-    with _op("colsum", 1, x.numel() * x.element_size(), "byte"):
+    with _op("colsum", 1, x.numel() * x.element_size(), "byte", dev=_dev(x, out)):
         check(lib().desta_colsum(_p(x), 0 if x.dtype == torch.float32 else 1, x.stride(0), M, N, _p(out), _stream()), "desta_colsum")
 
 
@@ -226,14 +255,14 @@ def layer_mix_bwd(dm, x, layer_weights, N, Q, dx, dlw):
     for t in (dm, x, layer_weights, dx, dlw):
         _cuda(t, torch.float32)
         assert t.is_contiguous()
-    with _op("layer_mix", 1, (2 * x.numel() + dm.numel()) * 4, "byte"):
+    with _op("layer_mix", 1, (2 * x.numel() + dm.numel()) * 4, "byte", dev=_dev(dm, x, layer_weights, dx, dlw)):
         check(lib().desta_layer_mix_bwd(_p(dm), _p(x), _p(layer_weights), taps, N, Q, D, _p(dx), _p(dlw), _stream()), "desta_layer_mix_bwd")
 
 
 def cast_bf16(x, y):
     _cuda(x, torch.float32), _cuda(y, torch.bfloat16)
     assert x.is_contiguous() and y.is_contiguous() and x.numel() == y.numel()
-    with _op("cast", 1, x.numel() * 6, "byte"):
+    with _op("cast", 1, x.numel() * 6, "byte", dev=_dev(x, y)):
         check(lib().desta_cast_f32_bf16(_p(x), _p(y), x.numel(), _stream()), "desta_cast_f32_bf16")
 
 
@@ -250,14 +279,14 @@ def splice_bwd(grad_out, descs, Q, dfeats):
     _cuda(grad_out, torch.bfloat16), _cuda(dfeats, torch.float32)
     B, S, d = grad_out.shape
     _, dev = splice_descs_device(descs, grad_out.device)
-    with _op("splice", 1, dfeats.numel() * 6, "byte"):
+    with _op("splice", 1, dfeats.numel() * 6, "byte", dev=_dev(grad_out, dfeats)):
         check(lib().desta_splice_bwd(_p(grad_out.contiguous()), _p(dev), len(descs), Q, S, d, _p(dfeats), _stream()), "desta_splice_bwd")
 
 
 def im2col_k3(x, N, T_in, C, stride, cols):
     _cuda(x, torch.bfloat16), _cuda(cols, torch.bfloat16)
     assert x.is_contiguous() and cols.is_contiguous() and cols.numel() == N * (T_in // stride) * 3 * C
-    with _op("im2col", 1, cols.numel() * 4, "byte"):
+    with _op("im2col", 1, cols.numel() * 4, "byte", dev=_dev(x, cols)):
         check(lib().desta_im2col_k3(_p(x), N, T_in, C, stride, _p(cols), _stream()), "desta_im2col_k3")
 
 
@@ -265,7 +294,7 @@ def layer_mix(x, layer_weights, N, Q, out):
     _cuda(x, torch.float32), _cuda(layer_weights, torch.float32), _cuda(out, torch.float32)
     taps, rows, D = x.shape
     assert rows == N * Q and x.is_contiguous() and out.is_contiguous() and layer_weights.is_contiguous()
-    with _op("layer_mix", 1, (x.numel() + out.numel()) * 4, "byte"):
+    with _op("layer_mix", 1, (x.numel() + out.numel()) * 4, "byte", dev=_dev(x, layer_weights, out)):
         check(lib().desta_layer_mix(_p(x), _p(layer_weights), taps, N, Q, D, _p(out), _stream()), "desta_layer_mix")
 
 
@@ -296,7 +325,8 @@ def logmel(wave, n_mels, *, n_valid=None, want_bf16_tm=False):
     if n_valid is not None:
         _cuda(n_valid, torch.int32)
     nbytes = N * (480000 * 4 + n_mels * 3000 * 4)      # algorithmic bytes: waveform in + fp32 log-mel out
-    with _op("logmel", 2, nbytes, "byte"):
+    STATS["logmel_calls"] = STATS.get("logmel_calls", 0) + 1
+    with _op("logmel", 2, nbytes, "byte", dev=_dev(wave, n_valid, plan)):
         check(lib().desta_logmel(_p(wave), _p(n_valid), N, n_mels, _p(plan), _p(out), _p(out_tm), _p(cmax), _stream()), "desta_logmel")
     return out, out_tm
 
@@ -344,15 +374,57 @@ def decode_resample(pcm, clips, fmt, channels, sr_in, sr_out, out, general_kerne
     dev = torch.frombuffer(bytearray(bytes(host)), dtype=torch.int64).to(out.device)
     frames = sum(c[1] for c in clips)
     nbytes = frames * channels * (1, 2, 3, 4, 4, 8)[fmt] + n * out.shape[1] * 4
-    with _op("decode_resample", 1, nbytes, "byte"):
+    with _op("decode_resample", 1, nbytes, "byte", dev=_dev(pcm, out, taps)):
         check(lib().desta_decode_resample(_p(dev), n, int(fmt), int(channels), ctypes.byref(plan), _p(taps), _p(out), out.stride(0),
                                           out.shape[1], _stream()), "desta_decode_resample")
     return lengths
 
 
+_err_words = {}
+
+
+def _err_word(device):
+    """int64[2] in pinned host memory that the splice kernel writes through UVA (count of rows with a token id outside the
+    embedding table, one offending id).  The host can read it at any time without touching the stream."""
+    key = str(device)
+    if key not in _err_words:
+        _err_words[key] = torch.zeros(2, dtype=torch.int64).pin_memory()
+    return _err_words[key]
+
+
+def check_token_ids(device=None, sync=False):
+    """Raise IndexError if a splice on `device` (all devices if None) saw a token id outside the embedding table - the
+    reference's `embed_tokens(...)` raises there (modeling_desta25.py:981, :1009; IndexError on the CPU, a device-side
+    assert on CUDA).  Like CUDA's own asynchronous errors the report surfaces at the next call on that device (every
+    `splice` checks first), or immediately with sync=True."""
+    for key, w in list(_err_words.items()):
+        if device is not None and key != str(torch.device(device)):
+            continue
+        if sync:
+            torch.cuda.synchronize(torch.device(key))
+        n = int(w[0])
+        if n:
+            bad = int(w[1])
+            w.zero_()
+            raise IndexError(f"index out of range in self: {n} row(s) of the <|AUDIO|> splice on {key} had a token id outside the "
+                             f"embedding table (e.g. {bad})")
+
+
+def row_hash(x):
+    """64-bit content hash of every row of a contiguous CUDA tensor [n, ...] (any 4-byte-multiple row size) -> int64 [n]."""
+    assert x.is_cuda and x.is_contiguous() and x.dim() >= 2
+    n = x.shape[0]
+    row_bytes = x[0].numel() * x.element_size()
+    out = torch.empty(max(n, 1), dtype=torch.int64, device=x.device)
+    with _op("row_hash", 1, n * row_bytes, "byte", dev=x.device):
+        check(lib().desta_row_hash(_p(x), n, row_bytes, row_bytes, _p(out), _stream()), "desta_row_hash")
+    return out[:n]
+
+
 def splice(input_ids, table, descs, trans_ids, feats, Q, out=None):
     """descs: list of (prompt, start, n_trans, trans_off); trans_ids: 1-D int64 CUDA tensor (concatenated) or None."""
     _cuda(input_ids, torch.int64), _cuda(table, torch.bfloat16)
+    check_token_ids(input_ids.device)                  # report of an earlier splice on this device, if any
     B, S = input_ids.shape
     V, d = table.shape
     n = len(descs)
@@ -370,7 +442,8 @@ def splice(input_ids, table, descs, trans_ids, feats, Q, out=None):
     fb = 4 if feat_dtype == 0 else 2
     n_audio_rows = n * Q
     nbytes = B * S * 8 + (B * S - n_audio_rows) * d * 2 + n_audio_rows * d * fb + B * S * d * 2
-    with _op("splice", 1, nbytes, "byte"):
+    err = _err_word(input_ids.device)
+    with _op("splice", 1, nbytes, "byte", dev=_dev(input_ids, table, trans_ids, feats, out)):
         check(lib().desta_splice(_p(input_ids.contiguous()), _p(table), V, _p(dev), host, n, _p(trans_ids), _p(feats), feat_dtype,
-                                 Q, _p(out), B, S, d, None, _stream()), "desta_splice")
+                                 Q, _p(out), B, S, d, ctypes.c_void_p(err.data_ptr()), _stream()), "desta_splice")
     return out

@@ -20,8 +20,8 @@ def install(model, wrap_processor: bool = True, patch_audio: bool = False):
     opt-in because it is module-wide and because other containers (flac, mp3 ...) need the reference's libsndfile path."""
     if getattr(model.config, "connector_mode", "qformer_1") != "qformer_1":
         raise NotImplementedError("desta_b200 covers connector_mode='qformer_1' (ORCA modifies LLM decoding: out of scope)")
-    ref_perception = model.perception
-    model.perception = WhisperPerceptionB200.from_reference(ref_perception)
+    if not isinstance(model.perception, WhisperPerceptionB200):        # idempotent: a second install() changes nothing
+        model.perception = WhisperPerceptionB200.from_reference(model.perception)
 
     def _prepare_inputs_for_llm(self, input_ids, attention_mask, batch_features, batch_transcription_ids, batch_start_positions):
         return prepare_inputs_for_llm(self.llm_model.model.embed_tokens.weight, self.perception, input_ids, attention_mask,
@@ -37,6 +37,31 @@ def install(model, wrap_processor: bool = True, patch_audio: bool = False):
         if mod is None or not hasattr(mod, "AudioSegment"):
             raise RuntimeError(f"{type(model).__module__} has no AudioSegment to replace")
         mod.AudioSegment = AudioSegment
-    if wrap_processor and getattr(model, "processor", None) is not None and not isinstance(model.processor, WaveformProcessor):
-        model.processor = WaveformProcessor(model.processor)
+    if wrap_processor:
+        _wrap_processor(model)
     return model
+
+
+def _wrap_processor(model):
+    """Boundary b1.  The reference creates `self.processor` lazily: `generate()` calls `_setup_generation()` on its first
+    use (modeling_desta25.py:1514-1515 -> :1467-1482, `AutoProcessor.from_pretrained` at :1475), i.e. usually AFTER
+    `install(model)`.  So besides wrapping a processor that already exists, `_setup_generation` itself is wrapped: whatever
+    processor it creates is handed back as a WaveformProcessor, and `generate()`'s
+    `self.processor(batch_features, sampling_rate=16000, return_tensors="pt").input_features` (:1570, :1583) yields padded
+    waveforms for the device log-mel instead of running the CPU WhisperFeatureExtractor."""
+    if getattr(model, "processor", None) is not None and not isinstance(model.processor, WaveformProcessor):
+        model.processor = WaveformProcessor(model.processor)
+    setup = getattr(model, "_setup_generation", None)
+    if setup is None or getattr(setup, "_desta_b200_wrapped", False):
+        return
+
+    def _setup_generation(self, *args, **kwargs):
+        out = setup(*args, **kwargs)
+        proc = getattr(self, "processor", None)
+        if proc is not None and not isinstance(proc, WaveformProcessor):
+            self.processor = WaveformProcessor(proc)
+        return out
+
+    bound = types.MethodType(_setup_generation, model)
+    bound.__func__._desta_b200_wrapped = True
+    model._setup_generation = bound

@@ -119,6 +119,11 @@ int desta_colsum(const void* x, int dtype, int ld, int M, int N, float* out, voi
 int desta_layer_mix_bwd(const float* dm, const float* x, const float* layer_weights, int taps, int N, int Q, int D, float* dx,
                         float* dlw, void* stream);
 int desta_cast_f32_bf16(const float* x, void* y, size_t n, void* stream);
+/* 64-bit content hash of each row (row_bytes % 4 == 0, rows 4-byte aligned): out[r] = sum over 32-bit words w_i of
+ * mix64(w_i, i) mod 2^64 - position-keyed, order-independent sum, hence deterministic.  Scope row n2: the ASR pass of
+ * generate() (modeling_desta25.py:1582-1601) encodes a SUBSET of the clips the perception call encodes again; the host
+ * keys the encoder state per clip with this hash (and confirms candidates bit-for-bit) so no clip is encoded twice. */
+int desta_row_hash(const void* rows, int64_t n_rows, int64_t row_bytes, int64_t row_stride_bytes, uint64_t* out, void* stream);
 /* ---- (4) splice: replaces the gathers + per-audio scatter loop of
  *      DeSTA25AudioModel._prepare_inputs_for_llm (modeling_desta25.py:940-1050; gathers :975-982,1009; loop :1014-1045).
  *      out[b,s,:] = table[input_ids[b,s]] for text rows; rows [start, start+Q) of prompt b <- bf16_rne(audio_feats[i]);
@@ -129,11 +134,13 @@ typedef struct desta_splice_desc {
   int32_t n_trans;     /* T_i */
   int32_t trans_off;   /* offset into trans_ids */
 } desta_splice_desc;
-/* row_map: unused (may be NULL; kept for ABI stability).  feat_dtype: 0 = fp32, 1 = bf16.  Returns DESTA_ERR_SHAPE if a span
- * leaves [0,S) (the reference raises at :1041); descs are validated on the host copy `descs_host`. */
+/* feat_dtype: 0 = fp32, 1 = bf16.  Returns DESTA_ERR_SHAPE if a span leaves [0,S) (the reference raises at :1041); descs are
+ * validated on the host copy `descs_host`.  err_word: optional int64[2] the kernel can write (device memory, or pinned host
+ * memory under UVA): token ids outside [0, vocab) make the reference's embedding lookup raise (:981, :1009); the kernel
+ * reads a clamped row instead (memory safety) and reports it as err_word[0] += offending rows, err_word[1] = one such id. */
 int desta_splice(const int64_t* input_ids, const void* table, int64_t vocab, const desta_splice_desc* descs_dev,
                  const desta_splice_desc* descs_host, int n_desc, const int64_t* trans_ids, const void* audio_feats,
-                 int feat_dtype, int Q, void* out, int B, int S, int d, int32_t* row_map, void* stream);
+                 int feat_dtype, int Q, void* out, int B, int S, int d, int64_t* err_word, void* stream);
 /* Gradient of the splice w.r.t. the audio features: dfeats[i] = grad_out[prompt_i, start_i : start_i + Q] (bf16 -> fp32). */
 int desta_splice_bwd(const void* grad_out, const desta_splice_desc* descs_dev, int n_desc, int Q, int S, int d, float* dfeats,
                      void* stream);

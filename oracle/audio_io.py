@@ -37,11 +37,17 @@ def parse_wav(data):
         tag, size = data[pos:pos + 4], struct.unpack("<I", data[pos + 4:pos + 8])[0]
         body = pos + 8
         if tag == b"fmt ":
+            if len(data) < body + 16:
+                raise ValueError("truncated fmt chunk")
             code, ch, sr, _, align, bits = struct.unpack("<HHIIHH", data[body:body + 16])
             if code == 0xFFFE:
+                if len(data) < body + 26 or size < 26:
+                    raise ValueError("truncated extensible fmt chunk")
                 code = struct.unpack("<H", data[body + 24:body + 26])[0]
             fmt = (code, ch, sr, bits)
         elif tag == b"data":
+            if fmt is None:
+                raise ValueError("data chunk before fmt chunk")
             code, ch, sr, bits = fmt
             kind = {(1, 8): FMT_U8, (1, 16): FMT_S16, (1, 24): FMT_S24, (1, 32): FMT_S32, (3, 32): FMT_F32, (3, 64): FMT_F64}[(code, bits)]
             size = min(size, len(data) - body)

@@ -240,3 +240,72 @@ def test_native_training_schedule_equals_per_op_schedule(train_mode):
     for n in g_ops:
         assert (g_native[n] - g_ops[n]).abs().max().item() <= 1e-5 * gmax, n
     assert len(g_native) == 61
+
+
+def test_saved_activations_survive_other_forwards():
+    """The backward's inputs live in the module's workspaces, not in autograd saved tensors.  A second forward of the same
+    batch size before the backward (two grad-enabled forwards in one loss, an eval call in between) must not corrupt the
+    first one's gradients, and differentiating a retained graph after its buffers were reused must raise, not miscompute."""
+    from oracle.configs import CONFIGS
+    from oracle.synth import synth_waves
+    from oracle import logmel as o_mel
+    from oracle.weights import make_weights
+    cfg = CONFIGS["micro"]
+    W = make_weights(cfg, seed=11, with_table=False)
+    p = build_perception(cfg, W)
+    p.train()
+    p.connector.qformer.config.hidden_dropout_prob = 0.0            # deterministic: compare runs exactly up to fp32 atomics
+    p.connector.qformer.config.attention_probs_dropout_prob = 0.0
+    for prm in p.whisper.parameters():
+        prm.requires_grad_(False)
+    waves = synth_waves(seed=7, kinds=KINDS)
+    pad = lambda ws: torch.from_numpy(np.stack([o_mel.pad_or_truncate(w) for w in ws])).cuda()   # noqa: E731
+    wa, wb = pad(waves[0:2]), pad(waves[2:4])
+    ga = torch.randn(2, cfg.prompt_size, cfg.d_llm, device="cuda")
+    gb = torch.randn(2, cfg.prompt_size, cfg.d_llm, device="cuda")
+    names = [n for n, _ in p.connector.named_parameters()]
+
+    def grads():
+        out = {n: prm.grad.clone() for n, prm in p.connector.named_parameters()}
+        p.connector.zero_grad()
+        return out
+
+    def close(g1, g2):
+        for n in names:
+            scale = g2[n].abs().max().item() + 1e-12
+            assert (g1[n] - g2[n]).abs().max().item() <= 2e-3 * scale + 1e-7, n
+
+    p.connector.zero_grad()
+    fa, _ = p(input_features=wa)
+    (fa * ga).sum().backward()
+    want_a = grads()
+    fb, _ = p(input_features=wb)
+    (fb * gb).sum().backward()
+    want_b = grads()
+    # (1) two grad-enabled forwards, then one backward through both
+    fa, _ = p(input_features=wa)
+    fb, _ = p(input_features=wb)
+    ((fa * ga).sum() + (fb * gb).sum()).backward()
+    close(grads(), {n: want_a[n] + want_b[n] for n in names})
+    # (2) an eval-mode call of the same batch size between forward and backward
+    fa, _ = p(input_features=wa)
+    with torch.no_grad():
+        p(input_features=wb)
+    (fa * ga).sum().backward()
+    close(grads(), want_a)
+    # (3) steady state reuses the same buffers (no reallocation per step)
+    fa, _ = p(input_features=wa)
+    ws1 = next(iter(p._ws.values()))
+    (fa * ga).sum().backward()
+    grads()
+    fa, _ = p(input_features=wa)
+    assert next(iter(p._ws.values())) is ws1
+    # (4) retained graph: a second backward is fine while nothing overwrote the buffers, and raises afterwards
+    loss = (fa * ga).sum()
+    loss.backward(retain_graph=True)
+    close(grads(), want_a)
+    loss.backward(retain_graph=True)
+    close(grads(), want_a)
+    fb, _ = p(input_features=wb)                                    # same size: reuses (and overwrites) the released buffers
+    with pytest.raises(RuntimeError, match="overwritten"):
+        loss.backward()

@@ -72,6 +72,27 @@ def test_flagship_clips_are_independent_and_deterministic(flagship):
     assert not torch.equal(all3[0], all3[1])
 
 
+@pytest.mark.parametrize("n_clips,probe", [(64, (0, 31, 63)), (256, (0, 31, 63, 255))])
+def test_flagship_bench_batch_equals_solo_runs(flagship, n_clips, probe):
+    """Parity AT the benchmark batch sizes (BASELINE configs[1]: 64 clips; configs[2] sweeps to 256): at N = 64 the Q-Former
+    K/V buffer alone is [384000, 15360] bf16 = 5.9e9 elements (> 2^32), at N = 256 four times that - an offset that wraps at
+    32 bits shows up only here.  Clip i inside the batch must equal its solo run bit for bit (clips are independent units),
+    for the first, a middle and the last clip; the solo run itself is pinned against the oracle by
+    test_flagship_full_depth_vs_oracle / test_flagship_oracle_clip_inside_bench_batch."""
+    w = _waves(n_clips, seed=1234)
+    with torch.no_grad():
+        full, lens = flagship(input_features=w)
+        full = full.clone()
+        assert lens == [64] * n_clips and torch.isfinite(full).all()
+        for i in probe:
+            solo, _ = flagship(input_features=w[i:i + 1].contiguous())
+            assert torch.equal(solo[0], full[i]), f"clip {i} of {n_clips} differs from its solo run"
+    # distinct clips give distinct features (a wrapped offset would alias rows)
+    assert not torch.equal(full[0], full[n_clips - 1]) and not torch.equal(full[31], full[63])
+    flagship._ws = {}
+    torch.cuda.empty_cache()
+
+
 def test_flagship_zero_padding_equals_short_clip(flagship):
     from desta_b200 import ops
     w = _waves(2, seed=9)
@@ -132,3 +153,13 @@ def test_flagship_full_depth_vs_oracle():
     rel, cos = _rel(feats, feats_ref), _cos(feats, feats_ref)
     print(f"connector out: rel {rel:.4f} cos {cos:.6f}")
     assert rel <= 2e-2 and cos >= 0.999, f"connector out: rel {rel:.4f} cos {cos:.6f}"
+    # the same clip as member 17 (and last member) of a 64-clip benchmark batch: still the oracle-checked values, bit for bit
+    solo = feats.clone()
+    batch = _waves(64, seed=77)
+    batch[17] = wave[0]
+    batch[63] = wave[0]
+    with torch.no_grad():
+        full, _ = p(input_features=batch)
+    assert torch.equal(full[17], solo[0]) and torch.equal(full[63], solo[0])
+    rel, cos = _rel(full[17:18], feats_ref), _cos(full[17:18], feats_ref)
+    assert rel <= 2e-2 and cos >= 0.999

@@ -1,10 +1,13 @@
 """install() against the REAL reference model class (build container only: skipped where /root/reference is absent)."""
 import os
 
+import numpy as np
 import pytest
 import torch
 
-REF = "/root/reference/desta/models/modeling_desta25.py"
+from oracle import refshim
+
+REF = (refshim.ref_root() or "/nonexistent") + "/desta/models/modeling_desta25.py"
 
 
 @pytest.mark.skipif(not os.path.exists(REF), reason="reference tree not present on this machine")
@@ -58,3 +61,33 @@ def test_install_patch_audio_rebinds_the_name_generate_uses():
         assert callable(mod.AudioSegment.from_file) and hasattr(mod.AudioSegment, "samples")
     finally:
         mod.AudioSegment = original
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="reference tree not present on this machine")
+def test_install_wraps_the_processor_generate_creates_lazily():
+    """The documented order is from_pretrained -> install -> generate, and the reference creates `self.processor` inside
+    generate() (`_setup_generation`, modeling_desta25.py:1467-1482, called at :1514-1515): install() must catch it."""
+    import desta_b200
+    from desta_b200.processor import WaveformProcessor
+    from oracle.configs import CONFIGS
+    cfg = CONFIGS["micro"]
+    ref = refshim.load_reference(cfg)
+    rcfg = ref.DeSTA25Config(llm_model_id="llama-micro", encoder_model_id=cfg.encoder_model_id,
+                             qformer_num_hidden_layers=cfg.qf_layers, prompt_size=cfg.prompt_size)
+    model = ref.DeSTA25AudioModel(rcfg)
+    refshim.offline_generation(model, cfg.n_mels)
+    assert not hasattr(model, "processor") and not hasattr(model, "tokenizer")
+    desta_b200.install(model)
+    desta_b200.install(model)                                  # idempotent: no double wrapping
+    model._setup_generation()                                  # what generate() does on its first call
+    assert isinstance(model.processor, WaveformProcessor) and not isinstance(model.processor._wrapped, WaveformProcessor)
+    feats = model.processor([np.zeros(1600, np.float32), np.ones(500000, np.float32)], sampling_rate=16000,
+                            return_tensors="pt").input_features
+    assert feats.shape == (2, 480000) and feats.dtype == torch.float32 and model.processor._wrapped.calls == 0
+    assert model.processor.batch_decode([[5, 6, 7]], skip_special_tokens=True) == model.processor._wrapped.batch_decode([[5, 6, 7]])
+    # a model that already has a processor (install after the first generate) is wrapped on the spot
+    model2 = ref.DeSTA25AudioModel(rcfg)
+    refshim.offline_generation(model2, cfg.n_mels)
+    model2._setup_generation()
+    desta_b200.install(model2)
+    assert isinstance(model2.processor, WaveformProcessor)

@@ -67,6 +67,28 @@ def test_gemm_epilogues():
     assert torch.equal(tap, buf.to(torch.bfloat16))
 
 
+def test_gemm_gelu_tails():
+    """The fused erf-GELU epilogue on large pre-activations (real Whisper checkpoints have fc1 outliers): GELU(x) -> 0 for
+    x << 0 and -> x for x >> 0.  An identity weight makes the accumulator equal the (bf16-exact) input."""
+    K = 64
+    x = torch.cat([torch.linspace(-60, 60, 128 * K - 8), torch.tensor([-60., -30., -10., -4.25, 4.25, 10., 30., 60.])])
+    a = x.to(torch.bfloat16).view(128, K).cuda()
+    w = torch.eye(K, device="cuda").to(torch.bfloat16)
+    out = torch.empty(128, K, device="cuda")
+    ops.gemm(a, w, None, out_f32=out, gelu=True)
+    xf = a.float()
+    ref = torch.nn.functional.gelu(xf.double()).float()
+    err = (out - ref).abs()
+    assert err.max().item() < 2.5e-4, err.max().item()
+    assert err[xf < -4.3].max().item() < 6e-5                  # the negative tail is ~0, not |x| * 1e-4
+    assert ((out - ref).abs()[xf > 4.3] / ref[xf > 4.3]).max().item() < 1e-5
+    # the 1-CTA GEMM (M <= 128 path is the one above); the 2-CTA kernel through a taller problem
+    a2 = a.repeat(4, 1).contiguous()
+    out2 = torch.empty(512, K, device="cuda")
+    ops.gemm(a2, w, None, out_f32=out2, gelu=True)
+    assert torch.equal(out2[:128], out2[128:256]) and (out2[:128] - ref).abs().max().item() < 2.5e-4
+
+
 def test_gemm_strided_output():
     M, N, K = 300, 256, 128
     a = torch.randn(M, K, device="cuda").to(torch.bfloat16)
@@ -234,6 +256,28 @@ def test_splice_errors_and_empty():
         ops.splice(ids, table, [(0, 30, 0, 0)], None, feats, 64)
 
 
+def test_splice_reports_token_ids_outside_the_table():
+    """embed_tokens(ids) raises in the reference for ids outside [0, V) (modeling_desta25.py:981, :1009).  The kernel stays
+    memory-safe and reports through the error word: IndexError at the next call on the device, or at once with sync."""
+    table = torch.randn(100, 64).to(torch.bfloat16).cuda()
+    ids = torch.randint(0, 100, (2, 80)).cuda()
+    ops.check_token_ids(sync=True)
+    bad = ids.clone()
+    bad[1, 7] = 100
+    bad[0, 3] = -5
+    ops.splice(bad, table, [], None, None, 64)
+    with pytest.raises(IndexError, match="2 row"):
+        ops.check_token_ids(sync=True)
+    ops.check_token_ids(sync=True)                                    # the report is consumed
+    feats = torch.randn(1, 64, 64).cuda()
+    ops.splice(ids, table, [(0, 2, 3, 0)], torch.tensor([1, 2, 4096]).cuda(), feats, 64)     # transcript id out of range
+    torch.cuda.synchronize()
+    with pytest.raises(IndexError, match="4096"):
+        ops.splice(ids, table, [], None, None, 64)                    # surfaces at the next splice on this device
+    out = ops.splice(ids, table, [], None, None, 64)
+    assert torch.equal(out, table[ids])
+
+
 @pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
 def test_one_process_two_devices():
     """The library keeps no cross-device state (kernel attributes are set per device): the same process can run the
@@ -253,6 +297,22 @@ def test_one_process_two_devices():
             outs.append((out.cpu(), o.float().cpu()))
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][0], outs[2][0])
     assert torch.equal(outs[0][1], outs[1][1])
+    # tensors on a device that is NOT the current one (model.to("cuda:1") without set_device): every op makes the tensors'
+    # device current for its launch and uses that device's stream
+    torch.cuda.set_device(0)
+    g = torch.Generator(device="cuda:1").manual_seed(3)
+    a = torch.randn(512, 256, device="cuda:1", generator=g).to(torch.bfloat16)
+    w = torch.randn(384, 256, device="cuda:1", generator=g).to(torch.bfloat16)
+    out = torch.empty(512, 384, device="cuda:1")
+    ops.gemm(a, w, None, out_f32=out)
+    q = torch.randn(2 * 200, 3 * 128, device="cuda:1", generator=g).to(torch.bfloat16)
+    o = torch.empty(2 * 200, 128, device="cuda:1", dtype=torch.bfloat16)
+    ops.attention(q[:, :128], q[:, 128:256], q[:, 256:], o, 2, 2, 200, 200, 0.125)
+    torch.cuda.synchronize(1)
+    assert torch.cuda.current_device() == 0
+    assert torch.equal(out.cpu(), outs[1][0]) and torch.equal(o.float().cpu(), outs[1][1])
+    with pytest.raises(ValueError, match="different devices"):
+        ops.gemm(a, w.to("cuda:0"), None, out_f32=out)
 
 
 def _guarded(rows, cols, dtype, ld=None, guard_rows=64, fill=7.0):

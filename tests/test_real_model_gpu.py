@@ -1,0 +1,190 @@
+"""The drop-in on the REAL reference class, on the GPU: the unmodified `DeSTA25AudioModel` (from /root/reference in the
+build container, from baseline/_ref on the GPU box; oracle/refshim.py supplies hub-free configs, tokenizer, processor and
+VAD stand-ins) is run through its own public entry points before and after `desta_b200.install(model)`:
+
+  * `model.forward(**batch).loss` and `model._prepare_inputs_for_llm(...)`       (modeling_desta25.py:758-767, :933, :940-1050)
+  * `model.generate(messages)` end to end                                          (:1491-1721, `_generate_step` :1358-1419)
+
+Before = the reference's stock PyTorch path on the same GPU (fp32 Whisper + Q-Former, CPU WhisperFeatureExtractor).
+Tolerances (north_star): text / transcript rows of inputs_embeds bit-exact; audio rows max|delta|/max|ref| <= 2e-2 and
+cosine >= 0.999.  The loss has no stated tolerance: we hold it to 1e-2 relative (it is a mean over ~100 positions whose
+inputs differ by <= 2e-2 relative).
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import refshim  # noqa: E402
+from oracle.configs import CONFIGS  # noqa: E402
+from oracle.synth import synth_waves  # noqa: E402
+from oracle.weights import make_weights  # noqa: E402
+
+needs_ref = pytest.mark.skipif(refshim.ref_root() is None, reason="reference neither at /root/reference nor in baseline/_ref")
+CFG = CONFIGS["micro"]
+
+
+def _bits(t):
+    return t.contiguous().view(torch.int16).cpu().numpy().view(np.uint16)
+
+
+def _build_real_model():
+    ref = refshim.load_reference(CFG, max_target_positions=160)
+    rcfg = ref.DeSTA25Config(llm_model_id="llama-micro", encoder_model_id=CFG.encoder_model_id,
+                             qformer_num_hidden_layers=CFG.qf_layers, prompt_size=CFG.prompt_size)
+    torch.manual_seed(0)
+    model = ref.DeSTA25AudioModel(rcfg)
+    W = make_weights(CFG, seed=11)
+    params = dict(model.named_parameters())
+    with torch.no_grad():
+        for k, v in W.items():
+            params[k].copy_(v.to(params[k].dtype))
+    return ref, model.cuda().eval()
+
+
+def _audio_rows_close(emb, emb_ref, positions, Q):
+    for (b, s) in positions:
+        a, r = emb[b, s:s + Q].float(), emb_ref[b, s:s + Q].float()
+        rel = ((a - r).abs().max() / r.abs().max()).item()
+        cos = (torch.dot(a.flatten(), r.flatten()) / (a.norm() * r.norm())).item()
+        assert rel <= 2e-2 and cos >= 0.999, f"audio rows of clip at {(b, s)}: rel {rel:.4f} cos {cos:.6f}"
+
+
+@needs_ref
+def test_forward_and_prepare_inputs_before_vs_after_install():
+    import desta_b200
+    from desta_b200 import ops
+    from desta_b200.perception import WhisperPerceptionB200
+    from transformers import WhisperFeatureExtractor
+    ref, model = _build_real_model()
+    assert type(model).__module__ == "desta.models.modeling_desta25"
+    Q = CFG.prompt_size
+    waves = synth_waves(seed=7, kinds=("noise_full", "speechy_12s", "short_3p5s"))
+    mel = WhisperFeatureExtractor(feature_size=CFG.n_mels)(waves, sampling_rate=16000, return_tensors="pt").input_features
+    g = torch.Generator().manual_seed(3)
+    B, S = 2, 200
+    input_ids = torch.randint(0, CFG.vocab, (B, S), generator=g).cuda()
+    attn = torch.ones(B, S, dtype=torch.long).cuda()
+    trans = [torch.randint(0, CFG.vocab, (1, t), generator=g).cuda() for t in (5, 0, 2)]
+    positions = [(0, 4), (1, 7), (1, 7 + Q + 3)]
+    labels = input_ids.clone()
+    labels[:, :150] = -100
+    batch = dict(input_ids=input_ids, attention_mask=attn, batch_features=mel.cuda(), batch_transcription_ids=trans,
+                 batch_start_positions=positions, labels=labels)
+
+    with torch.no_grad():
+        emb_ref = model._prepare_inputs_for_llm(input_ids, attn, mel.cuda(), trans, positions)
+        loss_ref = model(**batch).loss.float().item()
+    keys_before = sorted(model.state_dict().keys())
+
+    desta_b200.install(model)
+    assert isinstance(model.perception, WhisperPerceptionB200) and sorted(model.state_dict().keys()) == keys_before
+
+    # (a) the reference's own input: CPU log-mel [N, n_mels, 3000]
+    l0 = ops.STATS["launches"]
+    with torch.no_grad():
+        emb = model._prepare_inputs_for_llm(input_ids, attn, mel.cuda(), trans, positions)
+        loss = model(**batch).loss.float().item()
+    assert ops.STATS["launches"] > l0, "the installed path did not launch any libdesta_b200 kernel"
+    assert emb.dtype == emb_ref.dtype == torch.bfloat16 and emb.shape == emb_ref.shape
+    audio = torch.zeros(B, S, dtype=torch.bool)
+    for (b, s) in positions:
+        audio[b, s:s + Q] = True
+    assert np.array_equal(_bits(emb)[~audio.numpy()], _bits(emb_ref)[~audio.numpy()]), "text / transcript rows must be bit-exact"
+    _audio_rows_close(emb, emb_ref, positions, Q)
+    assert abs(loss - loss_ref) <= 1e-2 * abs(loss_ref), (loss, loss_ref)
+
+    # (b) the processor shim's input: padded waveforms, log-mel on the device
+    from desta_b200.processor import WaveformProcessor
+    feats = WaveformProcessor()(waves, sampling_rate=16000, return_tensors="pt").input_features
+    assert feats.shape == (3, 480000)
+    prof0 = ops.STATS.get("logmel_calls", 0)
+    with torch.no_grad():
+        emb_w = model._prepare_inputs_for_llm(input_ids, attn, feats.cuda(), trans, positions)
+        loss_w = model(**dict(batch, batch_features=feats.cuda())).loss.float().item()
+    assert ops.STATS.get("logmel_calls", 0) == prof0 + 2, "logmel_fft_kernel must run once per perception call"
+    assert np.array_equal(_bits(emb_w)[~audio.numpy()], _bits(emb_ref)[~audio.numpy()])
+    _audio_rows_close(emb_w, emb_ref, positions, Q)
+    assert abs(loss_w - loss_ref) <= 1e-2 * abs(loss_ref), (loss_w, loss_ref)
+
+    # training mode: the loss back-propagates into the connector parameters through the installed path
+    model.train()
+    model.zero_grad()
+    out = model(**dict(batch, batch_features=feats.cuda()))
+    out.loss.backward()
+    grads = [p.grad for n, p in model.named_parameters() if n.startswith("perception.connector.") and p.requires_grad]
+    assert grads and all(gr is not None and torch.isfinite(gr).all() for gr in grads)
+    assert any(gr.abs().max().item() > 0 for gr in grads)
+
+
+@needs_ref
+def test_generate_through_install_runs_the_device_logmel(tmp_path):
+    """INTEGRATION.md §1 literally: build the model, `install(model)` BEFORE the first `generate()` (the reference creates
+    tokenizer and processor lazily inside it, modeling_desta25.py:1514-1515 -> :1467-1482), then `generate(messages)`."""
+    import desta_b200
+    import wavutil as W
+    from desta_b200 import ops
+    from desta_b200.processor import WaveformProcessor
+    ref, model = _build_real_model()
+    refshim.offline_generation(model, CFG.n_mels)
+    waves = synth_waves(seed=7, kinds=("speechy_12s", "short_3p5s", "silence", "tone_clip"))
+    paths = []
+    for i, w in enumerate(waves):
+        p = tmp_path / f"clip{i}.wav"
+        p.write_bytes(W.wav_bytes(np.asarray(w, np.float64).reshape(-1, 1), 16000, W.S16))
+        paths.append(str(p))
+    # two conversations; clip 0 is speech without transcript (-> ASR pass on a SUBSET of the batch), clip 1 has a transcript,
+    # clip 2 is silence (VAD: no speech -> " "), clip 3 is speech with a transcript
+    convs = [
+        [{"role": "system", "content": "focus on the audio clips and instructions"},
+         {"role": "user", "content": "hello this is my audio <|AUDIO|> and <|AUDIO|> help me transcribe",
+          "audios": [{"audio": paths[0], "text": None}, {"audio": paths[1], "text": "a dog bark"}]}],
+        [{"role": "user", "content": "what is the sound <|AUDIO|> <|AUDIO|>",
+          "audios": [{"audio": paths[2], "text": None}, {"audio": paths[3], "text": "w1 w2 w3 w4 w5"}]}],
+    ]
+    captured = {}
+    llm_generate = model.llm_model.generate
+
+    def spy(**kw):
+        captured["emb"] = kw["inputs_embeds"].detach().clone()
+        captured["mask"] = kw["attention_mask"].detach().clone()
+        return llm_generate(**kw)
+
+    model.llm_model.generate = spy
+    with torch.no_grad():
+        out_ref = model.generate(convs, do_sample=False, max_new_tokens=4)
+    emb_ref, mask_ref = captured["emb"], captured["mask"]
+    assert not isinstance(model.processor, WaveformProcessor) and model.processor.calls >= 1
+
+    # a fresh model (no tokenizer / processor yet), installed first - the documented order
+    ref, model = _build_real_model()
+    refshim.offline_generation(model, CFG.n_mels)
+    assert not hasattr(model, "processor")
+    desta_b200.install(model)
+    llm_generate2 = model.llm_model.generate
+
+    def spy2(**kw):
+        captured["emb2"] = kw["inputs_embeds"].detach().clone()
+        captured["mask2"] = kw["attention_mask"].detach().clone()
+        return llm_generate2(**kw)
+
+    model.llm_model.generate = spy2
+    mel0, enc0 = ops.STATS.get("logmel_calls", 0), ops.STATS.get("encoder_clips", 0)
+    with torch.no_grad():
+        out = model.generate(convs, do_sample=False, max_new_tokens=4)
+    assert isinstance(model.processor, WaveformProcessor), "generate() created its processor lazily and it was not wrapped"
+    assert model.processor._wrapped.calls == 0, "the CPU WhisperFeatureExtractor still ran on the generate() path"
+    assert ops.STATS.get("logmel_calls", 0) > mel0, "logmel_fft_kernel never launched through processor -> perception"
+    # ASR pass on clip 0 only + perception on all 4 clips: with per-clip reuse the encoder sees 4 clips, not 5
+    assert ops.STATS.get("encoder_clips", 0) - enc0 == 4, ops.STATS.get("encoder_clips", 0) - enc0
+    assert [a for a, _ in out.audios] == [a for a, _ in out_ref.audios]
+    assert [t for _, t in out.audios][1:] == [t for _, t in out_ref.audios][1:]      # given / VAD transcripts are identical
+    if [t for _, t in out.audios] == [t for _, t in out_ref.audios]:                  # same ASR text -> same prompt layout
+        emb, mask = captured["emb2"], captured["mask2"]
+        assert torch.equal(mask, mask_ref) and emb.shape == emb_ref.shape
+        d = (emb.float() - emb_ref.float()).abs().max().item() / emb_ref.float().abs().max().item()
+        assert d <= 2e-2, d
+        exact = (_bits(emb) == _bits(emb_ref)).all(axis=-1)
+        assert exact.sum() >= emb.shape[0] * emb.shape[1] - 4 * CFG.prompt_size     # everything but the audio rows is bit-exact
+    assert len(out.text) == len(out_ref.text) == 2

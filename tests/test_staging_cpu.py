@@ -74,3 +74,19 @@ def test_pcm_stager_host_side_without_cuda(tmp_path):
     bad.write_bytes(b"RIFFxxxxWAVE")
     with pytest.raises(Exception, match="could not be decoded"):
         st.fill(1, [str(bad)])
+
+
+def test_device_wave_is_only_trusted_by_identity():
+    """The device copy rides on the exact object AudioSegment.samples returns; anything derived from it is plain host data
+    again (the processor then uploads the edited samples instead of silently reusing the stale device tensor)."""
+    from desta_b200.audio import DeviceWave
+    from desta_b200.processor import _device_batch
+    marker = object()
+    w = DeviceWave(np.linspace(-1, 1, 1000, dtype=np.float32), marker)
+    assert w.device_tensor is marker
+    for derived in (w * 0.5, w[::-1], np.clip(w, -0.1, 0.1), w[:500], w.copy(), w + 0, np.asarray(w) * 1.0, -w):
+        assert getattr(derived, "device_tensor", None) is None
+        assert _device_batch([derived]) is None
+    with np.testing.assert_raises(ValueError):
+        w *= 0.5                                                     # the carrier is read-only: no silent drift
+    assert w.tolist()[0] == -1.0 and w.device_tensor is marker
