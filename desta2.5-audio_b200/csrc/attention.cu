@@ -19,6 +19,19 @@
 //              against the running max of the previous blocks while the block max is gathered in the same pass; only
 //              when a row's max grows by more than 2^20 is the reference raised (O and l rescaled in TMEM) and the block
 //              redone from the scores still held in registers.  Final 1/l and 128-byte row stores.
+//
+// UNIT mode (scale * log2(e) == 1: the Whisper encoder, whose q is pre-scaled by the QKV GEMM epilogue - the log2(e) factor
+// is folded into that scale): the softmax shift is folded into the tensor-core product.  tools/issue_bench.cu shows that the
+// softmax loop is not bound by the MUFU pipe alone (8 cycles per warp instruction) but by the scale-subtract / max / row-sum
+// instructions around it, whose dependent issue leaves the XU idle a quarter of the time (2 warps per sub-partition: 73 %
+// XU utilisation with today's instruction mix, 92 % with exp + pack + row-sum only).  So S' = Q K^T - m 1^T is computed BY
+// THE MMA: a fifth K = 16 step multiplies a [128 x 16] operand holding -m_row (bf16) in its first column with a [64 x 16]
+// operand of ones (both un-swizzled K-major tiles in shared memory), and the softmax threads take p = ex2(S') straight from
+// the TMEM registers - no FFMA, no running max (a row sum above 2^20 triggers the same lazy rescale).  The shift is a
+// per-row constant, so its bf16 rounding cancels exactly in the softmax; it only changes at the first block and at
+// rescale events, and every thread remembers which shift each in-flight S block was computed with.
+#include <math.h>
+
 #include "common.cuh"
 #include "desta_b200.h"
 
@@ -27,7 +40,9 @@ namespace desta {
 constexpr int AT_BQ = 128, AT_BKV = 64, AT_HD = 64, AT_STAGES = 5, AT_SBUF = 3;
 constexpr int AT_Q_BYTES = AT_BQ * AT_HD * 2;      // 16 KB
 constexpr int AT_KV_BYTES = AT_BKV * AT_HD * 2;    // 8 KB (K) + 8 KB (V) per stage
-constexpr int AT_SMEM = AT_Q_BYTES + AT_STAGES * 2 * AT_KV_BYTES + 256;   // 98,560 B -> 2 CTAs / SM
+constexpr int AT_AX_BYTES = AT_BQ * 32;            // shift operand  [128 rows x 16 bf16], un-swizzled K-major (UNIT mode)
+constexpr int AT_BX_BYTES = AT_BKV * 32;           // ones operand   [64 keys x 16 bf16]
+constexpr int AT_SMEM = AT_Q_BYTES + AT_STAGES * 2 * AT_KV_BYTES + AT_AX_BYTES + AT_BX_BYTES + 256;   // 104,704 B -> 2 CTAs / SM
 constexpr int AT_THREADS = 192;
 constexpr int AT_TMEM_COLS = 256;                  // S/P buffers: [0,64) [64,128) [128,192)   O: [192,256)
 constexpr int AT_TMEM_O = AT_SBUF * AT_BKV;
@@ -52,17 +67,36 @@ __device__ __forceinline__ void reg_fence32(uint32_t (&v)[32]) {
 
 struct SoftmaxAcc { float l0, l1, m0, m1; };
 
+
+
 #ifdef DESTA_ATTN_TRACE
 // Debug build only (tools/attn_trace.py): per-CTA cycle accounting of the MMA warp and of softmax warp 2.
 __device__ long long g_attn_trace[8];
 #define TRACE_T0() const long long _t0 = clock64()
 #define TRACE_ADD(slot) do { trace_acc[slot] += clock64() - _t0; } while (0)
 #define TRACE_FLUSH() do { if (lane == 0) for (int _i = 0; _i < 8; ++_i) if (trace_acc[_i]) atomicAdd((unsigned long long*)&g_attn_trace[_i], (unsigned long long)trace_acc[_i]); } while (0)
+// timeline of ONE CTA (blockIdx 5,7,30): [event][block] clock64 stamps.  events: 0 MMA saw p_ready[j], 1 PV_j issued,
+// 2 QK_{j+3} issued (slot j+3), 3..6 softmax warps 2..5 step j start, 7..10 warps 2..5 got s_full[j+1], 11 warp 2 step end
+__device__ long long g_attn_tl[12][32];
+#define TL(ev, j) do { if (tl_on && lane == 0 && (j) < 32) g_attn_tl[ev][j] = clock64(); } while (0)
 #else
+#define TL(ev, j)
 #define TRACE_T0()
 #define TRACE_ADD(slot)
 #define TRACE_FLUSH()
 #endif
+
+// UNIT-mode hot path: the scores arrive shifted (S' = s - m, log2 domain) -> p = ex2(S'), bf16 pack, row sum.  Nothing else.
+__device__ __forceinline__ void softmax_chunk_unit(const uint32_t (&v)[32], uint32_t (&pk)[16], uint64_t& lacc) {
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) {
+    const float p0 = fast_exp2(__uint_as_float(v[i])), p1 = fast_exp2(__uint_as_float(v[i + 1]));
+    const float p2 = fast_exp2(__uint_as_float(v[i + 2])), p3 = fast_exp2(__uint_as_float(v[i + 3]));
+    lacc = fadd2(lacc, fadd2(pack_f32x2(p0, p1), pack_f32x2(p2, p3)));
+    pk[i >> 1] = pack_bf16(p0, p1);
+    pk[(i >> 1) + 1] = pack_bf16(p2, p3);
+  }
+}
 
 // 32 score columns (one TMEM chunk held in registers) of one query row: p = exp2(c*s - mc) packed as bf16 pairs into
 // pk; running row sum / row max accumulated in `acc`.  MASKED (ragged last key block only) selects -inf for padded keys
@@ -137,15 +171,21 @@ __device__ __forceinline__ void softmax_block(const uint32_t (&va)[32], const ui
   m_blk = fmaxf(acc.m0, acc.m1);
 }
 
-template <bool DROP>
+// bf16 round-to-nearest-even of a float, returned as float (the shift operand holds bf16 values)
+__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+template <bool DROP, bool UNIT>
 __global__ void __launch_bounds__(AT_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnArgs a) {
+  static_assert(!(DROP && UNIT), "the dropout variant keeps the general path");
   extern __shared__ __align__(1024) uint8_t smem[];   // SWIZZLE_128B tiles need 1024-byte alignment
   if (smem_u32(smem) & 1023) __trap();
   uint8_t* sQ = smem;
   uint8_t* sKV = sQ + AT_Q_BYTES;                       // stage s: K at s*16K, V at s*16K + 8K
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + AT_STAGES * 2 * AT_KV_BYTES);
+  uint8_t* sAx = sKV + AT_STAGES * 2 * AT_KV_BYTES;     // UNIT: [128 x 16] bf16, column 0 = -shift of the row, rest 0
+  uint8_t* sBx = sAx + AT_AX_BYTES;                     // UNIT: [64 x 16] bf16, column 0 = 1, rest 0
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sBx + AT_BX_BYTES);
   uint64_t* q_full = bars;                              // 1
   uint64_t* kv_full = bars + 1;                         // [AT_STAGES]
   uint64_t* kv_empty = kv_full + AT_STAGES;             // [AT_STAGES]
@@ -160,12 +200,26 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   long long trace_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #endif
   const int n_kv = (a.Tk + AT_BKV - 1) / AT_BKV;
+#ifdef DESTA_ATTN_TRACE
+  const bool tl_on = blockIdx.x == 5 && blockIdx.y == 7 && blockIdx.z == 30;
+#endif
 
   if (a.kv_rows < AT_BKV || a.q_rows < AT_BQ) {
     // short sequences: rows the TMA boxes never write must read as zeros (keys: P = 0 there; queries: finite scores, so
     // that the unused rows of a 64-query Q-Former tile can never send their warps down the rescale path)
     uint4* z = reinterpret_cast<uint4*>(smem);
     for (int i = threadIdx.x; i < (AT_Q_BYTES + AT_STAGES * 2 * AT_KV_BYTES) / 16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async_smem();
+  }
+  if (UNIT) {
+    // un-swizzled K-major operand tiles ("interleaved" canonical layout): core matrix = 8 rows x 16 B stored contiguously,
+    // 8-row groups SBO = 128 B apart, the two 16-byte K chunks LBO = rows*16 B apart.  Shift operand: all zero for now
+    // (blocks 0..2 are issued before any row max is known); ones operand: element [key][0] = 1.
+    uint4* z = reinterpret_cast<uint4*>(sAx);
+    for (int i = threadIdx.x; i < (AT_AX_BYTES + AT_BX_BYTES) / 16; i += blockDim.x) {
+      const bool ones_chunk0 = i >= AT_AX_BYTES / 16 && i < AT_AX_BYTES / 16 + AT_BKV;      // K chunk 0 of the ones tile
+      z[i] = make_uint4(ones_chunk0 ? 0x00003F80u : 0u, 0, 0, 0);
+    }
     fence_proxy_async_smem();
   }
   if (warp == 0 && lane == 0) {
@@ -206,7 +260,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     constexpr uint32_t idesc_qk = umma_idesc_bf16(AT_BQ, AT_BKV, 0, 0);
     constexpr uint32_t idesc_pv = umma_idesc_bf16(AT_BQ, AT_HD, 0, 1);   // B (= V) is MN-major
     const uint64_t qdesc = umma_desc_sw128(smem_u32(sQ), 16, 1024);
-    // S_j = Q K_j^T into buffer j % 3; issued three blocks ahead of the P V product of the same buffer
+    const uint64_t axdesc = umma_desc_nosw(smem_u32(sAx), AT_BQ * 16, 128);
+    const uint64_t bxdesc = umma_desc_nosw(smem_u32(sBx), AT_BKV * 16, 128);
+    // S_j = Q K_j^T (- shift 1^T in UNIT mode) into buffer j % 3; issued three blocks ahead of the P V product of the buffer
     auto issue_qk = [&](int j) {
       const int st = j % AT_STAGES;
       { TRACE_T0(); mbar_wait_sleep(&kv_full[st], (j / AT_STAGES) & 1); TRACE_ADD(0); }
@@ -216,6 +272,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
         for (int k = 0; k < AT_HD / 16; ++k)
           umma_bf16_ss(tmem_base + (j % AT_SBUF) * AT_BKV, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, k != 0);
+        if (UNIT) umma_bf16_ss(tmem_base + (j % AT_SBUF) * AT_BKV, axdesc, bxdesc, idesc_qk, 1);
         umma_commit(&s_full[j % AT_SBUF]);
       }
       __syncwarp();
@@ -226,6 +283,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     for (int j = 0; j < n_kv; ++j) {
       const int st = j % AT_STAGES, b = j % AT_SBUF;
       { TRACE_T0(); mbar_wait_sleep(&p_ready[b], (j / AT_SBUF) & 1); TRACE_ADD(1); }     // P_j in TMEM (over S_j), O rescaled if needed
+      TL(0, j);
       tcgen05_fence_after();
       // V stage: 64 key rows x 128 B (64 head-dim values) -> MN-major B operand, 8-row groups 1024 B apart
       const uint64_t vdesc = umma_desc_sw128(smem_u32(sKV + st * 2 * AT_KV_BYTES + AT_KV_BYTES), 1024, 1024);
@@ -238,7 +296,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         umma_commit(&pv_done[b]);
       }
       __syncwarp();
-      if (j + AT_SBUF < n_kv) issue_qk(j + AT_SBUF);   // in-order tensor pipe: overwrites buffer b after P_j V_j
+      TL(1, j);
+      if (j + AT_SBUF < n_kv) { issue_qk(j + AT_SBUF); TL(2, j + AT_SBUF); }   // in-order tensor pipe: overwrites buffer b after P_j V_j
     }
     TRACE_ADD(3);
   } else {
@@ -246,25 +305,90 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;                 // row inside the tile
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-    const float c = a.scale_log2;
-    float m_run = -INFINITY, l_run = 0.f;
+    const float c = UNIT ? 1.0f : a.scale_log2;
+    // everything below lives in the log2 domain: m_ref = reference exponent of the row (P, l, O are relative to 2^m_ref)
+    float m_ref = -INFINITY, l_run = 0.f;
+    // UNIT: shift folded into S by the MMA.  sh_cur = shift this thread last wrote to the operand tile; bk0..2 = the shift
+    // block j % 3 was (or will be) computed with - a QK^T issued after this thread's arrival on p_ready[j-3] sees the
+    // operand as it was then.
+    float sh_cur = 0.f, bk0 = 0.f, bk1 = 0.f, bk2 = 0.f;
+    __nv_bfloat16* ax_elem = reinterpret_cast<__nv_bfloat16*>(sAx + (r >> 3) * 128 + (r & 7) * 16);
     // dropout group index of key 0 for this thread's row: row = (batch*heads + head)*Tq + query
     const uint64_t grp_row = DROP ? (((uint64_t)batch * gridDim.y + head) * a.Tq + (q0 + r)) * (uint64_t)((a.Tk + 7) >> 3) : 0;
+    // New shift for the row: only legal while no S block that reads the operand is in flight, i.e. once S_{j+1} and S_{j+2}
+    // (issued earlier, with the old shift) have landed; S_{j+3} is issued after this thread's next p_ready arrival.
+    auto set_shift = [&](int j, float sh) {
+      if (j + 1 < n_kv) mbar_wait(&s_full[(j + 1) % AT_SBUF], ((j + 1) / AT_SBUF) & 1);
+      if (j + 2 < n_kv) mbar_wait(&s_full[(j + 2) % AT_SBUF], ((j + 2) / AT_SBUF) & 1);
+      *ax_elem = __float2bfloat16_rn(-sh);
+      fence_proxy_async_smem();
+      sh_cur = sh;
+    };
     // Software pipeline over 32-column chunks with three register sets: while the exponentials of one chunk occupy the
     // MUFU pipe, the tcgen05.ld of the next chunk (the second half of this block, then the first half of the NEXT block,
     // which the three S buffers make available early) is already in flight, and the tcgen05.st of the previous block's P
     // is only waited for - and announced to the MMA warp - one chunk later.  `ca` = this block's keys [0,32) (already
     // requested), `cb` = keys [32,64), `na` = the next block's keys [0,32).
+
+    // announce P_{j-1} (its stores were issued 32 exponentials ago); S_{j+2} will be computed with the current shift
+    auto announce_prev = [&](int j) {
+      tmem_wait_st();
+      tcgen05_fence_before();
+      mbar_arrive(&p_ready[(j - 1) % AT_SBUF]);
+      if (UNIT) {
+        const int pb = (j - 1) % AT_SBUF;
+        bk0 = pb == 0 ? sh_cur : bk0; bk1 = pb == 1 ? sh_cur : bk1; bk2 = pb == 2 ? sh_cur : bk2;
+      }
+    };
+    auto request_next = [&](int j, uint32_t (&na)[32]) {
+      if (j + 1 < n_kv) {
+        { TRACE_T0(); mbar_wait(&s_full[(j + 1) % AT_SBUF], ((j + 1) / AT_SBUF) & 1); if (warp == 2) TRACE_ADD(2); if (warp == 4) TRACE_ADD(5); if (warp == 5) TRACE_ADD(6); if (warp == 3) TRACE_ADD(7); }
+        TL(5 + warp, j + 1);
+        tcgen05_fence_after();
+        tmem_ld_32x32(tmem_base + ((j + 1) % AT_SBUF) * AT_BKV + lane_off, na);
+      }
+    };
+    // rare: raise the reference to m_blk, rescale O and l, redo the block's exponentials from the registers
+    auto rescale = [&](int j, uint32_t (&ca)[32], uint32_t (&cb)[32], uint32_t tS, float baked, int kv_valid, uint64_t grp0,
+                       float m_blk, float& l_blk, bool from_fast_loop) {
+      float m_new = fmaxf(m_ref, m_blk);
+      if (UNIT) m_new = bf16_round(m_new);
+      if (j > 0) {
+        mbar_wait(&pv_done[(j - 1) % AT_SBUF], ((j - 1) / AT_SBUF) & 1);   // P_{j-1} V_{j-1} must have landed in O
+        tcgen05_fence_after();
+        const float f = exp2f(m_ref - m_new);
+        l_run *= f;
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch) {
+          uint32_t o[16];
+          tmem_ld_32x16(tmem_O + lane_off + ch * 16, o);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+          tmem_st_32x16(tmem_O + lane_off + ch * 16, o);
+        }
+      }
+      m_ref = m_new;
+      float m_unused;
+      softmax_block<true, DROP>(ca, cb, tS, c, m_ref - baked, kv_valid, l_blk, m_unused, a.drop, grp0);
+      if (UNIT && m_ref != sh_cur) {
+        if (from_fast_loop) bk0 = bk1 = bk2 = sh_cur;   // the fast loop does not track the slots: S_{j+1}, S_{j+2} carry the old shift
+        set_shift(j, m_ref);
+      }
+    };
+    // general step: any block (first block, ragged last block, dropout, blocks whose S carries a stale shift)
     auto step = [&](int j, uint32_t (&ca)[32], uint32_t (&cb)[32], uint32_t (&na)[32]) {
       const int b = j % AT_SBUF;
       const uint64_t grp0 = grp_row + (uint64_t)(j * (AT_BKV / 8));
       const uint32_t tS = tmem_base + b * AT_BKV + lane_off;
       const int kv_valid = a.Tk - j * AT_BKV;
+      const float baked = UNIT ? (b == 0 ? bk0 : (b == 1 ? bk1 : bk2)) : 0.f;
+      TL(1 + warp, j);
       tmem_wait_ld();                                   // ca
       reg_fence32(ca);
       tmem_ld_32x32(tS + 32, cb);
       if (j == 0) {
-        // first block: no reference max yet -> its own row max
+        // first block: no reference yet -> its own row max
         tmem_wait_ld();
         reg_fence32(cb);
         float m0 = -INFINITY;
@@ -273,65 +397,108 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           m0 = max3(m0, (i < kv_valid) ? __uint_as_float(ca[i]) : -INFINITY, (i + 1 < kv_valid) ? __uint_as_float(ca[i + 1]) : -INFINITY);
           m0 = max3(m0, (32 + i < kv_valid) ? __uint_as_float(cb[i]) : -INFINITY, (33 + i < kv_valid) ? __uint_as_float(cb[i + 1]) : -INFINITY);
         }
-        m_run = m0;
+        m_ref = UNIT ? bf16_round(m0) : m0 * c;
       }
-      // exp pass against the running max of the PREVIOUS blocks; the block max comes out of the same pass
-      const float mc = m_run * c;
+      // exp pass against the reference of the PREVIOUS blocks; the block max comes out of the same pass
+      const float off = m_ref - baked;                  // p = exp2(c * S - off)
       SoftmaxAcc acc = {0.f, 0.f, -INFINITY, -INFINITY};
       uint32_t pk[16];
-      if (kv_valid >= AT_BKV) softmax_chunk<false, DROP>(ca, 0, pk, c, mc, kv_valid, acc, a.drop, grp0);
-      else softmax_chunk<true, DROP>(ca, 0, pk, c, mc, kv_valid, acc, a.drop, grp0);
-      if (j > 0) {                                      // P_{j-1} has landed in TMEM: its stores were issued 32 exponentials ago
-        tmem_wait_st();
-        tcgen05_fence_before();
-        mbar_arrive(&p_ready[(j - 1) % AT_SBUF]);
-      }
+      if (kv_valid >= AT_BKV) softmax_chunk<false, DROP>(ca, 0, pk, c, off, kv_valid, acc, a.drop, grp0);
+      else softmax_chunk<true, DROP>(ca, 0, pk, c, off, kv_valid, acc, a.drop, grp0);
+      if (j > 0) announce_prev(j);
       tmem_st_32x16(tS, pk);                            // P keys [0,32) in place over S columns [0,16)
       tmem_wait_ld();                                   // cb
       reg_fence32(cb);
-      if (j + 1 < n_kv) {
-        { TRACE_T0(); mbar_wait(&s_full[(j + 1) % AT_SBUF], ((j + 1) / AT_SBUF) & 1); if (warp == 2) TRACE_ADD(2); if (warp == 4) TRACE_ADD(5); if (warp == 5) TRACE_ADD(6); if (warp == 3) TRACE_ADD(7); }
-        tcgen05_fence_after();
-        tmem_ld_32x32(tmem_base + ((j + 1) % AT_SBUF) * AT_BKV + lane_off, na);
-      }
-      if (kv_valid >= AT_BKV) softmax_chunk<false, DROP>(cb, 1, pk, c, mc, kv_valid, acc, a.drop, grp0);
-      else softmax_chunk<true, DROP>(cb, 1, pk, c, mc, kv_valid, acc, a.drop, grp0);
+      request_next(j, na);
+      if (kv_valid >= AT_BKV) softmax_chunk<false, DROP>(cb, 1, pk, c, off, kv_valid, acc, a.drop, grp0);
+      else softmax_chunk<true, DROP>(cb, 1, pk, c, off, kv_valid, acc, a.drop, grp0);
       tmem_st_32x16(tS + 16, pk);                       // P keys [32,64) over S columns [16,32)
-      float l_blk = acc.l0 + acc.l1, m_blk = fmaxf(acc.m0, acc.m1);
+      float l_blk = acc.l0 + acc.l1;
+      const float m_blk = fmaxf(acc.m0, acc.m1) * c + baked;      // block max in the log2 domain
       // P is bf16 and O / l are fp32, so exponents up to 2^20 above the reference are harmless; only beyond that is the
       // reference raised (FA-style lazy rescale; the common case never takes the slow path)
-      const bool need = (m_blk - m_run) * c > 20.0f;
-      if (__any_sync(0xffffffffu, need)) {
-        // rare: raise the reference max, rescale O and l, redo the block's exponentials from the registers
-        const float m_new = fmaxf(m_run, m_blk);
-        if (j > 0) {
-          mbar_wait(&pv_done[(j - 1) % AT_SBUF], ((j - 1) / AT_SBUF) & 1);   // P_{j-1} V_{j-1} must have landed in O
-          tcgen05_fence_after();
-          const float f = exp2f((m_run - m_new) * c);
-          l_run *= f;
-#pragma unroll 1
-          for (int ch = 0; ch < 4; ++ch) {
-            uint32_t o[16];
-            tmem_ld_32x16(tmem_O + lane_off + ch * 16, o);
-            tmem_wait_ld();
+      const bool need = (m_blk - m_ref) > 20.0f;
+      if (__builtin_expect(__any_sync(0xffffffffu, need), 0)) rescale(j, ca, cb, tS, baked, kv_valid, grp0, m_blk, l_blk, false);
+      else if (UNIT && j == 0) set_shift(0, m_ref);     // the first reference becomes the shift of blocks 3, 4, ...
+      l_run += l_blk;
+    };
+    // UNIT fast step: a full block whose S already carries this row's current reference as shift (S' = s - m_ref):
+    // p = ex2(S'), bf16 pack, row sum - nothing else.  A row sum above 2^40 (some p far above the reference, inf included)
+    // sends the warp through the same rescale as the general step; below that bf16 P / fp32 l, O lose nothing.
+    // `tracked` = false inside the fast loop (all three slots equal the current shift there, nothing to maintain).
+    // Returns true (warp-uniform) if the block had to raise the reference.
+    auto step_unit = [&](int j, uint32_t (&ca)[32], uint32_t (&cb)[32], uint32_t (&na)[32], bool tracked) -> bool {
+      const uint32_t tS = tmem_base + (j % AT_SBUF) * AT_BKV + lane_off;
+      TL(1 + warp, j);
+      tmem_wait_ld();                                   // ca
+      reg_fence32(ca);
+      tmem_ld_32x32(tS + 32, cb);
+      uint64_t lacc = 0;                                // (0.f, 0.f)
+      uint32_t pk[16];
+      softmax_chunk_unit(ca, pk, lacc);
+      if (tracked) announce_prev(j); else { tmem_wait_st(); tcgen05_fence_before(); mbar_arrive(&p_ready[(j - 1) % AT_SBUF]); }
+      tmem_st_32x16(tS, pk);
+      tmem_wait_ld();                                   // cb
+      reg_fence32(cb);
+      request_next(j, na);
+      softmax_chunk_unit(cb, pk, lacc);
+      tmem_st_32x16(tS + 16, pk);
+      float la, lb;
+      unpack_f32x2(lacc, la, lb);
+      float l_blk = la + lb;
+      const bool need = __any_sync(0xffffffffu, !(l_blk <= 1.0995116e12f));
+      if (__builtin_expect(need, 0)) {
+        float mx = -INFINITY;                           // the fast pass keeps no maximum: take it from the registers
 #pragma unroll
-            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
-            tmem_st_32x16(tmem_O + lane_off + ch * 16, o);
-          }
+        for (int i = 0; i < 32; i += 2) {
+          mx = max3(mx, __uint_as_float(ca[i]), __uint_as_float(ca[i + 1]));
+          mx = max3(mx, __uint_as_float(cb[i]), __uint_as_float(cb[i + 1]));
         }
-        m_run = m_new;
-        softmax_block<true, DROP>(ca, cb, tS, c, m_run * c, kv_valid, l_blk, m_blk, a.drop, grp0);
+        rescale(j, ca, cb, tS, m_ref, AT_BKV, 0, mx + m_ref, l_blk, !tracked);
       }
       l_run += l_blk;
+      return need;
+    };
+    // the fast step needs, for EVERY row of the warp, a full block computed with the row's current reference as shift
+    auto unit_ready = [&](int j) {
+      if (!UNIT) return false;
+      const int b = j % AT_SBUF;
+      const float baked = b == 0 ? bk0 : (b == 1 ? bk1 : bk2);
+      return a.Tk - j * AT_BKV >= AT_BKV && __all_sync(0xffffffffu, baked == m_ref);
     };
     uint32_t ra[32], rb[32], rc[32];
     TRACE_T0();
     mbar_wait(&s_full[0], 0);
     tcgen05_fence_after();
     tmem_ld_32x32(tmem_base + lane_off, ra);
-    for (int j = 0; j < n_kv; j += 2) {
-      step(j, ra, rb, rc);
-      if (j + 1 < n_kv) step(j + 1, rc, rb, ra);
+    int j = 0;
+    if (UNIT) {
+      // blocks 0..2 were issued before any row max was known: general steps (shift 0 baked in)
+      step(0, ra, rb, rc);
+      if (n_kv > 1) step(1, rc, rb, ra);
+      if (n_kv > 2) step(2, ra, rb, rc);
+      j = n_kv < 3 ? n_kv : 3;
+      // fast loop over the full blocks: two steps per iteration (register sets alternate), no per-step bookkeeping.
+      // Entered only if every row of the warp has all in-flight blocks on its current reference; left on a rescale.
+      const int n_full = a.Tk / AT_BKV;                 // blocks without padded keys
+      bool fast_ok = __all_sync(0xffffffffu, bk0 == m_ref && bk1 == m_ref && sh_cur == m_ref);
+      if (fast_ok) bk2 = sh_cur;                        // S_5 is issued behind this thread's next arrival (p_ready[2])
+      while (fast_ok && j + 1 < n_full) {               // j is odd here
+        if (step_unit(j, rc, rb, ra, false)) { j += 1; break; }
+        if (step_unit(j + 1, ra, rb, rc, false)) { j += 2; break; }
+        j += 2;
+      }
+    }
+    if (UNIT) {
+      for (; j < n_kv; ++j) {                           // blocks after a rescale inside the fast loop, ragged last block
+        if (j & 1) { if (unit_ready(j)) step_unit(j, rc, rb, ra, true); else step(j, rc, rb, ra); }
+        else { if (unit_ready(j)) step_unit(j, ra, rb, rc, true); else step(j, ra, rb, rc); }
+      }
+    } else {
+      for (; j < n_kv; j += 2) {
+        step(j, ra, rb, rc);
+        if (j + 1 < n_kv) step(j + 1, rc, rb, ra);
+      }
     }
     tmem_wait_st();                 // the last P (and a rescaled O) have landed in TMEM
     tcgen05_fence_before();         // orders this thread's TMEM accesses before the MMA warp's next MMAs
@@ -342,7 +509,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tcgen05_fence_after();
     const float inv = 1.0f / l_run;
     const int row = q0 + r;
-    if (a.lse && row < a.Tq) a.lse[((size_t)batch * gridDim.y + head) * a.Tq + row] = m_run * c + log2f(l_run);
+    if (a.lse && row < a.Tq) a.lse[((size_t)batch * gridDim.y + head) * a.Tq + row] = m_ref + log2f(l_run);
     __nv_bfloat16* orow = a.out + ((size_t)batch * a.Tq + row) * a.ldo + head * AT_HD;
 #pragma unroll 1
     for (int ch = 0; ch < 2; ++ch) {
@@ -388,6 +555,9 @@ extern "C" int desta_attention_trace(long long* host8, int reset) {
   if (reset) return cudaMemcpyToSymbol(g_attn_trace, z, sizeof(z)) == cudaSuccess ? 0 : -2;
   return cudaMemcpyFromSymbol(host8, g_attn_trace, sizeof(z)) == cudaSuccess ? 0 : -2;
 }
+extern "C" int desta_attention_timeline(long long* host_12x32) {
+  return cudaMemcpyFromSymbol(host_12x32, g_attn_tl, sizeof(long long) * 12 * 32) == cudaSuccess ? 0 : -2;
+}
 #endif
 
 extern "C" int desta_attention(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo,
@@ -403,7 +573,10 @@ extern "C" int desta_attention(const void* q, int ldq, const void* k, int ldk, c
   if (heads > 65535 || batch > 65535) { set_error("desta_attention: heads/batch too large for one launch"); return DESTA_ERR_ARG; }
   AttnArgs a;
   a.out = (__nv_bfloat16*)out; a.ldo = ldo; a.Tq = Tq; a.Tk = Tk;
-  a.scale_log2 = scale * 1.4426950408889634f;
+  const double scale_log2 = (double)scale * 1.4426950408889634;
+  a.scale_log2 = (float)scale_log2;
+  // UNIT mode: the scores are already log2-domain exponents (the encoder folds head_dim^-1/2 * log2(e) into q)
+  const bool unit = !(drop && drop->thr16) && fabs(scale_log2 - 1.0) < 1e-6;
   a.lse = lse;
   a.drop = make_dropout_cfg(drop);
   a.q_rows = Tq < AT_BQ ? Tq : AT_BQ;
@@ -414,13 +587,15 @@ extern "C" int desta_attention(const void* q, int ldq, const void* k, int ldk, c
   if (make_qkv_tmap(&tmV, v, heads, Tk, ldv, batch, a.kv_rows)) return DESTA_ERR_CUDA;
   bool& attr_set = *device_once_flag(2);
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_fwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
     if (e != cudaSuccess) { set_error("attention smem attribute: %s", cudaGetErrorString(e)); return DESTA_ERR_CUDA; }
     attr_set = true;
   }
   const dim3 grid((Tq + AT_BQ - 1) / AT_BQ, heads, batch);
-  if (a.drop.thr16) attn_fwd_kernel<true><<<grid, AT_THREADS, AT_SMEM, (cudaStream_t)stream>>>(tmQ, tmK, tmV, a);
-  else attn_fwd_kernel<false><<<grid, AT_THREADS, AT_SMEM, (cudaStream_t)stream>>>(tmQ, tmK, tmV, a);
+  if (a.drop.thr16) attn_fwd_kernel<true, false><<<grid, AT_THREADS, AT_SMEM, (cudaStream_t)stream>>>(tmQ, tmK, tmV, a);
+  else if (unit) attn_fwd_kernel<false, true><<<grid, AT_THREADS, AT_SMEM, (cudaStream_t)stream>>>(tmQ, tmK, tmV, a);
+  else attn_fwd_kernel<false, false><<<grid, AT_THREADS, AT_SMEM, (cudaStream_t)stream>>>(tmQ, tmK, tmV, a);
   return check_launch("attn_fwd_kernel");
 }

@@ -228,6 +228,17 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t
   d |= (uint64_t)2 << 61;
   return d;
 }
+// Same with no swizzle ("interleaved" canonical K-major layout, layout_type 0): core matrix = 8 rows x 16 bytes stored
+// contiguously (128 B); LBO = byte distance between the two 16-byte K chunks of a K = 16 step, SBO = byte distance
+// between consecutive 8-row groups.
+__device__ __forceinline__ uint64_t umma_desc_nosw(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
 // Instruction descriptor for kind::f16, bf16 x bf16 -> fp32.
 //   c_format [4,6)=1 (F32), a_format [7,10)=1 (BF16), b_format [10,13)=1, a_major bit 15, b_major bit 16
 //   (0 = K-major, 1 = MN-major), n_dim [17,23) = N>>3, m_dim [24,29) = M>>4.

@@ -110,7 +110,11 @@ extern "C" int desta_encoder_fwd(const desta_dims* dims, const desta_encoder_wei
   const EncWs ws = carve_encoder(dims, N, workspace);
   if (workspace_bytes < ws.bytes) { set_error("desta_encoder_fwd: workspace too small (%zu < %zu)", workspace_bytes, ws.bytes); return DESTA_ERR_ARG; }
   const int d = dims->d_model, T = dims->max_pos, M = N * T, H = dims->n_heads, F = dims->ffn;
-  const float q_scale = 1.0f / sqrtf((float)(d / H));
+  // q = (y Wq^T + bq) * head_dim^-1/2 (modeling_whisper.py:310).  The softmax works with base-2 exponentials, so log2(e)
+  // is folded into the same epilogue scale and the attention kernel is called with scale = ln 2: its scores are then
+  // already log2-domain exponents (UNIT mode of attn_fwd_kernel: the max shift is applied by the tensor cores).
+  const float q_scale = 1.4426950408889634f / sqrtf((float)(d / H));
+  const float attn_scale = 0.6931471805599453f;
   // conv stem as im2col + GEMM: gelu(conv1), gelu(conv2 stride 2) + positions -> fp32 residual stream (:563-570)
   RUN(desta_im2col_k3(mel_tm, N, 2 * T, dims->n_mels, 1, ws.cols1, stream));
   RUN(gemm(ws.cols1, 3 * dims->n_mels, w->conv1_w, 3 * dims->n_mels, 2 * M, d, 3 * dims->n_mels, w->conv1_b, ws.c1, d, nullptr, 0,
@@ -122,7 +126,7 @@ extern "C" int desta_encoder_fwd(const desta_dims* dims, const desta_encoder_wei
     const desta_enc_layer& L = w->layers[i];
     RUN(desta_layernorm(h, d, L.ln1_w, L.ln1_b, 1e-5f, M, d, ws.y, d, nullptr, 0, stream));
     RUN(gemm(ws.y, d, L.qkv_w, d, M, 3 * d, d, L.qkv_b, ws.qkv, 3 * d, nullptr, 0, nullptr, 0, nullptr, 0, q_scale, d, 0, stream));
-    RUN(desta_attention(ws.qkv, 3 * d, ws.qkv + d, 3 * d, ws.qkv + 2 * d, 3 * d, ws.ao, d, N, H, T, T, 1.0f, nullptr, nullptr, stream));
+    RUN(desta_attention(ws.qkv, 3 * d, ws.qkv + d, 3 * d, ws.qkv + 2 * d, 3 * d, ws.ao, d, N, H, T, T, attn_scale, nullptr, nullptr, stream));
     RUN(gemm(ws.ao, d, L.o_w, d, M, d, d, L.o_b, nullptr, 0, h, d, h, d, nullptr, 0, 1.f, 0, 0, stream));
     RUN(desta_layernorm(h, d, L.ln2_w, L.ln2_b, 1e-5f, M, d, ws.y, d, nullptr, 0, stream));
     RUN(gemm(ws.y, d, L.fc1_w, d, M, F, d, L.fc1_b, ws.ff, F, nullptr, 0, nullptr, 0, nullptr, 0, 1.f, 0, 1, stream));

@@ -17,6 +17,7 @@ import ctypes
 from . import ops
 from ._lib import ConnectorWeights, Dims, EncLayer, EncoderWeights, QfLayer, check, lib
 
+LOG2E, LN2 = 1.4426950408889634, 0.6931471805599453
 ENC = "whisper.model.encoder."
 CON = "connector."
 
@@ -279,8 +280,9 @@ def encoder_forward_ops(enc: EncoderPack, dims: PathDims, ws: Workspace, mel_tm:
     tap_idx = 0
     for i, L in enumerate(enc.layers):
         ops.layernorm(ws.h, L["ln1_w"], L["ln1_b"], 1e-5, out_bf16=ws.y)
-        ops.gemm(ws.y, L["qkv_w"], L["qkv_b"], out_bf16=ws.qkv, scale=hd ** -0.5, scale_cols=d)
-        ops.attention(ws.qkv[:, :d], ws.qkv[:, d:2 * d], ws.qkv[:, 2 * d:], ws.ao, N, dims.n_heads, T, T, 1.0)
+        # head_dim^-1/2 * log2(e) folded into q, attention scale ln 2: same arithmetic as desta_encoder_fwd (schedule.cu)
+        ops.gemm(ws.y, L["qkv_w"], L["qkv_b"], out_bf16=ws.qkv, scale=LOG2E * hd ** -0.5, scale_cols=d)
+        ops.attention(ws.qkv[:, :d], ws.qkv[:, d:2 * d], ws.qkv[:, 2 * d:], ws.ao, N, dims.n_heads, T, T, LN2)
         ops.gemm(ws.ao, L["o_w"], L["o_b"], out_f32=ws.h, resid=ws.h)
         ops.layernorm(ws.h, L["ln2_w"], L["ln2_b"], 1e-5, out_bf16=ws.y)
         ops.gemm(ws.y, L["fc1_w"], L["fc1_b"], out_bf16=ws.ff, gelu=True)

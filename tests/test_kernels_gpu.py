@@ -175,6 +175,44 @@ def test_attention_peaky_softmax():
     assert _rel(out, ref) < 2e-2
 
 
+LN2 = 0.6931471805599453
+
+
+@pytest.mark.parametrize("B,H,Tq,Tk,amp,ramp", [(2, 3, 1500, 1500, 1.0, 0.0), (1, 2, 300, 700, 1.0, 0.0), (2, 2, 64, 1500, 1.5, 0.0),
+                                                (1, 2, 128, 1024, 3.0, 0.0), (1, 2, 256, 960, 1.0, 6.0), (1, 1, 128, 100, 2.0, 0.0),
+                                                (1, 2, 200, 64, 1.0, 0.0), (1, 2, 130, 192, 1.0, 3.0)])
+def test_attention_unit_scale_mode(B, H, Tq, Tk, amp, ramp):
+    """scale = ln 2 (scale * log2 e == 1) selects the kernel variant whose softmax shift is applied by the tensor cores
+    (the encoder's call: q carries head_dim^-1/2 * log2 e).  Same oracle, same tolerance; lse in the log2 domain.
+    `ramp` makes the scores grow along the keys so that later blocks raise the reference (lazy rescale + shift update:
+    blocks computed with a stale shift take the general path), `amp` scales the logits (peaky rows)."""
+    g = torch.Generator(device="cuda").manual_seed(Tq * 3 + Tk)
+    d = H * 64
+    q = (torch.randn(B * Tq, d, device="cuda", generator=g) * amp).to(torch.bfloat16)
+    k = (torch.randn(B * Tk, d, device="cuda", generator=g) * amp).to(torch.bfloat16)
+    if ramp:
+        growth = torch.linspace(1.0, ramp, Tk, device="cuda").repeat(B)[:, None]
+        k = (k.float() * growth).to(torch.bfloat16)
+    v = torch.randn(B * Tk, d, device="cuda", generator=g).to(torch.bfloat16)
+    out = torch.zeros(B * Tq, d, device="cuda", dtype=torch.bfloat16)
+    lse = torch.empty(B * H * Tq, device="cuda")
+    ops.attention(q, k, v, out, B, H, Tq, Tk, LN2, lse=lse)
+    qf = q.float().reshape(B, Tq, H, 64).transpose(1, 2)
+    kf = k.float().reshape(B, Tk, H, 64).transpose(1, 2)
+    vf = v.float().reshape(B, Tk, H, 64).transpose(1, 2)
+    s = qf @ kf.transpose(-1, -2) * LN2
+    ref = (torch.softmax(s, -1) @ vf).transpose(1, 2).reshape(B * Tq, d)
+    err = _rel(out, ref)
+    assert torch.isfinite(out.float()).all()
+    assert err < 2e-2 and _cos(out, ref) > 0.9995, f"attention (unit mode) rel err {err} cos {_cos(out, ref)}"
+    lse_ref = (torch.logsumexp(s, -1) * 1.4426950408889634).reshape(-1)
+    assert (lse - lse_ref).abs().max().item() < 2e-2 * max(1.0, lse_ref.abs().max().item() / 16)
+    # the general variant (scale passed separately) must agree with it closely: same inputs, scale moved into q
+    out2 = torch.zeros_like(out)
+    ops.attention((q.float() * 0.5).to(torch.bfloat16), k, v, out2, B, H, Tq, Tk, 2 * LN2)
+    assert _rel(out2, ref) < 2e-2
+
+
 # ------------------------------------------------------------------ log-mel
 @pytest.mark.parametrize("n_mels", [80, 128])
 def test_logmel_vs_oracle_and_golden(n_mels, golden_dir):

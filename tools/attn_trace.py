@@ -31,14 +31,14 @@ def run():
              "softmax warp 3 (SMSP 3): wait s_full"]
     ctas, blocks = 12 * H * B, 24
     # layouts: (label, row pitch in elements, junk bytes allocated before the buffer to shift its address)
-    for label, pitch, junk in [("fused qkv pitch 3840", 3 * d, 0), ("pitch 3840, base shifted 3 MB + 512 B", 3 * d, 3 * 2 ** 20 + 512),
-                               ("pitch 3840 + 64", 3 * d + 64, 0), ("pitch 4096", 4096, 0), ("pitch 3840 again", 3 * d, 0)]:
+    LN2 = 0.6931471805599453
+    for label, pitch, junk, scale in [("general path (scale 1.0)", 3 * d, 0, 1.0), ("UNIT path (scale ln 2)", 3 * d, 0, LN2)]:
         pad = torch.empty(junk, dtype=torch.uint8, device="cuda") if junk else None
         buf_t = torch.empty(B * T, pitch, device="cuda", dtype=torch.bfloat16)
         buf_t.normal_(0, 0.5)
         out = torch.empty(B * T, d, device="cuda", dtype=torch.bfloat16)
         args = [vp(buf_t.data_ptr()), pitch, vp(buf_t.data_ptr() + 2 * d), pitch, vp(buf_t.data_ptr() + 4 * d), pitch, vp(out.data_ptr()), d,
-                B, H, T, T, ctypes.c_float(1.0), None, None, vp(torch.cuda.current_stream().cuda_stream)]
+                B, H, T, T, ctypes.c_float(scale), None, None, vp(torch.cuda.current_stream().cuda_stream)]
         for _ in range(3):
             assert L.desta_attention(*args) == 0
         torch.cuda.synchronize()
@@ -53,7 +53,18 @@ def run():
         L.desta_attention_trace(buf, 0)
         print(f"{label}: {e0.elapsed_time(e1) / 5:.3f} ms  (qkv at 0x{buf_t.data_ptr():x})  per key block per CTA: "
               f"kv_full wait {buf[0] / ctas / blocks / 5:.0f}, p_ready wait {buf[1] / ctas / blocks / 5:.0f}, MMA loop {buf[3] / ctas / blocks / 5:.0f}, "
-              f"softmax s_full wait {buf[2] / ctas / blocks / 5:.0f}, softmax loop {buf[4] / ctas / blocks / 5:.0f}", flush=True)
+              f"softmax s_full wait {buf[2] / ctas / blocks / 5:.0f} (w4 {buf[5] / ctas / blocks / 5:.0f}, w5 {buf[6] / ctas / blocks / 5:.0f}, w3 {buf[7] / ctas / blocks / 5:.0f}), "
+              f"softmax loop {buf[4] / ctas / blocks / 5:.0f}", flush=True)
+        tl = (ctypes.c_longlong * (12 * 32))()
+        if hasattr(L, "desta_attention_timeline") and L.desta_attention_timeline(tl) == 0:
+            ev = [[tl[e * 32 + j] for j in range(24)] for e in range(12)]
+            t0 = min(v for row in ev for v in row if v > 0)
+            rel = lambda v: (v - t0) if v > 0 else -1
+            print("   timeline of CTA (5,7,30), cycles from its first event; per block j:")
+            print("    j | MMA: p_ready seen, PV issued, QK_j issued | softmax step start w2 w3 w4 w5 | got S_j w2 w3 w4 w5")
+            for j in range(24):
+                print(f"   {j:2d} | {rel(ev[0][j]):6d} {rel(ev[1][j]):6d} {rel(ev[2][j]):6d} | {rel(ev[3][j]):6d} {rel(ev[4][j]):6d} {rel(ev[5][j]):6d} {rel(ev[6][j]):6d} |"
+                      f" {rel(ev[7][j]):6d} {rel(ev[8][j]):6d} {rel(ev[9][j]):6d} {rel(ev[10][j]):6d}")
         del buf_t, out, pad
 
 

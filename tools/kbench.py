@@ -45,7 +45,8 @@ def bench_gemm():
 
 
 def bench_attn():
-    for name, B, H, Tq, Tk, scale in [("encoder", 64, 20, 1500, 1500, 1.0), ("qf_cross", 256, 20, 64, 1500, 0.125), ("qf_self", 256, 20, 64, 64, 0.125)]:
+    for name, B, H, Tq, Tk, scale in [("encoder", 64, 20, 1500, 1500, 1.0), ("enc_unit", 64, 20, 1500, 1500, 0.6931471805599453),
+                                      ("qf_cross", 256, 20, 64, 1500, 0.125), ("qf_self", 256, 20, 64, 64, 0.125)]:
         d = H * 64
         qkv = (torch.randn(B * max(Tq, Tk), 3 * d, device="cuda") * 0.5).to(torch.bfloat16)   # logits ~ N(0, 2): few rescales, like the model
         out = torch.empty(B * Tq, d, device="cuda", dtype=torch.bfloat16)
