@@ -2,22 +2,33 @@
 """bench.py — waveform -> LLM-input-embeddings throughput (audio-seconds / second), BASELINE.json's metric.
 
   python bench.py --gpus N --steps K --warmup W            # our arm (one process per GPU under torchrun for N > 1)
-  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port) on the host cores
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU path on the host cores
 
 A "step" is one pass of the hot path over one batch of synthetic 30 s / 16 kHz clips per GPU:
   log-mel -> whisper-large-v3 encoder with taps -> Q-Former-6L connector -> <|AUDIO|> splice into Llama-3.1-8B-sized
   token embeddings (configs[1] of BASELINE.json: 64 clips on one B200; random-init weights of that architecture).
-`value`  : inputs already resident in HBM when the timed region starts.
-`e2e`    : the public call with HOST buffers: pinned waveforms H2D + perception + splice + D2H of inputs_embeds.
+`value`      : inputs already resident in HBM when the timed region starts.
+`e2e`        : the PUBLIC call with HOST buffers - `processor(list of numpy clips)` (the b1 shim installed by
+               `desta_b200.install`, packing into pinned slots) -> `.to(device)` -> `model._prepare_inputs_for_llm(...)`
+               on an installed model object -> D2H of inputs_embeds; host packing, H2D and D2H are inside the timed
+               region.  The packing of step k+1 runs on a loader thread while step k computes, as the reference's
+               DataLoader workers do for its collate function (simple_dataset.py:239-243).
+`e2e_staged` : the same from PRE-PACKED pinned buffers through `desta_b200.staging.WaveformStager` (round-1 definition).
+`train`      : BASELINE configs[4] in the same line - frozen encoder forward + Q-Former forward / backward on 32 clips
+               per GPU, connector gradients all-reduced across ranks (the reference's only exchange: DDP over the
+               131.5 M connector parameters), with the all-reduce overlapped per Q-Former layer; `comm` reports the
+               bytes exchanged and the exposed time (step with the exchange minus step without it).
 Clips are independent -> ranks shard clips, no data-path collective ("scaling": "weak").
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
 import sys
 import threading
 import time
+import types
 
 import numpy as np
 import torch
@@ -26,7 +37,6 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (oracle config name, dims)
     "large_v3_llama": dict(n_mels=128, d_model=1280, n_heads=20, ffn=5120, n_layers=32, tap_layers=[7, 15, 23, 31],
                            qf_layers=6, prompt_size=64, d_llm=4096, vocab=128256),
     # whisper-large-v3-turbo shares the large-v3 encoder (32 layers, d 1280); only the decoder differs
@@ -43,7 +53,7 @@ START_POS = 20
 
 
 def fwd_flops_per_clip(w):
-    d, f, L, T, H = w["d_model"], w["ffn"], w["n_layers"], 1500, w["n_heads"]
+    d, f, L, T = w["d_model"], w["ffn"], w["n_layers"], 1500
     conv = 2 * 3000 * d * 3 * w["n_mels"] + 2 * T * d * 3 * d
     layer = 2 * T * d * 3 * d + 2 * T * d * d + 4 * T * T * d + 2 * 2 * T * d * f
     enc = conv + L * layer
@@ -53,6 +63,16 @@ def fwd_flops_per_clip(w):
            + 2 * 2 * Q * d * qf)
     con = K * w["qf_layers"] * per + 2 * Q * d * w["d_llm"]
     return enc + con
+
+
+def train_flops_per_clip(w):
+    """+ connector backward = 2 x connector forward minus the K/V data-gradient (taps need no grad), SURVEY.md §8d."""
+    d_, T_, K_, L_ = w["d_model"], 1500, len(w["tap_layers"]), w["qf_layers"]
+    fwd = fwd_flops_per_clip(w)
+    kv = K_ * L_ * 2 * T_ * d_ * 2 * d_
+    enc_only = fwd_flops_per_clip(dict(w, qf_layers=0)) - 2 * w["prompt_size"] * d_ * w["d_llm"]
+    con = fwd - enc_only
+    return fwd + 2 * con - kv
 
 
 def synth_wave_batch(n, seed):
@@ -108,8 +128,34 @@ def measured_peaks():
     return 6650.0, 1590.0, 1400.0, "fallback"
 
 
-# --------------------------------------------------------------------------------------------- CPU arm (oracle port)
-def cpu_reference_rate(workload, n_clips, steps=1, warmup=0, threads=None):
+def gemm_source_sha():
+    """Hash of the sources the GEMM kernels are built from: the committed ncu DRAM-traffic figure is only quoted while it
+    still describes this code."""
+    h = hashlib.sha256()
+    for name in ("gemm2.cu", "gemm.cu", "common.cuh"):
+        h.update(open(os.path.join(ROOT, "desta2.5-audio_b200", "csrc", name), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def committed_gemm_traffic(workload, n, train):
+    """`roofline.traffic`: DRAM bytes per GEMM launch from the committed `ncu --set full` capture of this command - or None
+    when no capture matches the current GEMM sources (a stale constant is worse than none)."""
+    if train or workload != "large_v3_llama" or n != 64:
+        return None, "no capture for this configuration"
+    best = None
+    pdir = os.path.join(ROOT, "profiles")
+    for name in sorted(os.listdir(pdir)):
+        if name.endswith("gemm_traffic.json"):
+            d = json.load(open(os.path.join(pdir, name)))
+            if d.get("gemm_source_sha") == gemm_source_sha():
+                best = (d["dram_bytes_per_launch_avg"], name)
+    if best is None:
+        return None, "no committed capture matches the current GEMM sources (sha %s)" % gemm_source_sha()
+    return best
+
+
+# --------------------------------------------------------------------------------------------- CPU arm
+def cpu_port_rate(workload, n_clips, steps=1, warmup=0, threads=None):
     """The reference's CPU path restated in oracle/ (same ATen CPU kernels the reference reaches through transformers),
     fp32, all host threads; returns (audio-s/s, seconds per step, threads)."""
     from oracle import encoder as o_enc, logmel as o_mel, qformer as o_qf, splice as o_sp
@@ -138,6 +184,56 @@ def cpu_reference_rate(workload, n_clips, steps=1, warmup=0, threads=None):
         step()
     dt = (time.perf_counter() - t0) / steps
     return 30.0 * n_clips / dt, dt, threads
+
+
+def cpu_reference_rate(workload, n_clips, steps=1, warmup=0, threads=None):
+    """The UNMODIFIED reference (baseline/_ref, or /root/reference in the build container) on the host cores: its own
+    `WhisperFeatureExtractor` call, `DeSTA25AudioModel.perception` and `_prepare_inputs_for_llm`, fp32 as the reference runs
+    inference, random-init weights of the named architecture from explicit configs (oracle/refshim.py replaces only what
+    would hit the network).  Returns (audio-s/s, seconds per step, threads)."""
+    from oracle import refshim
+    from oracle.configs import CONFIGS
+    cfg = CONFIGS[workload]
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    ref = refshim.load_reference(cfg)
+    rcfg = ref.DeSTA25Config(llm_model_id="llama", encoder_model_id=cfg.encoder_model_id, qformer_num_hidden_layers=cfg.qf_layers,
+                             prompt_size=cfg.prompt_size)
+    torch.manual_seed(0)
+    model = ref.DeSTA25AudioModel(rcfg).eval()
+    processor = refshim.OfflineWhisperProcessor(cfg.n_mels)
+    waves = [w.numpy() for w in synth_wave_batch(n_clips, 1234)]
+    ids = torch.from_numpy(np.random.default_rng(0).integers(0, cfg.vocab, (n_clips, SEQ_LEN)))
+    attn = torch.ones_like(ids)
+    pos = [(i, START_POS) for i in range(n_clips)]
+    trans = [torch.zeros(1, 0, dtype=torch.int64) for _ in range(n_clips)]
+
+    def step():
+        feats = processor(waves, sampling_rate=16000, return_tensors="pt").input_features      # modeling_desta25.py:1570
+        with torch.no_grad():
+            return model._prepare_inputs_for_llm(ids, attn, feats, trans, pos)                  # :940-1050
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return 30.0 * n_clips / dt, dt, threads
+
+
+def cpu_arm(workload, n_clips, steps=1, warmup=0):
+    """-> (rate, dt, threads, kind, note): the reference's own code when it is installed on this machine, else the port."""
+    from oracle import refshim
+    note = None
+    if refshim.ref_root() is not None and workload in ("large_v3_llama", "turbo_llama", "debug"):
+        try:
+            wl = "large_v3_llama" if workload == "turbo_llama" else workload
+            return (*cpu_reference_rate(wl, n_clips, steps, warmup), "reference", None)
+        except Exception as e:      # reported in the line; the port below restates the same arithmetic
+            note = "reference run failed (%r): oracle port timed instead" % (e,)
+    wl = "large_v3_llama" if workload == "turbo_llama" else workload
+    return (*cpu_port_rate(wl, n_clips, steps, warmup), "port", note)
 
 
 def decode_resample_rates(n, dev):
@@ -171,48 +267,54 @@ def run_reference(args):
     if rank != 0:
         return
     n = args.ref_clips
-    rate, dt, threads = cpu_reference_rate(args.workload, n, steps=args.steps, warmup=min(args.warmup, 1))
+    rate, dt, threads, kind, note = cpu_arm(args.workload, n, steps=args.steps, warmup=min(args.warmup, 1))
+    what = ("the unmodified reference from baseline/_ref (WhisperFeatureExtractor + DeSTA25AudioModel.perception + "
+            "_prepare_inputs_for_llm)") if kind == "reference" else "oracle/ (fp32 ATen CPU kernels, restatement of the reference)"
     line = {
         "impl": "reference", "metric": "audio-sec/sec waveform->LLM embeds", "value": rate, "unit": "audio-s/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.workload}: whisper-large-v3 encoder + Qformer6L -> Llama-3.1-8B embeds, 30 s clips",
-                   "clips_per_step": n, "seq_len": SEQ_LEN},
-        "cpu_baseline": {"value": rate, "unit": "audio-s/s", "cores": threads, "kind": "port",
-                         "sample": f"{n} clips x {args.steps} steps through oracle/ (fp32 ATen CPU kernels)"},
+                   "clips_per_step": n, "seq_len": SEQ_LEN,
+                   "note": "ONE host process on rank 0 whatever --gpus says: at N > 1 the driver's ratio compares N GPUs with one CPU run"},
+        "cpu_baseline": {"value": rate, "unit": "audio-s/s", "cores": threads, "kind": kind,
+                         "sample": f"{n} clips x {args.steps} steps through {what}"},
         "e2e": {"value": rate, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if note:
+        line["cpu_baseline"]["note"] = note
     print(json.dumps(line))
 
 
 # --------------------------------------------------------------------------------------------- our arm
-def run_ours(args):
-    import torch.distributed as dist
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    import __graft_entry__
-    if rank == 0:
-        __graft_entry__.build()
-    if world > 1:
-        dist.barrier()
-    from desta_b200 import ops
-    from desta_b200.splice import prepare_inputs_for_llm
-    from desta_b200.synthetic import build_perception
+class _Host:
+    """The attribute layout `desta_b200.install` needs of a DeSTA25AudioModel (modeling_desta25.py:698-757): the LLM's
+    embedding table, the perception module, the config flag - no LLM decoder (out of scope, never on this path)."""
 
-    w = WORKLOADS[args.workload]
-    n = args.clips
+
+def build_installed_model(w, dev, seed=0):
+    """Random-init perception of the named architecture + an embedding table, handed to `desta_b200.install` exactly like
+    a reference model: `.processor` becomes the b1 shim, `._prepare_inputs_for_llm` the b3 drop-in."""
+    import desta_b200
+    from desta_b200.synthetic import build_perception
     perception = build_perception(w["n_mels"], w["d_model"], w["n_heads"], w["ffn"], w["n_layers"], w["tap_layers"],
-                                  w["qf_layers"], w["prompt_size"], w["d_llm"], dev, seed=0)
+                                  w["qf_layers"], w["prompt_size"], w["d_llm"], dev, seed=seed)
     g = torch.Generator(device=dev).manual_seed(1)
-    table = (0.02 * torch.randn(w["vocab"], w["d_llm"], device=dev, generator=g)).to(torch.bfloat16)
-    wave_host = synth_wave_batch(n, 1234 + rank).pin_memory()
-    wave_dev = wave_host.to(dev)
+    embed = torch.nn.Embedding(w["vocab"], w["d_llm"], device=dev, dtype=torch.bfloat16)
+    with torch.no_grad():
+        embed.weight.copy_((0.02 * torch.randn(w["vocab"], w["d_llm"], device=dev, generator=g)).to(torch.bfloat16))
+    embed.weight.requires_grad_(False)
+    model = _Host()
+    model.config = types.SimpleNamespace(connector_mode="qformer_1", prompt_size=w["prompt_size"])
+    model.perception = perception                       # already the B200 module (install is idempotent on it)
+    model.llm_model = types.SimpleNamespace(model=types.SimpleNamespace(embed_tokens=embed))
+    model.processor = types.SimpleNamespace(batch_decode=lambda *a, **k: [])      # stands for the HF WhisperProcessor
+    desta_b200.install(model)
+    return model
+
+
+def prompts_for(args, w, n, rank):
     gen = torch.Generator().manual_seed(7 + rank)
     if args.prompts == "multi":
         # multi-clip prompts (SURVEY.md §8d): B = N/4 prompts, 4 locators each, transcripts of 0/3/17/40 tokens, S = 512
@@ -232,174 +334,322 @@ def run_ours(args):
         positions = [(i, START_POS) for i in range(n)]
         trans = [torch.zeros(1, 0, dtype=torch.int64) for _ in range(n)]     # empty transcripts (simple_dataset.py:668)
     ids_host = torch.randint(0, w["vocab"], (B_prompts, S_len), generator=gen).pin_memory()
-    ids_dev = ids_host.to(dev)
-    out_host = torch.empty(B_prompts, S_len, w["d_llm"], dtype=torch.bfloat16).pin_memory()
+    return S_len, B_prompts, positions, trans, ids_host
 
-    train = args.mode == "train"
-    bucket = None
-    if train:
-        from desta_b200.dist import GradBucket
-        perception.train()
-        grad_emb = (0.01 * torch.randn(B_prompts, S_len, w["d_llm"], device=dev, generator=g)).to(torch.bfloat16)
-        if world > 1:
-            if args.grad_sync == "overlap":
-                from desta_b200.dist import GradSync
-                perception.grad_sync = GradSync()       # all-reduce per Q-Former layer inside the backward
-            else:
-                bucket = GradBucket(list(perception.connector.parameters()))
 
-    def train_step(ii, wv):
-        # frozen encoder forward + Q-Former forward/backward; the LLM's gradient w.r.t. inputs_embeds is synthetic
-        for prm in perception.connector.parameters():
-            prm.grad = None
-        emb = prepare_inputs_for_llm(table, perception, ii, None, wv, trans, positions)
-        emb.backward(grad_emb)
-        if bucket is not None:
-            bucket.allreduce()      # same exchange as the reference's DDP: one averaged all-reduce of connector grads
-        return emb
+def rank_stats(ms_local, world, dev):
+    """Per-rank step time statistics (ms per step): the max is the reported step; the spread attributes a scaling loss."""
+    import torch.distributed as dist
+    t = torch.tensor([ms_local], device=dev)
+    if world > 1:
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        vals = sorted(float(x.item()) for x in allt)
+    else:
+        vals = [ms_local]
+    return {"min": round(vals[0], 3), "median": round(vals[len(vals) // 2], 3), "max": round(vals[-1], 3)}
 
-    if args.graph and not train:
-        perception.capture_graph(n)
 
-    def step_resident():
-        if train:
-            return train_step(ids_dev, wave_dev)
-        with torch.no_grad():
-            return prepare_inputs_for_llm(table, perception, ids_dev, None, wave_dev, trans, positions)
-
-    # e2e: the public call fed from PINNED HOST memory through the double-buffered stager (desta_b200.staging, scope row
-    # n1): the H2D copy of step k+1 runs on the copy stream while the kernels of step k execute, the D2H read of the
-    # result runs on its own stream; every step still moves its own inputs and outputs (bytes counted below).
-    from desta_b200.staging import WaveformStager
-    stager = WaveformStager(n, dev, slots=2)
-    for sl in range(2):
-        stager.fill(sl, wave_host.numpy())
-    d2h_stream = torch.cuda.Stream(dev)
-    e2e_state = {"k": 0, "primed": False}
-
-    def step_e2e():
-        k = e2e_state["k"]
-        slot = k % 2
-        if not e2e_state["primed"]:
-            stager.submit(slot)
-            e2e_state["primed"] = True
-        stager.submit((k + 1) % 2)                      # next step's inputs: in flight during this step's kernels
-        wv, _ = stager.acquire(slot)
-        ii = ids_host.to(dev, non_blocking=True)
-        if train:
-            emb = train_step(ii, wv)
-        else:
-            with torch.no_grad():
-                emb = prepare_inputs_for_llm(table, perception, ii, None, wv, trans, positions)
-        stager.release(slot)
-        done = torch.cuda.Event()
-        done.record()
-        d2h_stream.wait_event(done)
-        with torch.cuda.stream(d2h_stream):
-            out_host.copy_(emb.detach(), non_blocking=True)
-        emb.record_stream(d2h_stream)
-        e2e_state["k"] = k + 1
-        return emb
-
-    def timed(fn, steps):
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0 = time.time()
-        e0.record()
-        for _ in range(steps):
-            fn()
-        torch.cuda.current_stream().wait_stream(d2h_stream)      # the steps' D2H reads and H2D copies belong to the timed region
-        torch.cuda.current_stream().wait_stream(stager.copy_stream)
-        e1.record()
-        torch.cuda.synchronize()
-        t1 = time.time()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.barrier()
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return ms.item(), t0, t1
-
-    for _ in range(max(args.warmup, 3)):
-        step_resident()
-    sampler = ClockSampler(local)
-    sampler.start()
-    time.sleep(0.3)
-    l0 = ops.STATS["launches"] + ops.STATS.get("graph_kernels", 0)
-    ms, t0, t1 = timed(step_resident, args.steps)
-    launches = ops.STATS["launches"] + ops.STATS.get("graph_kernels", 0) - l0     # kernels executed, eagerly or by graph replay
-    clocks = sampler.stop(t0, t1)
-    # The part is power-capped: whichever region is timed second reads 1-2 % slower (same-box A/B with the order swapped:
-    # e2e / value = 0.986 vs 1.004).  Let the power governor settle, then give the e2e region the same warm-up.
+def timed(fn, steps, world, dev, extra_streams=()):
+    import torch.distributed as dist
     torch.cuda.synchronize()
-    time.sleep(1.5)
-    for _ in range(max(args.warmup, 3)):
-        step_e2e()
-    ms_e2e, _, _ = timed(step_e2e, args.steps)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    e0.record()
+    for _ in range(steps):
+        fn()
+    for s in extra_streams:                               # the steps' D2H reads and H2D copies belong to the timed region
+        torch.cuda.current_stream().wait_stream(s)
+    e1.record()
+    torch.cuda.synchronize()
+    t1 = time.time()
+    local = e0.elapsed_time(e1)
+    ms = torch.tensor([local], device=dev)
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return ms.item(), local, t0, t1
 
-    # one instrumented step (outside the timed regions): per-kernel-family device time with CUDA events
-    ops.start_profile()
-    step_resident()
-    prof = ops.stop_profile()
 
-    hbm_peak, tf_burst, tf_sust, peak_kind = measured_peaks()
+def family_table(prof):
     total_ms = sum(v["ms"] for v in prof.values())
     fam = {k: {"ms": round(v["ms"], 3), "share": round(v["ms"] / total_ms, 4), "calls": v["calls"],
                "achieved": round(v["work"] / (v["ms"] * 1e-3) / (1e12 if v["unit"] == "flop" else 1e9), 1),
                "unit": "TFLOP/s" if v["unit"] == "flop" else "GB/s"} for k, v in prof.items()}
-    gm = {"work": sum(prof[k]["work"] for k in ("gemm", "gemm_wgrad") if k in prof),
-          "ms": sum(prof[k]["ms"] for k in ("gemm", "gemm_wgrad") if k in prof),
-          "bytes": sum(prof[k]["bytes"] for k in ("gemm", "gemm_wgrad") if k in prof),
-          "calls": sum(prof[k]["calls"] for k in ("gemm", "gemm_wgrad") if k in prof)}
-    # DRAM traffic of the same kernel from the committed ncu capture of this command (per launch, like `achieved`)
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r1f_gemm_traffic.json")
-    if os.path.exists(tpath) and not train and args.workload == "large_v3_llama" and n == 64:
-        traffic = json.load(open(tpath))["dram_bytes_per_launch_avg"]
+    gm = {key: sum(prof[k][key] for k in ("gemm", "gemm_wgrad") if k in prof) for key in ("work", "ms", "bytes", "calls")}
+    return fam, gm, total_ms
+
+
+def roofline_of(gm, total_ms, traffic, traffic_note):
+    hbm_peak, tf_burst, tf_sust, peak_kind = measured_peaks()
     gemm_tflops = gm["work"] / (gm["ms"] * 1e-3) / 1e12
-    step_s = ms * 1e-3 / args.steps
-    value = 30.0 * n * world / step_s
-    e2e_value = 30.0 * n * world / (ms_e2e * 1e-3 / args.steps)
-    flops_clip = fwd_flops_per_clip(w)
-    if train:   # + connector backward = 2 x forward minus the K/V data-gradient (taps need no grad), SURVEY.md §8d
-        d_, T_, K_, L_ = w["d_model"], 1500, len(w["tap_layers"]), w["qf_layers"]
-        kv = K_ * L_ * 2 * T_ * d_ * 2 * d_
-        enc_only = fwd_flops_per_clip(dict(w, qf_layers=0)) - 2 * w["prompt_size"] * d_ * w["d_llm"]
-        con = flops_clip - enc_only
-        flops_clip = flops_clip + 2 * con - kv
-    line = {
-        "metric": "audio-sec/sec waveform->LLM embeds" if not train else "audio-sec/sec training step (frozen encoder fwd + Q-Former fwd/bwd)", "value": value, "unit": "audio-s/s", "n_gpus": world,
-        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": step_s * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: whisper-large-v3(-turbo) encoder + Qformer6L -> d_llm {w['d_llm']} token embeds, 30 s clips",
-                   "mode": args.mode, "cuda_graph": bool(args.graph and not train), "clips_per_gpu": n, "prompts": args.prompts, "seq_len": S_len, "l2": "working set >> 126 MB L2 (no flush needed)",
-                   "parallelism": f"clips sharded over {world} GPU(s), no data-path collective"},
-        "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": wave_host.numel() * 4 + ids_host.numel() * 8,
-                "d2h_bytes_per_step": out_host.numel() * 2, "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": launches,
-        "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "gemm_bf16_tn_2cta_kernel (per launch, averaged over the GEMM launches of one step)",
-                     "achieved": round(gemm_tflops, 1), "peak": tf_sust, "unit": "TFLOP/s",
-                     "frac": round(gemm_tflops / tf_sust, 4), "frac_of_burst_peak": round(gemm_tflops / tf_burst, 4), "traffic": traffic,
-                     "algorithmic_bytes": round(gm["bytes"] / max(gm["calls"], 1)), "launches_per_step": gm["calls"],
-                     "avg_launch_ms": round(gm["ms"] / max(gm["calls"], 1), 4), "flop_per_launch": round(gm["work"] / max(gm["calls"], 1)),
-                     "peak_kind": f"{peak_kind} sustained bf16 (cuBLAS under the power cap; burst {tf_burst})",
-                     "share_of_step": round(gm["ms"] / total_ms, 4)},
-        "step_tensor_frac": round(flops_clip * n / step_s / 1e12 / tf_sust, 4),
-        "kernels": fam,
-    }
+    return {"bound": "tensor", "kernel": "gemm_bf16_tn_2cta_kernel (per launch, averaged over the GEMM launches of one step)",
+            "achieved": round(gemm_tflops, 1), "peak": tf_sust, "unit": "TFLOP/s",
+            "frac": round(gemm_tflops / tf_sust, 4), "frac_of_burst_peak": round(gemm_tflops / tf_burst, 4), "traffic": traffic,
+            "traffic_source": traffic_note,
+            "algorithmic_bytes": round(gm["bytes"] / max(gm["calls"], 1)), "launches_per_step": gm["calls"],
+            "avg_launch_ms": round(gm["ms"] / max(gm["calls"], 1), 4), "flop_per_launch": round(gm["work"] / max(gm["calls"], 1)),
+            "peak_kind": f"{peak_kind} sustained bf16 (cuBLAS under the power cap; burst {tf_burst})",
+            "share_of_step": round(gm["ms"] / total_ms, 4)}
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import __graft_entry__
+    if rank == 0:
+        __graft_entry__.build()
+    if world > 1:
+        dist.barrier()
+    from desta_b200 import ops
+    from desta_b200.staging import WaveformStager
+
+    w = WORKLOADS[args.workload]
+    hbm_peak, tf_burst, tf_sust, peak_kind = measured_peaks()
+    model = build_installed_model(w, dev, seed=0)
+    perception = model.perception
+    table = model.llm_model.model.embed_tokens.weight
+
+    # =========================================================================================== forward (headline)
+    def forward_line(n):
+        S_len, B_prompts, positions, trans, ids_host = prompts_for(args, w, n, rank)
+        wave_host = synth_wave_batch(n, 1234 + rank).pin_memory()
+        wave_dev = wave_host.to(dev)
+        ids_dev = ids_host.to(dev)
+        out_host = torch.empty(B_prompts, S_len, w["d_llm"], dtype=torch.bfloat16).pin_memory()
+        perception.eval()
+        if args.graph:
+            perception.capture_graph(n)
+
+        def step_resident():
+            with torch.no_grad():
+                return model._prepare_inputs_for_llm(ids_dev, None, wave_dev, trans, positions)
+
+        d2h_stream = torch.cuda.Stream(dev)
+
+        def read_back(emb):
+            done = torch.cuda.Event()
+            done.record()
+            d2h_stream.wait_event(done)
+            with torch.cuda.stream(d2h_stream):
+                out_host.copy_(emb.detach(), non_blocking=True)
+            emb.record_stream(d2h_stream)
+
+        # ---- e2e_staged: pre-packed pinned slots, double-buffered H2D on a copy stream (scope row n1) ----
+        stager = WaveformStager(n, dev, slots=2)
+        for sl in range(2):
+            stager.fill(sl, wave_host.numpy())
+        st_state = {"k": 0, "primed": False}
+
+        def step_staged():
+            k = st_state["k"]
+            slot = k % 2
+            if not st_state["primed"]:
+                stager.submit(slot)
+                st_state["primed"] = True
+            stager.submit((k + 1) % 2)                      # next step's inputs: in flight during this step's kernels
+            wv, _ = stager.acquire(slot)
+            ii = ids_host.to(dev, non_blocking=True)
+            with torch.no_grad():
+                emb = model._prepare_inputs_for_llm(ii, None, wv, trans, positions)
+            stager.release(slot)
+            read_back(emb)
+            st_state["k"] = k + 1
+
+        # ---- e2e (public): processor(list of numpy clips) -> .to(device) -> _prepare_inputs_for_llm -> D2H ----
+        clips = [wave_host[i].numpy() for i in range(n)]    # what AudioSegment.samples / the dataset hand to the processor
+        model.processor.enable_pinned_staging(n, slots=3)
+        pub = {"next": None}
+
+        def pack():
+            pub["next"] = model.processor(clips, sampling_rate=16000, return_tensors="pt").input_features
+
+        def step_public():
+            if pub["next"] is None:
+                pack()
+            feats, pub["next"] = pub["next"], None
+            loader = threading.Thread(target=pack)          # the reference's DataLoader workers: next batch while this one computes
+            loader.start()
+            wv = feats.to(dev, non_blocking=True)
+            model.processor.release_after(feats)            # the pinned slot is reused only after this copy
+            ii = ids_host.to(dev, non_blocking=True)
+            with torch.no_grad():
+                emb = model._prepare_inputs_for_llm(ii, None, wv, trans, positions)
+            read_back(emb)
+            loader.join()
+
+        for _ in range(max(args.warmup, 3)):
+            step_resident()
+        sampler = ClockSampler(local)
+        sampler.start()
+        time.sleep(0.3)
+        l0 = ops.STATS["launches"] + ops.STATS.get("graph_kernels", 0)
+        ms, ms_local, t0, t1 = timed(step_resident, args.steps, world, dev)
+        launches = ops.STATS["launches"] + ops.STATS.get("graph_kernels", 0) - l0     # kernels executed, eagerly or by graph replay
+        clocks = sampler.stop(t0, t1)
+        ranks = rank_stats(ms_local / args.steps, world, dev)
+        # The part is power-capped: whichever region is timed second reads 1-2 % slower (same-box A/B with the order swapped:
+        # e2e / value = 0.986 vs 1.004).  Let the power governor settle, then give each e2e region the same warm-up.
+        torch.cuda.synchronize()
+        time.sleep(1.5)
+        for _ in range(max(args.warmup, 3)):
+            step_public()
+        ms_pub, _, _, _ = timed(step_public, args.steps, world, dev, (d2h_stream,))
+        torch.cuda.synchronize()
+        time.sleep(1.0)
+        for _ in range(max(args.warmup, 3)):
+            step_staged()
+        ms_st, _, _, _ = timed(step_staged, args.steps, world, dev, (d2h_stream, stager.copy_stream))
+
+        # one instrumented step (outside the timed regions): per-kernel-family device time with CUDA events
+        ops.start_profile()
+        step_resident()
+        prof = ops.stop_profile()
+        fam, gm, total_ms = family_table(prof)
+        traffic, traffic_note = committed_gemm_traffic(args.workload, n, False)
+        step_s = ms * 1e-3 / args.steps
+        h2d = wave_host.numel() * 4 + ids_host.numel() * 8
+        line = {
+            "metric": "audio-sec/sec waveform->LLM embeds", "value": 30.0 * n * world / step_s, "unit": "audio-s/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": step_s * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: whisper-large-v3(-turbo) encoder + Qformer6L -> d_llm {w['d_llm']} token embeds, 30 s clips",
+                       "mode": "forward", "cuda_graph": bool(args.graph), "clips_per_gpu": n, "prompts": args.prompts,
+                       "seq_len": S_len, "l2": "working set >> 126 MB L2 (no flush needed)",
+                       "parallelism": f"clips sharded over {world} GPU(s), no data-path collective"},
+            "e2e": {"value": 30.0 * n * world / (ms_pub * 1e-3 / args.steps), "unit": "audio-s/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": out_host.numel() * 2, "ms_per_step": ms_pub / args.steps,
+                    "path": "WaveformProcessor(list of numpy clips, pinned slots; next batch packed by a loader thread) -> .to(device) "
+                            "-> installed model._prepare_inputs_for_llm -> D2H of inputs_embeds"},
+            "e2e_staged": {"value": 30.0 * n * world / (ms_st * 1e-3 / args.steps), "unit": "audio-s/s", "h2d_bytes_per_step": h2d,
+                           "d2h_bytes_per_step": out_host.numel() * 2, "ms_per_step": ms_st / args.steps,
+                           "path": "pre-packed pinned slots (WaveformStager) -> _prepare_inputs_for_llm -> D2H"},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "rank_ms_per_step": ranks,
+            "roofline": roofline_of(gm, total_ms, traffic, traffic_note),
+            "step_tensor_frac": round(fwd_flops_per_clip(w) * n / step_s / 1e12 / tf_sust, 4),
+            "kernels": fam,
+        }
+        if args.check:
+            line["check"] = check_batch(model, wave_dev, ids_dev, trans, positions, n, w)
+        del stager, wave_dev, out_host
+        return line
+
+    # =========================================================================================== training (configs[4])
+    def train_line(n):
+        S_len, B_prompts, positions, trans, ids_host = prompts_for(args, w, n, rank)
+        wave_dev = synth_wave_batch(n, 4321 + rank).to(dev)
+        ids_dev = ids_host.to(dev)
+        g = torch.Generator(device=dev).manual_seed(11 + rank)
+        grad_emb = (0.01 * torch.randn(B_prompts, S_len, w["d_llm"], device=dev, generator=g)).to(torch.bfloat16)
+        perception.train()
+        perception._graph = None
+        from desta_b200.dist import GradBucket, GradSync
+        n_params = sum(p.numel() for p in perception.connector.parameters())
+
+        def make_step(sync):
+            bucket = GradBucket(list(perception.connector.parameters())) if (sync == "bucket" and world > 1) else None
+            perception.grad_sync = GradSync() if (sync == "overlap" and world > 1) else None
+
+            def train_step():
+                # frozen encoder forward + Q-Former forward/backward; the LLM's gradient w.r.t. inputs_embeds is synthetic
+                for prm in perception.connector.parameters():
+                    prm.grad = None
+                emb = model._prepare_inputs_for_llm(ids_dev, None, wave_dev, trans, positions)
+                emb.backward(grad_emb)
+                if bucket is not None:
+                    bucket.allreduce()      # same exchange as the reference's DDP: one averaged all-reduce of connector grads
+            return train_step
+
+        res = {}
+        for sync in (("none", args.grad_sync) if world > 1 else ("none",)):
+            fn = make_step(sync)
+            for _ in range(max(args.warmup, 3)):
+                fn()
+            ms, ms_local, _, _ = timed(fn, args.steps, world, dev)
+            res[sync] = (ms / args.steps, rank_stats(ms_local / args.steps, world, dev))
+            torch.cuda.synchronize()
+            time.sleep(0.5)
+        key = args.grad_sync if world > 1 else "none"
+        step_ms, ranks = res[key]
+        fn = make_step(key)
+        fn()
+        ops.start_profile()
+        fn()
+        prof = ops.stop_profile()
+        perception.grad_sync = None
+        fam, gm, total_ms = family_table(prof)
+        line = {
+            "metric": "audio-sec/sec training step (frozen encoder fwd + Q-Former fwd/bwd, connector gradients all-reduced)",
+            "value": 30.0 * n * world / (step_ms * 1e-3), "unit": "audio-s/s", "ms_per_step": step_ms, "n_gpus": world, "clips_per_gpu": n,
+            "scaling": "weak", "dtype": "bf16 (fp32 gradient arena)", "dropout": "BertConfig p = 0.1 (train mode, Philox)",
+            "rank_ms_per_step": ranks,
+            "comm": {"collective": "NCCL all-reduce (sum) of the fp32 connector-gradient arena, averaged like DDP" if world > 1 else "none (1 GPU)",
+                     "bytes_per_step": 4 * n_params if world > 1 else 0, "mode": key if world > 1 else "none",
+                     "ms_per_step_without_exchange": round(res["none"][0], 3),
+                     "exposed_ms": round(step_ms - res["none"][0], 3) if world > 1 else 0.0},
+            "roofline": roofline_of(gm, total_ms, None, "no capture for the training step"),
+            "step_tensor_frac": round(train_flops_per_clip(w) * n / (step_ms * 1e-3) / 1e12 / tf_sust, 4),
+            "kernels": fam,
+        }
+        perception.eval()
+        perception._train = {}
+        del wave_dev, grad_emb
+        return line
+
+    if args.mode == "train":
+        line = train_line(args.clips)
+        line.update({"steps": args.steps, "warmup": max(args.warmup, 3), "higher_is_better": True, "vs_baseline": None, "data": "synthetic",
+                     "config": {"workload": args.workload, "mode": "train", "clips_per_gpu": args.clips}})
+    else:
+        line = forward_line(args.clips)
+        if not args.no_train:
+            perception._ws = {}
+            torch.cuda.empty_cache()
+            line["train"] = train_line(args.train_clips)
     if rank == 0 and world == 1:
-        line["upstream_n3"] = decode_resample_rates(n, dev)
+        line["upstream_n3"] = decode_resample_rates(min(args.clips, 64), dev)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        rate, dt, threads = cpu_reference_rate(args.workload, args.cpu_clips)
-        line["cpu_baseline"] = {"value": rate, "unit": "audio-s/s", "cores": threads, "kind": "port",
-                                "sample": f"{args.cpu_clips} clips, 1 step, oracle/ fp32 on host cores ({dt:.1f} s)"}
+        rate, dt, threads, kind, note = cpu_arm(args.workload, args.cpu_clips)
+        line["cpu_baseline"] = {"value": rate, "unit": "audio-s/s", "cores": threads, "kind": kind,
+                                "sample": f"{args.cpu_clips} clips, 1 step, " + ("the unmodified reference (baseline/_ref) " if kind == "reference" else "oracle/ port ")
+                                          + f"fp32 on the host cores ({dt:.1f} s)"}
+        if note:
+            line["cpu_baseline"]["note"] = note
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def check_batch(model, wave_dev, ids_dev, trans, positions, n, w):
+    """Outside the timed regions: the benchmark batch itself is output-checked.  Clip i inside the batch must equal its solo
+    run bit for bit (clips are independent units), for the first, a middle and the last clip - an offset that wraps at
+    32 bits (the K/V buffer of 64 clips has 5.9e9 elements) shows up here and nowhere at small batches."""
+    p = model.perception
+    with torch.no_grad():
+        full, _ = p(input_features=wave_dev)
+        full = full.clone()
+        probe = sorted({0, n // 2 - 1 if n > 1 else 0, n - 1})
+        ok = True
+        for i in probe:
+            solo, _ = p(input_features=wave_dev[i:i + 1].contiguous())
+            ok = ok and bool(torch.equal(solo[0], full[i]))
+        finite = bool(torch.isfinite(full).all())
+        emb = model._prepare_inputs_for_llm(ids_dev, None, wave_dev, trans, positions)
+        b, s = positions[-1]
+        splice_ok = bool(torch.equal(emb[b, s:s + w["prompt_size"]], full[n - 1].to(torch.bfloat16)))
+    return {"clips_equal_solo_run_bitwise": ok, "probe": probe, "finite": finite, "splice_rows_are_bf16_of_features": splice_ok}
 
 
 def main():
@@ -410,15 +660,18 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="large_v3_llama", choices=sorted(WORKLOADS))
     ap.add_argument("--clips", type=int, default=64, help="clips per GPU per step")
+    ap.add_argument("--train-clips", type=int, default=32, help="clips per GPU of the training step reported under `train`")
     ap.add_argument("--prompts", default="single", choices=["single", "multi"],
                     help="single = one clip per prompt, S 128; multi = 4 clips per prompt with transcripts, S 512")
     ap.add_argument("--mode", default="forward", choices=["forward", "train"],
-                    help="forward = BASELINE.json configs[1] (default); train = configs[4] step (connector fwd+bwd, grad all-reduce)")
+                    help="forward = BASELINE.json configs[1] (default; the line also carries configs[4] under `train`); train = only configs[4]")
+    ap.add_argument("--no-train", action="store_true", help="forward mode: skip the `train` object")
     ap.add_argument("--cpu-clips", type=int, default=8, help="clips in the bounded cpu_baseline sample (~10 s of CPU work on 16 cores)")
     ap.add_argument("--ref-clips", type=int, default=2, help="clips per step of the --impl reference arm")
     ap.add_argument("--grad-sync", default="overlap", choices=["overlap", "bucket"],
                     help="training on N > 1 GPUs: all-reduce overlapped with the backward (default) or one flat bucket after it")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-check", dest="check", action="store_false", help="skip the output check of the benchmark batch")
     ap.add_argument("--graph", action="store_true", help="forward mode: replay log-mel + encoder + connector as one CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":

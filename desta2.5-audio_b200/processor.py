@@ -72,6 +72,29 @@ class WaveformProcessor:
     def __init__(self, wrapped=None, sampling_rate: int = SAMPLING_RATE):
         self._wrapped = wrapped
         self.sampling_rate = sampling_rate
+        self._slots = None          # optional pinned output slots, see enable_pinned_staging
+
+    def enable_pinned_staging(self, n_clips: int, slots: int = 3):
+        """Pack batches of up to `n_clips` clips straight into rotating PINNED host slots (main process only: DataLoader
+        workers have no CUDA context and keep the pageable default).  `input_features` is then a pinned tensor, so the
+        caller's `.to(device, non_blocking=True)` (modeling_desta25.py:1571) is a genuinely asynchronous copy and no
+        intermediate pageable [N, 480000] array is allocated per call.  A slot is reused `slots` calls later; a caller that
+        enqueues work without ever synchronising should tell the processor when the slot's copy is ordered with
+        `release_after(input_features)` - the slot is then not overwritten before that point of the stream has passed."""
+        assert torch.cuda.is_available(), "pinned staging needs a CUDA context"
+        self._slots = [dict(wave=torch.zeros(n_clips, N_SAMPLES, dtype=torch.float32).pin_memory(),
+                            lens=torch.zeros(n_clips, dtype=torch.int32).pin_memory(), event=None) for _ in range(slots)]
+        self._next_slot = 0
+
+    def release_after(self, input_features, stream=None):
+        """Record an event on `stream` (default: current) after which the pinned slot behind `input_features` may be reused."""
+        if self._slots is None:
+            return
+        for sl in self._slots:
+            if sl["wave"].data_ptr() == input_features.data_ptr():
+                ev = torch.cuda.Event()
+                ev.record(stream if stream is not None else torch.cuda.current_stream())
+                sl["event"] = ev
 
     def __call__(self, raw_speech=None, sampling_rate=None, return_tensors="pt", **kwargs):
         if raw_speech is None:
@@ -85,6 +108,16 @@ class WaveformProcessor:
         on_device = _device_batch(raw_speech) if return_tensors == "pt" else None
         if on_device is not None:
             return _Features(input_features=on_device[0], num_samples=on_device[1])
+        if self._slots is not None and return_tensors == "pt":
+            n = len(raw_speech) if isinstance(raw_speech, (list, tuple)) or getattr(raw_speech, "ndim", 1) == 2 else 1
+            sl = self._slots[self._next_slot]
+            if n <= sl["wave"].shape[0]:
+                self._next_slot = (self._next_slot + 1) % len(self._slots)
+                if sl["event"] is not None:
+                    sl["event"].synchronize()          # the copy that read this slot has been passed by the GPU
+                    sl["event"] = None
+                wave, lengths = pad_or_truncate_batch(raw_speech, out=sl["wave"].numpy(), lengths=sl["lens"].numpy())
+                return _Features(input_features=sl["wave"][:len(wave)], num_samples=sl["lens"][:len(wave)])
         wave, lengths = pad_or_truncate_batch(raw_speech)
         feats = torch.from_numpy(wave) if return_tensors == "pt" else wave
         return _Features(input_features=feats, num_samples=torch.from_numpy(lengths) if return_tensors == "pt" else lengths)
