@@ -403,13 +403,24 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
     import __graft_entry__
-    if rank == 0:
-        __graft_entry__.build()
     if world > 1:
-        dist.barrier()
+        # NCCL prints its version banner on stdout at communicator creation: keep stdout for the ONE JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            if rank == 0:
+                __graft_entry__.build()
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
+    else:
+        __graft_entry__.build()
     from desta_b200 import ops
     from desta_b200.staging import WaveformStager
 
