@@ -30,6 +30,14 @@
 // the TMEM registers - no FFMA, no running max (a row sum above 2^20 triggers the same lazy rescale).  The shift is a
 // per-row constant, so its bf16 rounding cancels exactly in the softmax; it only changes at the first block and at
 // rescale events, and every thread remembers which shift each in-flight S block was computed with.
+// Start of a tile: S_0 is issued with a zero shift; the softmax threads publish the row maxima of block 0 as the shift
+// BEFORE they start its exponentials (mbarrier shift_ready), and only then are S_1 and S_2 issued - their latency hides
+// behind block 0's exponentials, and every block but the first runs the lean step (round 2: 1.059 -> 0.997 ms per encoder
+// launch together with the items below).  The ragged last key block (1500 = 23 * 64 + 28) runs the lean step with selects
+// and skips the exponentials of a fully padded 32-key half.  One of every 8 (or 4) exponentials is evaluated on the FMA pipe
+// (poly_exp2): the XU pipe is the floor at head_dim 64, and profiles/r2_poly_attention.md shows where the issue slots run
+// out (12.5-25 %: 0.995 ms; 37.5 %: 1.07 ms; 50 %: 1.16 ms).  ex2.approx.f16x2 is no shortcut: MUFU.EX2.F16x2 issues
+// every 16 cycles per warp, i.e. the same 8 cycles per exponential (tools/issue_bench.cu).
 #include <math.h>
 
 #include "common.cuh"
@@ -86,15 +94,56 @@ __device__ long long g_attn_tl[12][32];
 #define TRACE_FLUSH()
 #endif
 
-// UNIT-mode hot path: the scores arrive shifted (S' = s - m, log2 domain) -> p = ex2(S'), bf16 pack, row sum.  Nothing else.
-__device__ __forceinline__ void softmax_chunk_unit(const uint32_t (&v)[32], uint32_t (&pk)[16], uint64_t& lacc) {
+// 2^x on the FMA pipe (no MUFU): round-to-nearest split x = n + f with the 1.5 * 2^23 magic add (n sits in the low
+// mantissa bits of t), cubic minimax polynomial for 2^f on [-0.5, 0.5] (max relative error 7.5e-5, a tenth of the bf16
+// rounding of P), exponent insertion by an integer shift-add.  x <= -126 flushes to ~0 like ex2.approx.ftz; x up to +127 is
+// exact in range (the lazy rescale keeps x below 2^40's exponent).
+__device__ __forceinline__ float poly_exp2(float x) {
+  x = fmaxf(x, -126.0f);
+  const float t = x + 12582912.0f;
+  const float f = x - (t - 12582912.0f);
+  float p = fmaf(f, 5.517132208e-02f, 2.426105440e-01f);
+  p = fmaf(p, f, 6.932609677e-01f);
+  p = fmaf(p, f, 9.999281168e-01f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
+// Which of every 8 consecutive exponentials are evaluated by poly_exp2 instead of MUFU.EX2 (bit e = element e of the octet).
+// The XU pipe (16 ex2 / clk / SM) is the floor of this kernel at head_dim 64; every exponential moved to the FMA pipe
+// shortens that floor as long as the issue slots last (profiles/r2_issue_bench.txt: 32 FFMA hide beside 8 MUFU).
+#ifndef DESTA_ATTN_POLY_MASK
+#define DESTA_ATTN_POLY_MASK 0x88
+#endif
+template <int E>
+__device__ __forceinline__ float exp2_sel(float x) {
+  return ((DESTA_ATTN_POLY_MASK >> (E & 7)) & 1) ? poly_exp2(x) : fast_exp2(x);
+}
+
+// UNIT-mode hot path: the scores arrive shifted (S' = s - m, log2 domain) -> p = 2^S', bf16 pack, row sum.  Nothing else.
+// The row sum runs as fma.rn.f32x2 with a unit multiplier on two accumulator pairs (profiles/r2_issue_bench.txt: FFMA2
+// issues every 2.25 cycles, FADD2 every 3.4).  MASKED (ragged last key block): columns >= nvalid contribute p = 0.
+template <bool MASKED>
+__device__ __forceinline__ void softmax_chunk_unit(const uint32_t (&v)[32], uint32_t (&pk)[16], uint64_t& lacc0, uint64_t& lacc1,
+                                                   int nvalid) {
+  const uint64_t one2 = pack_f32x2(1.0f, 1.0f);
 #pragma unroll
-  for (int i = 0; i < 32; i += 4) {
-    const float p0 = fast_exp2(__uint_as_float(v[i])), p1 = fast_exp2(__uint_as_float(v[i + 1]));
-    const float p2 = fast_exp2(__uint_as_float(v[i + 2])), p3 = fast_exp2(__uint_as_float(v[i + 3]));
-    lacc = fadd2(lacc, fadd2(pack_f32x2(p0, p1), pack_f32x2(p2, p3)));
+  for (int i = 0; i < 32; i += 8) {
+    float p0 = exp2_sel<0>(__uint_as_float(v[i])), p1 = exp2_sel<1>(__uint_as_float(v[i + 1]));
+    float p2 = exp2_sel<2>(__uint_as_float(v[i + 2])), p3 = exp2_sel<3>(__uint_as_float(v[i + 3]));
+    float p4 = exp2_sel<4>(__uint_as_float(v[i + 4])), p5 = exp2_sel<5>(__uint_as_float(v[i + 5]));
+    float p6 = exp2_sel<6>(__uint_as_float(v[i + 6])), p7 = exp2_sel<7>(__uint_as_float(v[i + 7]));
+    if (MASKED) {
+      p0 = i < nvalid ? p0 : 0.f; p1 = i + 1 < nvalid ? p1 : 0.f; p2 = i + 2 < nvalid ? p2 : 0.f; p3 = i + 3 < nvalid ? p3 : 0.f;
+      p4 = i + 4 < nvalid ? p4 : 0.f; p5 = i + 5 < nvalid ? p5 : 0.f; p6 = i + 6 < nvalid ? p6 : 0.f; p7 = i + 7 < nvalid ? p7 : 0.f;
+    }
+    lacc0 = ffma2(pack_f32x2(p0, p1), one2, lacc0);
+    lacc1 = ffma2(pack_f32x2(p2, p3), one2, lacc1);
+    lacc0 = ffma2(pack_f32x2(p4, p5), one2, lacc0);
+    lacc1 = ffma2(pack_f32x2(p6, p7), one2, lacc1);
     pk[i >> 1] = pack_bf16(p0, p1);
     pk[(i >> 1) + 1] = pack_bf16(p2, p3);
+    pk[(i >> 1) + 2] = pack_bf16(p4, p5);
+    pk[(i >> 1) + 3] = pack_bf16(p6, p7);
   }
 }
 
@@ -192,7 +241,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* s_full = kv_empty + AT_STAGES;              // [3]  S_j landed in buffer j % 3
   uint64_t* p_ready = s_full + AT_SBUF;                 // [3]  P_j written over S_j (128 arrivals), O rescaled if needed
   uint64_t* pv_done = p_ready + AT_SBUF;                // [3]  P_j V_j accumulated into O
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + AT_SBUF);
+  uint64_t* shift_ready = pv_done + AT_SBUF;             // 1   UNIT: every row's first reference sits in the shift operand
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(shift_ready + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * AT_BQ, head = blockIdx.y, batch = blockIdx.z;
@@ -214,7 +264,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (UNIT) {
     // un-swizzled K-major operand tiles ("interleaved" canonical layout): core matrix = 8 rows x 16 B stored contiguously,
     // 8-row groups SBO = 128 B apart, the two 16-byte K chunks LBO = rows*16 B apart.  Shift operand: all zero for now
-    // (blocks 0..2 are issued before any row max is known); ones operand: element [key][0] = 1.
+    // (block 0 is issued before any row max is known); ones operand: element [key][0] = 1.
     uint4* z = reinterpret_cast<uint4*>(sAx);
     for (int i = threadIdx.x; i < (AT_AX_BYTES + AT_BX_BYTES) / 16; i += blockDim.x) {
       const bool ones_chunk0 = i >= AT_AX_BYTES / 16 && i < AT_AX_BYTES / 16 + AT_BKV;      // K chunk 0 of the ones tile
@@ -227,6 +277,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     mbar_init(q_full, 1);
     for (int i = 0; i < AT_STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
     for (int i = 0; i < AT_SBUF; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 128); mbar_init(&pv_done[i], 1); }
+    mbar_init(shift_ready, 128);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<AT_TMEM_COLS>(tmem_slot);
@@ -279,7 +330,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     };
     mbar_wait(q_full, 0);
     TRACE_T0();
-    for (int j = 0; j < AT_SBUF && j < n_kv; ++j) issue_qk(j);
+    if (UNIT) {
+      // S_0 with a zero shift; S_1 and S_2 only once the softmax threads have put the row maxima of block 0 into the shift
+      // operand (a few hundred cycles after S_0 lands, hidden behind the exponentials of block 0), so that every block but
+      // the first runs the lean step.
+      issue_qk(0);
+      if (n_kv > 1) {
+        mbar_wait(shift_ready, 0);
+        tcgen05_fence_after();
+        for (int j = 1; j < AT_SBUF && j < n_kv; ++j) issue_qk(j);
+      }
+    } else {
+      for (int j = 0; j < AT_SBUF && j < n_kv; ++j) issue_qk(j);
+    }
     for (int j = 0; j < n_kv; ++j) {
       const int st = j % AT_STAGES, b = j % AT_SBUF;
       { TRACE_T0(); mbar_wait_sleep(&p_ready[b], (j / AT_SBUF) & 1); TRACE_ADD(1); }     // P_j in TMEM (over S_j), O rescaled if needed
@@ -398,6 +461,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           m0 = max3(m0, (32 + i < kv_valid) ? __uint_as_float(cb[i]) : -INFINITY, (33 + i < kv_valid) ? __uint_as_float(cb[i + 1]) : -INFINITY);
         }
         m_ref = UNIT ? bf16_round(m0) : m0 * c;
+        if (UNIT) {
+          // nothing reads the shift operand yet (S_1, S_2 are issued behind shift_ready): publish the row's reference now
+          *ax_elem = __float2bfloat16_rn(-m_ref);
+          fence_proxy_async_smem();
+          sh_cur = bk1 = bk2 = m_ref;
+          mbar_arrive(shift_ready);
+        }
       }
       // exp pass against the reference of the PREVIOUS blocks; the block max comes out of the same pass
       const float off = m_ref - baked;                  // p = exp2(c * S - off)
@@ -419,7 +489,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       // reference raised (FA-style lazy rescale; the common case never takes the slow path)
       const bool need = (m_blk - m_ref) > 20.0f;
       if (__builtin_expect(__any_sync(0xffffffffu, need), 0)) rescale(j, ca, cb, tS, baked, kv_valid, grp0, m_blk, l_blk, false);
-      else if (UNIT && j == 0) set_shift(0, m_ref);     // the first reference becomes the shift of blocks 3, 4, ...
       l_run += l_blk;
     };
     // UNIT fast step: a full block whose S already carries this row's current reference as shift (S' = s - m_ref):
@@ -427,34 +496,41 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // sends the warp through the same rescale as the general step; below that bf16 P / fp32 l, O lose nothing.
     // `tracked` = false inside the fast loop (all three slots equal the current shift there, nothing to maintain).
     // Returns true (warp-uniform) if the block had to raise the reference.
-    auto step_unit = [&](int j, uint32_t (&ca)[32], uint32_t (&cb)[32], uint32_t (&na)[32], bool tracked) -> bool {
+    auto step_unit = [&](int j, uint32_t (&ca)[32], uint32_t (&cb)[32], uint32_t (&na)[32], bool tracked, int kv_valid) -> bool {
       const uint32_t tS = tmem_base + (j % AT_SBUF) * AT_BKV + lane_off;
       TL(1 + warp, j);
       tmem_wait_ld();                                   // ca
       reg_fence32(ca);
       tmem_ld_32x32(tS + 32, cb);
-      uint64_t lacc = 0;                                // (0.f, 0.f)
+      uint64_t lacc0 = 0, lacc1 = 0;                    // (0.f, 0.f)
       uint32_t pk[16];
-      softmax_chunk_unit(ca, pk, lacc);
+      if (kv_valid >= 32) softmax_chunk_unit<false>(ca, pk, lacc0, lacc1, 32);
+      else softmax_chunk_unit<true>(ca, pk, lacc0, lacc1, kv_valid);
       if (tracked) announce_prev(j); else { tmem_wait_st(); tcgen05_fence_before(); mbar_arrive(&p_ready[(j - 1) % AT_SBUF]); }
       tmem_st_32x16(tS, pk);
       tmem_wait_ld();                                   // cb
       reg_fence32(cb);
       request_next(j, na);
-      softmax_chunk_unit(cb, pk, lacc);
+      if (kv_valid >= AT_BKV) softmax_chunk_unit<false>(cb, pk, lacc0, lacc1, 32);
+      else if (kv_valid > 32) softmax_chunk_unit<true>(cb, pk, lacc0, lacc1, kv_valid - 32);
+      else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pk[i] = 0u;        // ragged block with <= 32 keys: no exponentials for the padded half
+      }
       tmem_st_32x16(tS + 16, pk);
-      float la, lb;
-      unpack_f32x2(lacc, la, lb);
-      float l_blk = la + lb;
+      float la, lb, lc, ld;
+      unpack_f32x2(lacc0, la, lb);
+      unpack_f32x2(lacc1, lc, ld);
+      float l_blk = (la + lb) + (lc + ld);
       const bool need = __any_sync(0xffffffffu, !(l_blk <= 1.0995116e12f));
       if (__builtin_expect(need, 0)) {
         float mx = -INFINITY;                           // the fast pass keeps no maximum: take it from the registers
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          mx = max3(mx, __uint_as_float(ca[i]), __uint_as_float(ca[i + 1]));
-          mx = max3(mx, __uint_as_float(cb[i]), __uint_as_float(cb[i + 1]));
+          mx = max3(mx, (i < kv_valid) ? __uint_as_float(ca[i]) : -INFINITY, (i + 1 < kv_valid) ? __uint_as_float(ca[i + 1]) : -INFINITY);
+          mx = max3(mx, (32 + i < kv_valid) ? __uint_as_float(cb[i]) : -INFINITY, (33 + i < kv_valid) ? __uint_as_float(cb[i + 1]) : -INFINITY);
         }
-        rescale(j, ca, cb, tS, m_ref, AT_BKV, 0, mx + m_ref, l_blk, !tracked);
+        rescale(j, ca, cb, tS, m_ref, kv_valid, 0, mx + m_ref, l_blk, !tracked);
       }
       l_run += l_blk;
       return need;
@@ -464,7 +540,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if (!UNIT) return false;
       const int b = j % AT_SBUF;
       const float baked = b == 0 ? bk0 : (b == 1 ? bk1 : bk2);
-      return a.Tk - j * AT_BKV >= AT_BKV && __all_sync(0xffffffffu, baked == m_ref);
+      return __all_sync(0xffffffffu, baked == m_ref) != 0;
     };
     uint32_t ra[32], rb[32], rc[32];
     TRACE_T0();
@@ -473,10 +549,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tmem_ld_32x32(tmem_base + lane_off, ra);
     int j = 0;
     if (UNIT) {
-      // blocks 0..2 were issued before any row max was known: general steps (shift 0 baked in)
+      // block 0 was issued before any row max was known: general step (shift 0 baked in); it publishes the shift that
+      // S_1, S_2, ... are computed with
       step(0, ra, rb, rc);
-      if (n_kv > 1) step(1, rc, rb, ra);
-      if (n_kv > 2) step(2, ra, rb, rc);
+      if (n_kv > 1) { if (unit_ready(1)) step_unit(1, rc, rb, ra, true, a.Tk - AT_BKV); else step(1, rc, rb, ra); }
+      if (n_kv > 2) { if (unit_ready(2)) step_unit(2, ra, rb, rc, true, a.Tk - 2 * AT_BKV); else step(2, ra, rb, rc); }
       j = n_kv < 3 ? n_kv : 3;
       // fast loop over the full blocks: two steps per iteration (register sets alternate), no per-step bookkeeping.
       // Entered only if every row of the warp has all in-flight blocks on its current reference; left on a rescale.
@@ -484,15 +561,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       bool fast_ok = __all_sync(0xffffffffu, bk0 == m_ref && bk1 == m_ref && sh_cur == m_ref);
       if (fast_ok) bk2 = sh_cur;                        // S_5 is issued behind this thread's next arrival (p_ready[2])
       while (fast_ok && j + 1 < n_full) {               // j is odd here
-        if (step_unit(j, rc, rb, ra, false)) { j += 1; break; }
-        if (step_unit(j + 1, ra, rb, rc, false)) { j += 2; break; }
+        if (step_unit(j, rc, rb, ra, false, AT_BKV)) { j += 1; break; }
+        if (step_unit(j + 1, ra, rb, rc, false, AT_BKV)) { j += 2; break; }
         j += 2;
       }
     }
     if (UNIT) {
       for (; j < n_kv; ++j) {                           // blocks after a rescale inside the fast loop, ragged last block
-        if (j & 1) { if (unit_ready(j)) step_unit(j, rc, rb, ra, true); else step(j, rc, rb, ra); }
-        else { if (unit_ready(j)) step_unit(j, ra, rb, rc, true); else step(j, ra, rb, rc); }
+        const int kvv = a.Tk - j * AT_BKV;
+        if (j & 1) { if (unit_ready(j)) step_unit(j, rc, rb, ra, true, kvv); else step(j, rc, rb, ra); }
+        else { if (unit_ready(j)) step_unit(j, ra, rb, rc, true, kvv); else step(j, ra, rb, rc); }
       }
     } else {
       for (; j < n_kv; j += 2) {

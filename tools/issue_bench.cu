@@ -9,7 +9,7 @@
 using namespace desta;
 
 enum { S_MUFU, S_FFMA, S_FFMA2, S_FADD2, S_FMNMX3, S_F2FP, S_HMNMX2, S_LEA, S_MUFU_FFMA, S_MUFU_2FFMA, S_MUFU_FFMA2, S_MUFU_F2FP,
-       S_MUFU_FMNMX3, S_MUFU_4FFMA, S_SOFTMAX_NOW, S_SOFTMAX_NEW, S_COUNT };
+       S_MUFU_FMNMX3, S_MUFU_4FFMA, S_SOFTMAX_NOW, S_SOFTMAX_NEW, S_EX2_H2, S_EX2_BF2, S_CVT_H2, S_HADD2, S_EX2H2_BODY, S_COUNT };
 
 template <int S>
 __global__ void __launch_bounds__(512) k(float* out, int iters, long long* cyc) {
@@ -42,6 +42,10 @@ __global__ void __launch_bounds__(512) k(float* out, int iters, long long* cyc) 
       if (S == S_F2FP || S == S_MUFU_F2FP) { h[i] = pack_bf16(__uint_as_float(h[i]), __uint_as_float(h[(i + 1) & 7])); }
       if (S == S_HMNMX2) asm volatile("max.bf16x2 %0, %0, %1;" : "+r"(h[i]) : "r"(h[(i + 1) & 7]));
       if (S == S_LEA) h[i] = (h[i] << 23) + h[(i + 1) & 7];
+      if (S == S_EX2_H2) asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(h[i]));
+      if (S == S_EX2_BF2) asm volatile("ex2.approx.ftz.bf16x2 %0, %0;" : "+r"(h[i]));
+      if (S == S_CVT_H2) asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h[i]) : "f"(__uint_as_float(h[i])), "f"(__uint_as_float(h[(i + 1) & 7])));
+      if (S == S_HADD2) asm volatile("add.rn.f16x2 %0, %0, %1;" : "+r"(h[i]) : "r"(h[(i + 1) & 7]));
     }
     if (S == S_SOFTMAX_NOW) {
       // per 4 elements as attention.cu does today: 2 max3, 2 FFMA2, 4 ex2, 2 FADD2, 2 F2FP  (x2 to cover 8 elements)
@@ -59,6 +63,25 @@ __global__ void __launch_bounds__(512) k(float* out, int iters, long long* cyc) 
         h[2 * g + 1] = pack_bf16(p2, p3);
         x[i] = p0 - 1.5f; x[i + 1] = p1 - 1.5f; x[i + 2] = p2 - 1.5f; x[i + 3] = p3 - 1.5f;   // loop-carried (4 extra FADD, see NEW too)
       }
+    }
+    if (S == S_EX2H2_BODY) {
+      // 8 elements: 4 cvt f32x2->f16x2, 4 ex2.f16x2, 3 add.f16x2 (sum of 8 in two halves), row sum to fp32 (2 cvt + 1 ffma2)
+      uint32_t e[4];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(e[g]) : "f"(x[2 * g + 1]), "f"(x[2 * g]));
+        asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(e[g]));
+        h[g] = e[g];
+      }
+      uint32_t s01, s23, s4;
+      asm volatile("add.rn.f16x2 %0, %1, %2;" : "=r"(s01) : "r"(e[0]), "r"(e[1]));
+      asm volatile("add.rn.f16x2 %0, %1, %2;" : "=r"(s23) : "r"(e[2]), "r"(e[3]));
+      asm volatile("add.rn.f16x2 %0, %1, %2;" : "=r"(s4) : "r"(s01), "r"(s23));
+      float f0, f1;
+      asm volatile("{.reg .b16 lo, hi; mov.b32 {lo, hi}, %2; cvt.f32.f16 %0, lo; cvt.f32.f16 %1, hi;}" : "=f"(f0), "=f"(f1) : "r"(s4));
+      q[0] = ffma2(pack_f32x2(f0, f1), a2, q[0]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] = x[i] * 0.999f - 0.01f;   // loop-carried (8 FFMA)
     }
     if (S == S_SOFTMAX_NEW) {
       // proposed: 4 ex2, 2 F2FP, 1 max.bf16x2 per 4 elements (shift folded into the MMA, row sum from a ones column)
@@ -86,7 +109,7 @@ __global__ void __launch_bounds__(512) k(float* out, int iters, long long* cyc) 
 static const char* NAMES[S_COUNT] = {"8 MUFU.EX2", "8 FFMA", "8 FFMA2", "8 FADD2", "8 FMNMX3 (+8 FMUL)", "8 F2FP.BF16", "8 HMNMX2.BF16",
                                      "8 SHL+IADD (LEA)", "8 MUFU + 8 FFMA", "8 MUFU + 16 FFMA", "8 MUFU + 8 FFMA2", "8 MUFU + 8 F2FP",
                                      "8 MUFU + 8 FMNMX3 (+8 FMUL)", "8 MUFU + 32 FFMA", "softmax body today (8 elems, +8 FADD)",
-                                     "softmax body proposed (8 elems, +8 FADD)"};
+                                     "softmax body proposed (8 elems, +8 FADD)", "8 MUFU.EX2.F16x2 (16 exps)", "8 MUFU.EX2.BF16x2 (16 exps)", "8 cvt.rn.f16x2.f32", "8 HADD2.F16", "f16x2 softmax body (8 elems, +8 FFMA)"};
 
 template <int S>
 static void run(float* o, long long* c) {
@@ -108,5 +131,6 @@ int main() {
   run<S_MUFU>(o, c); run<S_FFMA>(o, c); run<S_FFMA2>(o, c); run<S_FADD2>(o, c); run<S_FMNMX3>(o, c); run<S_F2FP>(o, c);
   run<S_HMNMX2>(o, c); run<S_LEA>(o, c); run<S_MUFU_FFMA>(o, c); run<S_MUFU_2FFMA>(o, c); run<S_MUFU_4FFMA>(o, c);
   run<S_MUFU_FFMA2>(o, c); run<S_MUFU_F2FP>(o, c); run<S_MUFU_FMNMX3>(o, c); run<S_SOFTMAX_NOW>(o, c); run<S_SOFTMAX_NEW>(o, c);
+  run<S_EX2_H2>(o, c); run<S_EX2_BF2>(o, c); run<S_CVT_H2>(o, c); run<S_HADD2>(o, c); run<S_EX2H2_BODY>(o, c);
   return 0;
 }
