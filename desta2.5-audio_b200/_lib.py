@@ -10,7 +10,9 @@ LIB_PATH = os.environ.get("DESTA_B200_LIB") or os.path.join(HERE, "libdesta_b200
 class GemmEpilogue(Structure):
     _fields_ = [("out_f32", c_void_p), ("ld_f32", c_int), ("out_bf16", c_void_p), ("ld_bf16", c_int),
                 ("bias", c_void_p), ("resid", c_void_p), ("ld_resid", c_int), ("pos", c_void_p), ("pos_rows", c_int),
-                ("scale", c_float), ("scale_cols", c_int), ("gelu", c_int)]
+                ("scale", c_float), ("scale_cols", c_int), ("gelu", c_int),
+                ("ln_stats_out", c_void_p), ("ln_stats_in", c_void_p), ("ln_groups", c_int), ("ln_cols", c_int),
+                ("ln_eps", c_float), ("ln_colsum", c_void_p)]
 
 
 class Dropout(Structure):
@@ -26,7 +28,7 @@ class Dims(Structure):
 
 class EncLayer(Structure):
     _fields_ = [(n, c_void_p) for n in ("ln1_w", "ln1_b", "qkv_w", "qkv_b", "o_w", "o_b", "ln2_w", "ln2_b", "fc1_w", "fc1_b",
-                                        "fc2_w", "fc2_b")]
+                                        "fc2_w", "fc2_b", "qkv_w_ln", "qkv_s", "qkv_c", "fc1_w_ln", "fc1_s", "fc1_c")]
 
 
 class EncoderWeights(Structure):

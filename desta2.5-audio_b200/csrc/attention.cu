@@ -112,7 +112,7 @@ __device__ __forceinline__ float poly_exp2(float x) {
 // The XU pipe (16 ex2 / clk / SM) is the floor of this kernel at head_dim 64; every exponential moved to the FMA pipe
 // shortens that floor as long as the issue slots last (profiles/r2_issue_bench.txt: 32 FFMA hide beside 8 MUFU).
 #ifndef DESTA_ATTN_POLY_MASK
-#define DESTA_ATTN_POLY_MASK 0x88
+#define DESTA_ATTN_POLY_MASK 0x08
 #endif
 template <int E>
 __device__ __forceinline__ float exp2_sel(float x) {

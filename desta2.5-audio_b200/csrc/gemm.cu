@@ -321,6 +321,7 @@ extern "C" int desta_gemm_bf16(const void* A, int lda, const void* W, int ldw, i
   static int force_1cta = -1;
   if (force_1cta < 0) { const char* e = getenv("DESTA_GEMM_1CTA"); force_1cta = (e && e[0] == '1') ? 1 : 0; }
   if (!force_1cta && M > 128) return launch_gemm_2cta(A, lda, W, ldw, M, N, K, ep, (cudaStream_t)stream);
+  if (ep->ln_stats_out || ep->ln_stats_in) { set_error("desta_gemm_bf16: the LayerNorm hand-over needs M > 128 (CTA-pair kernel)"); return DESTA_ERR_ARG; }
   CUtensorMap tmA, tmB;
   if (make_tmap_2d_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM, BK)) return DESTA_ERR_CUDA;
   if (make_tmap_2d_bf16(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, BN, BK)) return DESTA_ERR_CUDA;

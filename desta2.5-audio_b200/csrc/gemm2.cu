@@ -25,7 +25,7 @@ constexpr int EPI_BF16 = 0, EPI_F32 = 1;
 __host__ __device__ constexpr int stages_of(int mode) { return 5; }
 __host__ __device__ constexpr int staging_of(int mode) { return 2 * 2048; }
 constexpr int BAR_BYTES = 512;
-__host__ __device__ constexpr int smem_of(int mode) { return stages_of(mode) * STAGE_BYTES + EPI_WARPS * staging_of(mode) + 1024 + BAR_BYTES + EPI_WARPS * 512; }
+__host__ __device__ constexpr int smem_of(int mode) { return stages_of(mode) * STAGE_BYTES + EPI_WARPS * staging_of(mode) + 1024 + BAR_BYTES + EPI_WARPS * 1024; }
 }  // namespace g2
 
 struct Gemm2Args {
@@ -38,6 +38,12 @@ struct Gemm2Args {
   const float* pos; int pos_rows;
   float scale; int scale_cols;
   int gelu;
+  // fused LayerNorm hand-over (see desta_gemm_epilogue): EPI_F32 emits per-row partial (sum, sum of squares) of its final
+  // output per 128-column group; EPI_BF16 applies  rstd * (acc - mean * colsum[n]) + bias[n]  with the row statistics of
+  // the tensor A was copied from (A = bf16 of the un-normalised rows, W carries the LayerNorm gain)
+  float2* ln_stats_out; int ln_groups_out;
+  const float2* ln_stats_in; int ln_groups_in; float ln_inv_cols, ln_eps;
+  const float* ln_colsum;
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -115,6 +121,7 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   uint64_t* rbar = bars + 2 * STAGES + 4;       // [EPI_WARPS][2] residual boxes landed (EPI_F32)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rbar + 2 * EPI_WARPS);
   float* bias_all = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + BAR_BYTES);   // [EPI_WARPS][128]
+  float* colsum_all = bias_all + EPI_WARPS * 128;                                              // [EPI_WARPS][128] (LayerNorm mode)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -226,6 +233,32 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         reinterpret_cast<float4*>(bias_s)[lane] = b4;
         __syncwarp();
       }
+      const bool ln_in = (MODE == EPI_BF16) && g.ln_stats_in != nullptr;
+      float* colsum_s = colsum_all + ew * 128;
+      float ln_rstd = 1.f, ln_nmu = 0.f;
+      if (ln_in) {
+        const int cb = colbase + lane * 4;
+        float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (cb + 3 < g.N) s4 = __ldg(reinterpret_cast<const float4*>(g.ln_colsum + cb));
+        else {
+          if (cb < g.N) s4.x = __ldg(g.ln_colsum + cb);
+          if (cb + 1 < g.N) s4.y = __ldg(g.ln_colsum + cb + 1);
+          if (cb + 2 < g.N) s4.z = __ldg(g.ln_colsum + cb + 2);
+        }
+        __syncwarp();
+        reinterpret_cast<float4*>(colsum_s)[lane] = s4;
+        __syncwarp();
+        if (row_ok) {      // mean / rstd of this thread's row from the producer's per-group partial sums
+          const float2* st = g.ln_stats_in + (size_t)row * g.ln_groups_in;
+          float s1 = 0.f, s2 = 0.f;
+          for (int i = 0; i < g.ln_groups_in; ++i) { const float2 p = __ldg(st + i); s1 += p.x; s2 += p.y; }
+          const float mu = s1 * g.ln_inv_cols;
+          const float var = fmaxf(fmaf(s2, g.ln_inv_cols, -mu * mu), 0.f);
+          ln_rstd = rsqrtf(var + g.ln_eps);
+          ln_nmu = -mu;
+        }
+      }
+      uint64_t st_sum = 0, st_sq = 0;     // EPI_F32 + ln_stats_out: (even, odd) column partial sums of this row
       if (use_resid && lane == 0 && colbase < g.N && row0 < g.M) {
         // residual box of the first half-chunk (the buffer's previous store was issued >= 2 boxes ago)
         bulk_wait_read<1>();
@@ -253,7 +286,18 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         float f[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        if (g.bias) {
+        if (ln_in) {
+          // LayerNorm folded into this GEMM: acc = sum_k bf16(x_k) (gain_k W_nk)  ->  rstd (acc - mean colsum_n) + bias_n
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 sn = reinterpret_cast<const float4*>(colsum_s + c * 32)[j >> 2];
+            const float4 b = reinterpret_cast<const float4*>(bias_s + c * 32)[j >> 2];
+            f[j] = fmaf(ln_rstd, fmaf(ln_nmu, sn.x, f[j]), b.x);
+            f[j + 1] = fmaf(ln_rstd, fmaf(ln_nmu, sn.y, f[j + 1]), b.y);
+            f[j + 2] = fmaf(ln_rstd, fmaf(ln_nmu, sn.z, f[j + 2]), b.z);
+            f[j + 3] = fmaf(ln_rstd, fmaf(ln_nmu, sn.w, f[j + 3]), b.w);
+          }
+        } else if (g.bias) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             const float4 b = reinterpret_cast<const float4*>(bias_s + c * 32)[j >> 2];   // broadcast read
@@ -339,7 +383,25 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             }
             ++nchunk;
           }
-          if (g.out_bf16 && row_ok) {                  // tap hand-off: direct bf16 copy (4 of 32 fc2 launches)
+          if (g.ln_stats_out) {
+            const uint64_t one2 = pack_f32x2(1.f, 1.f);
+            if (full_cols) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 2) {
+                const uint64_t v2 = pack_f32x2(f[j], f[j + 1]);
+                st_sum = ffma2(v2, one2, st_sum);
+                st_sq = ffma2(v2, v2, st_sq);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; j += 2) {
+                const uint64_t v2 = pack_f32x2(col0 + j < g.N ? f[j] : 0.f, col0 + j + 1 < g.N ? f[j + 1] : 0.f);
+                st_sum = ffma2(v2, one2, st_sum);
+                st_sq = ffma2(v2, v2, st_sq);
+              }
+            }
+          }
+          if (g.out_bf16 && row_ok) {                  // bf16 copy of the final rows: tap hand-off / A operand of the next GEMM
             __nv_bfloat16* o = g.out_bf16 + (size_t)row * g.ld_bf16 + col0;
             if (full_cols) {
 #pragma unroll
@@ -354,6 +416,15 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
               for (int j = 0; j < 32; ++j) if (col0 + j < g.N) o[j] = __float2bfloat16_rn(f[j]);
             }
           }
+        }
+      }
+      if (MODE == EPI_F32 && g.ln_stats_out && row_ok) {
+        const int grp = n_blk * 2 + half;
+        if (grp < g.ln_groups_out) {
+          float a0, a1, q0, q1;
+          unpack_f32x2(st_sum, a0, a1);
+          unpack_f32x2(st_sq, q0, q1);
+          g.ln_stats_out[(size_t)row * g.ln_groups_out + grp] = make_float2(a0 + a1, q0 + q1);
         }
       }
     }
@@ -404,6 +475,20 @@ int launch_gemm_2cta(const void* A, int lda, const void* W, int ldw, int M, int 
   g.bias = ep->bias; g.resid = ep->resid; g.ld_resid = ep->ld_resid;
   g.pos = ep->pos; g.pos_rows = ep->pos_rows > 0 ? ep->pos_rows : 1;
   g.scale = ep->scale; g.scale_cols = ep->scale_cols; g.gelu = ep->gelu;
+  g.ln_stats_out = nullptr; g.ln_groups_out = 0; g.ln_stats_in = nullptr; g.ln_groups_in = 0; g.ln_inv_cols = 0.f; g.ln_eps = 0.f;
+  g.ln_colsum = nullptr;
+  if (ep->ln_stats_out) {
+    if (mode != EPI_F32) { set_error("desta_gemm_bf16: ln_stats_out needs the fp32 output"); return DESTA_ERR_ARG; }
+    g.ln_stats_out = (float2*)ep->ln_stats_out; g.ln_groups_out = (N + 127) / 128;
+  }
+  if (ep->ln_stats_in) {
+    if (mode != EPI_BF16 || !ep->ln_colsum || !ep->bias || ep->ln_groups <= 0 || ep->ln_cols <= 0) {
+      set_error("desta_gemm_bf16: ln_stats_in needs the bf16 output, ln_colsum, bias, ln_groups and ln_cols");
+      return DESTA_ERR_ARG;
+    }
+    g.ln_stats_in = (const float2*)ep->ln_stats_in; g.ln_groups_in = ep->ln_groups; g.ln_inv_cols = 1.0f / (float)ep->ln_cols;
+    g.ln_eps = ep->ln_eps; g.ln_colsum = ep->ln_colsum;
+  }
   bool& attr_set = *device_once_flag(1);
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_2cta_kernel<EPI_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_of(EPI_BF16));

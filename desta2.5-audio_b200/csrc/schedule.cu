@@ -17,7 +17,7 @@ struct Carver {
   void* take(size_t bytes) { void* p = base ? base + off : nullptr; off += (bytes + 1023) & ~(size_t)1023; return p; }
 };
 
-struct EncWs { __nv_bfloat16 *cols1, *c1, *cols2, *y, *qkv, *ao, *ff; size_t bytes; };
+struct EncWs { __nv_bfloat16 *cols1, *c1, *cols2, *y, *qkv, *ao, *ff; float* stats; size_t bytes; };
 static EncWs carve_encoder(const desta_dims* d, int N, void* ws) {
   Carver c{(uint8_t*)ws, 0};
   const size_t M = (size_t)N * d->max_pos, D = d->d_model;
@@ -29,6 +29,7 @@ static EncWs carve_encoder(const desta_dims* d, int N, void* ws) {
   w.qkv = (__nv_bfloat16*)c.take(M * 3 * D * 2);
   w.ao = (__nv_bfloat16*)c.take(M * D * 2);
   w.ff = (__nv_bfloat16*)c.take(M * (size_t)d->ffn * 2);
+  w.stats = (float*)c.take(M * (size_t)((D + 127) / 128) * 2 * 4);     // LayerNorm hand-over: per row and 128-column group (sum, sumsq)
   w.bytes = c.off;
   return w;
 }
@@ -66,14 +67,20 @@ static int check_dims(const desta_dims* d, const char* who) {
 }
 
 // C = epi(A W^T): thin wrapper filling the epilogue struct
+// LayerNorm hand-over of a GEMM (desta_gemm_epilogue): producer side = stats_out, consumer side = the other four
+struct LnLink { float* stats_out; const float* stats_in; const float* colsum; int cols; float eps; };
 static int gemm(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias, void* out_bf16, int ld_bf16,
                 float* out_f32, int ld_f32, const float* resid, int ld_resid, const float* pos, int pos_rows, float scale,
-                int scale_cols, int gelu, void* stream) {
+                int scale_cols, int gelu, void* stream, const LnLink* ln = nullptr) {
   desta_gemm_epilogue ep;
   memset(&ep, 0, sizeof(ep));
   ep.out_f32 = out_f32; ep.ld_f32 = ld_f32; ep.out_bf16 = out_bf16; ep.ld_bf16 = ld_bf16; ep.bias = bias;
   ep.resid = resid; ep.ld_resid = ld_resid; ep.pos = pos; ep.pos_rows = pos_rows; ep.scale = scale; ep.scale_cols = scale_cols;
   ep.gelu = gelu;
+  if (ln) {
+    ep.ln_stats_out = ln->stats_out;
+    ep.ln_stats_in = ln->stats_in; ep.ln_colsum = ln->colsum; ep.ln_cols = ln->cols; ep.ln_groups = (ln->cols + 127) / 128; ep.ln_eps = ln->eps;
+  }
   return desta_gemm_bf16(A, lda, W, ldw, M, N, K, &ep, stream);
 }
 
@@ -120,6 +127,35 @@ extern "C" int desta_encoder_fwd(const desta_dims* dims, const desta_encoder_wei
   RUN(gemm(ws.cols1, 3 * dims->n_mels, w->conv1_w, 3 * dims->n_mels, 2 * M, d, 3 * dims->n_mels, w->conv1_b, ws.c1, d, nullptr, 0,
            nullptr, 0, nullptr, 0, 1.f, 0, 1, stream));
   RUN(desta_im2col_k3(ws.c1, N, 2 * T, d, 2, ws.cols2, stream));
+  // LayerNorm folded into the GEMMs around it when the pack carries the gain-folded weights: every residual GEMM
+  // (conv2, out_proj, fc2) also writes the bf16 copy of the stream (`hb`; on tap layers that copy IS the tap) and the
+  // per-row partial sums, the QKV / fc1 GEMMs read `hb` and normalise in their epilogue.  64 launches and 64 fp32 reads
+  // of the [M, d] stream fewer per forward.
+  bool fold = M > 128;
+  for (int i = 0; i < dims->n_layers; ++i) {
+    const desta_enc_layer& L = w->layers[i];
+    fold = fold && L.qkv_w_ln && L.qkv_s && L.qkv_c && L.fc1_w_ln && L.fc1_s && L.fc1_c;
+  }
+  if (fold) {
+    const LnLink produce = {ws.stats, nullptr, nullptr, 0, 0.f};
+    const __nv_bfloat16* hb = ws.y;
+    RUN(gemm(ws.cols2, 3 * d, w->conv2_w, 3 * d, M, d, 3 * d, w->conv2_b, ws.y, d, h, d, nullptr, 0, w->pos, T, 1.f, 0, 1, stream, &produce));
+    int tap = 0;
+    for (int i = 0; i < dims->n_layers; ++i) {
+      const desta_enc_layer& L = w->layers[i];
+      const LnLink use_qkv = {nullptr, ws.stats, L.qkv_s, d, 1e-5f}, use_fc1 = {nullptr, ws.stats, L.fc1_s, d, 1e-5f};
+      RUN(gemm(hb, d, L.qkv_w_ln, d, M, 3 * d, d, L.qkv_c, ws.qkv, 3 * d, nullptr, 0, nullptr, 0, nullptr, 0, q_scale, d, 0, stream, &use_qkv));
+      RUN(desta_attention(ws.qkv, 3 * d, ws.qkv + d, 3 * d, ws.qkv + 2 * d, 3 * d, ws.ao, d, N, H, T, T, attn_scale, nullptr, nullptr, stream));
+      RUN(gemm(ws.ao, d, L.o_w, d, M, d, d, L.o_b, ws.y, d, h, d, h, d, nullptr, 0, 1.f, 0, 0, stream, &produce));
+      RUN(gemm(ws.y, d, L.fc1_w_ln, d, M, F, d, L.fc1_c, ws.ff, F, nullptr, 0, nullptr, 0, nullptr, 0, 1.f, 0, 1, stream, &use_fc1));
+      __nv_bfloat16* copy = ws.y;
+      if (tap < dims->n_taps && dims->tap_layers[tap] == i) { copy = (__nv_bfloat16*)taps + (size_t)tap * M * d; ++tap; }
+      RUN(gemm(ws.ff, F, L.fc2_w, F, M, d, F, L.fc2_b, copy, d, h, d, h, d, nullptr, 0, 1.f, 0, 0, stream, &produce));
+      hb = copy;
+    }
+    if (tap != dims->n_taps) { set_error("desta_encoder_fwd: tap_layers must be ascending layer ids < n_layers"); return DESTA_ERR_ARG; }
+    return DESTA_OK;
+  }
   RUN(gemm(ws.cols2, 3 * d, w->conv2_w, 3 * d, M, d, 3 * d, w->conv2_b, nullptr, 0, h, d, nullptr, 0, w->pos, T, 1.f, 0, 1, stream));
   int tap = 0;
   for (int i = 0; i < dims->n_layers; ++i) {

@@ -88,11 +88,19 @@ class EncoderPack:
                 fc1_w=_bf16(get(p + "fc1.weight")), fc1_b=_f32(get(p + "fc1.bias")),
                 fc2_w=_bf16(get(p + "fc2.weight")), fc2_b=_f32(get(p + "fc2.bias")),
             )
+            # LayerNorm folded into the GEMM that consumes it (desta_gemm_epilogue ln_*):  LN(x) W^T + b  =
+            # rstd (x (gain o W)^T - mean colsum) + (W beta + b), colsum taken over the bf16 operand the tensor cores see
+            for name, wcat, bcat, ln in (("qkv", torch.cat([qw, kw, vw], 0), L["qkv_b"], "ln1"), ("fc1", get(p + "fc1.weight"), L["fc1_b"], "ln2")):
+                gain, beta = L[ln + "_w"], L[ln + "_b"]
+                L[name + "_w_ln"] = _bf16(wcat.float() * gain[None, :])
+                L[name + "_s"] = L[name + "_w_ln"].float().sum(1).contiguous()
+                L[name + "_c"] = (wcat.float() @ beta + bcat).contiguous()
             self.layers.append(L)
         # desta_encoder_weights for the native schedule (desta_encoder_fwd); the tensors above keep the memory alive
         self._c_layers = (EncLayer * dims.n_layers)(*[
             EncLayer(*[L[k].data_ptr() for k in ("ln1_w", "ln1_b", "qkv_w", "qkv_b", "o_w", "o_b", "ln2_w", "ln2_b", "fc1_w",
-                                                 "fc1_b", "fc2_w", "fc2_b")]) for L in self.layers])
+                                                 "fc1_b", "fc2_w", "fc2_b", "qkv_w_ln", "qkv_s", "qkv_c", "fc1_w_ln", "fc1_s",
+                                                 "fc1_c")]) for L in self.layers])
         self.c_weights = EncoderWeights(self.conv1_w.data_ptr(), self.conv1_b.data_ptr(), self.conv2_w.data_ptr(),
                                         self.conv2_b.data_ptr(), self.pos.data_ptr(), self._c_layers)
 
@@ -147,7 +155,7 @@ class Workspace:
     (taps, residual stream), one byte workspace per native stage entry point, and - allocated only when the per-op Python
     schedule is used (profiling / training) - the individual activation buffers."""
 
-    _PY = ("cols1", "c1", "cols2", "y", "qkv", "ao", "ff", "kv", "x_f32", "x_bf", "q_qkv", "q_ao", "q_tmp", "a_f32", "a_bf", "q_q",
+    _PY = ("cols1", "c1", "cols2", "y", "ln_stats", "qkv", "ao", "ff", "kv", "x_f32", "x_bf", "q_qkv", "q_ao", "q_tmp", "a_f32", "a_bf", "q_q",
            "c_f32", "c_bf", "q_ff", "mix", "mix_bf")
 
     def __init__(self, dims: PathDims, N: int, device, keep_for_backward: bool = False):
@@ -202,6 +210,7 @@ class Workspace:
         self.c1 = e(N * 2 * T, d)
         self.cols2 = e(M, 3 * d)
         self.y = e(M, d)
+        self.ln_stats = e(M, (d + 127) // 128, 2, dt=f32)
         self.qkv = e(M, 3 * d)
         self.ao = e(M, d)
         self.ff = e(M, dims.ffn)
@@ -249,7 +258,7 @@ def encoder_forward(enc: EncoderPack, dims: PathDims, ws: Workspace, mel_tm: tor
             return
         return encoder_forward_ops(enc, dims, ws, mel_tm)
     wsb = ws.native_ws("encoder")
-    ops.STATS["launches"] += 4 + 7 * dims.n_layers
+    ops.STATS["launches"] += 4 + (5 if n * dims.max_pos > 128 else 7) * dims.n_layers
     with ops.device_guard(ops._dev(mel_tm, taps, h, wsb, enc.pos)):
         check(lib().desta_encoder_fwd(ctypes.byref(ws._c_dims), ctypes.byref(enc.c_weights), ops._p(mel_tm), n, ops._p(wsb), wsb.numel(),
                                       ops._p(taps), ops._p(h), ops._stream()), "desta_encoder_fwd")
@@ -276,6 +285,23 @@ def encoder_forward_ops(enc: EncoderPack, dims: PathDims, ws: Workspace, mel_tm:
     ops.im2col_k3(mel_tm, N, 2 * T, dims.n_mels, 1, ws.cols1)
     ops.gemm(ws.cols1, enc.conv1_w, enc.conv1_b, out_bf16=ws.c1, gelu=True)
     ops.im2col_k3(ws.c1, N, 2 * T, d, 2, ws.cols2)
+    if N * T > 128:
+        # LayerNorm folded into the GEMMs around it (same launches as desta_encoder_fwd in schedule.cu)
+        stats = ws.ln_stats
+        ops.gemm(ws.cols2, enc.conv2_w, enc.conv2_b, out_f32=ws.h, out_bf16=ws.y, gelu=True, pos=enc.pos, ln_stats_out=stats)
+        hb, tap_idx = ws.y, 0
+        for i, L in enumerate(enc.layers):
+            ops.gemm(hb, L["qkv_w_ln"], L["qkv_c"], out_bf16=ws.qkv, scale=LOG2E * hd ** -0.5, scale_cols=d, ln_in=(stats, L["qkv_s"], d, 1e-5))
+            ops.attention(ws.qkv[:, :d], ws.qkv[:, d:2 * d], ws.qkv[:, 2 * d:], ws.ao, N, dims.n_heads, T, T, LN2)
+            ops.gemm(ws.ao, L["o_w"], L["o_b"], out_f32=ws.h, resid=ws.h, out_bf16=ws.y, ln_stats_out=stats)
+            ops.gemm(ws.y, L["fc1_w_ln"], L["fc1_c"], out_bf16=ws.ff, gelu=True, ln_in=(stats, L["fc1_s"], d, 1e-5))
+            hb = ws.y
+            if i in dims.tap_layers:
+                hb = ws.taps[tap_idx]
+                tap_idx += 1
+            ops.gemm(ws.ff, L["fc2_w"], L["fc2_b"], out_f32=ws.h, resid=ws.h, out_bf16=hb, ln_stats_out=stats)
+        assert tap_idx == len(dims.tap_layers)
+        return
     ops.gemm(ws.cols2, enc.conv2_w, enc.conv2_b, out_f32=ws.h, gelu=True, pos=enc.pos)
     tap_idx = 0
     for i, L in enumerate(enc.layers):

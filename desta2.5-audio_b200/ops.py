@@ -98,8 +98,11 @@ def _cuda(t, dtype=None):
     return t
 
 
-def gemm(a, w, bias=None, *, out_bf16=None, out_f32=None, resid=None, pos=None, scale=1.0, scale_cols=0, gelu=False):
-    """C = epi(a[M,K] @ w[N,K]^T).  a, w bf16 row-major (last dim contiguous); outputs written in place."""
+def gemm(a, w, bias=None, *, out_bf16=None, out_f32=None, resid=None, pos=None, scale=1.0, scale_cols=0, gelu=False,
+         ln_stats_out=None, ln_in=None):
+    """C = epi(a[M,K] @ w[N,K]^T).  a, w bf16 row-major (last dim contiguous); outputs written in place.
+    LayerNorm hand-over (desta_gemm_epilogue): ``ln_stats_out`` fp32 [M, ceil(N/128), 2] on a residual (fp32-output) GEMM;
+    ``ln_in = (stats, colsum, cols, eps)`` on the GEMM that consumes the bf16 copy with gain-folded weights."""
     _cuda(a, torch.bfloat16), _cuda(w, torch.bfloat16)
     M, K = a.shape
     N, K2 = w.shape
@@ -126,6 +129,17 @@ def gemm(a, w, bias=None, *, out_bf16=None, out_f32=None, resid=None, pos=None, 
         assert pos.shape[1] == N and pos.is_contiguous()
         ep.pos, ep.pos_rows = pos.data_ptr(), pos.shape[0]
     ep.scale, ep.scale_cols, ep.gelu = float(scale), int(scale_cols), int(bool(gelu))
+    if ln_stats_out is not None:
+        _cuda(ln_stats_out, torch.float32)
+        assert out_f32 is not None and ln_stats_out.is_contiguous() and ln_stats_out.numel() == M * ((N + 127) // 128) * 2
+        ep.ln_stats_out = ln_stats_out.data_ptr()
+    if ln_in is not None:
+        stats, colsum, cols, eps = ln_in
+        _cuda(stats, torch.float32), _cuda(colsum, torch.float32)
+        groups = (cols + 127) // 128
+        assert out_bf16 is not None and bias is not None and stats.is_contiguous() and stats.numel() == M * groups * 2
+        assert colsum.numel() == N and colsum.is_contiguous()
+        ep.ln_stats_in, ep.ln_groups, ep.ln_cols, ep.ln_eps, ep.ln_colsum = stats.data_ptr(), groups, int(cols), float(eps), colsum.data_ptr()
     # algorithmic bytes: A and W read once, every output written once, the residual read once
     nbytes = 2.0 * (M * K + N * K) + M * N * ((4 if out_f32 is not None else 0) + (2 if out_bf16 is not None else 0)
                                               + (4 if resid is not None else 0))

@@ -50,6 +50,16 @@ typedef struct desta_gemm_epilogue {
   const float* pos;   int pos_rows;     /* fp32 [pos_rows,N] table, row (m % pos_rows) added after activation */
   float scale;        int scale_cols;   /* columns < scale_cols are multiplied by scale after the bias */
   int gelu;                             /* erf-GELU after bias/scale */
+  /* LayerNorm folded into the GEMMs on either side of it (M > 128 only; the encoder's pre-LN layers,
+   * $TF/models/whisper/modeling_whisper.py:393-408, lose their stand-alone LayerNorm pass):
+   *   producer (fp32 output mode): ln_stats_out [M, ceil(N/128), 2] fp32 receives, per final output row and 128-column
+   *     group, the partial (sum, sum of squares); out_bf16 receives the bf16 copy of the same rows.
+   *   consumer (bf16 output mode): A is that bf16 copy, W holds gain[k] * W[n,k], bias holds sum_k beta[k] W[n,k] + b[n],
+   *     ln_colsum[n] = sum_k of the bf16 W row; the epilogue computes rstd * (acc - mean * ln_colsum[n]) + bias[n] from
+   *     ln_stats_in [M, ln_groups, 2] (mean / variance over ln_cols columns, eps = ln_eps) before scale / GELU. */
+  float* ln_stats_out;
+  const float* ln_stats_in; int ln_groups; int ln_cols; float ln_eps;
+  const float* ln_colsum;
 } desta_gemm_epilogue;
 int desta_gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int K,
                     const desta_gemm_epilogue* ep, void* stream);
@@ -197,6 +207,10 @@ typedef struct desta_enc_layer {              /* bf16 GEMM weights [out,in] row-
   const float *ln2_w, *ln2_b;
   const void* fc1_w; const float* fc1_b;
   const void* fc2_w; const float* fc2_b;
+  /* optional LayerNorm-folded operands (all six set -> desta_encoder_fwd runs without LayerNorm launches):
+   * *_w_ln = bf16(gain[k] * W[n,k]), *_s[n] = sum_k of that bf16 row (fp32), *_c[n] = sum_k beta[k] W[n,k] + bias[n] */
+  const void* qkv_w_ln; const float *qkv_s, *qkv_c;
+  const void* fc1_w_ln; const float *fc1_s, *fc1_c;
 } desta_enc_layer;
 typedef struct desta_encoder_weights {
   const void* conv1_w; const float* conv1_b;  /* [d, 3*n_mels] (tap-major im2col order) */

@@ -67,6 +67,54 @@ def test_gemm_epilogues():
     assert torch.equal(tap, buf.to(torch.bfloat16))
 
 
+@pytest.mark.parametrize("M,D,N2", [(3000, 1280, 3840), (1500, 384, 1536), (333, 200, 264)])
+def test_gemm_layernorm_handover(M, D, N2):
+    """LayerNorm folded into the GEMMs around it (desta_gemm_epilogue ln_*): the residual GEMM emits the bf16 copy of its
+    rows and per-row partial sums, the next GEMM normalises in its epilogue.  Against F.layer_norm + linear in fp32
+    ($TF/models/whisper/modeling_whisper.py:393-408), with an outlier channel and a row offset in the stream."""
+    g = torch.Generator(device="cuda").manual_seed(M + D)
+    K = 256
+    a = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
+    w0 = (torch.randn(D, K, device="cuda", generator=g) * 0.05).to(torch.bfloat16)
+    b0 = torch.randn(D, device="cuda", generator=g)
+    resid = torch.randn(M, D, device="cuda", generator=g) + 3.0
+    resid[:, 7] *= 40.0                                        # massive-activation channel
+    G = (D + 127) // 128
+    h = resid.clone()
+    hb = torch.empty(M, D, device="cuda", dtype=torch.bfloat16)
+    stats = torch.full((M, G, 2), float("nan"), device="cuda")
+    ops.gemm(a, w0, b0, out_f32=h, resid=h, out_bf16=hb, ln_stats_out=stats)
+    h_ref = a.float() @ w0.float().t() + b0 + resid
+    assert _rel(h, h_ref) < 2e-5 and torch.equal(hb, h.to(torch.bfloat16))
+    pad = torch.zeros(M, G * 128 - D, device="cuda")
+    hg = torch.cat([h, pad], 1).view(M, G, 128).double()
+    assert torch.allclose(stats[..., 0].double(), hg.sum(-1), rtol=1e-5, atol=1e-3)
+    assert torch.allclose(stats[..., 1].double(), (hg * hg).sum(-1), rtol=1e-5, atol=1e-3)
+    # consumer: gain-folded weights, colsum, folded bias (engine.EncoderPack builds the same three)
+    gain = 1.0 + 0.2 * torch.randn(D, device="cuda", generator=g)
+    beta = 0.1 * torch.randn(D, device="cuda", generator=g)
+    w1 = torch.randn(N2, D, device="cuda", generator=g) * 0.03
+    b1 = torch.randn(N2, device="cuda", generator=g)
+    w_ln = (w1 * gain[None, :]).to(torch.bfloat16)
+    colsum = w_ln.float().sum(1).contiguous()
+    cvec = (w1 @ beta + b1).contiguous()
+    out = torch.empty(M, N2, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(hb, w_ln, cvec, out_bf16=out, ln_in=(stats, colsum, D, 1e-5), scale=0.5, scale_cols=128)
+    y = torch.nn.functional.layer_norm(h_ref, (D,), gain, beta, 1e-5)
+    ref = y @ w1.t() + b1
+    ref[:, :128] *= 0.5
+    # the un-fused product path rounds LN(x) and W to bf16 as well: same error order
+    unfused = y.to(torch.bfloat16).float() @ w1.to(torch.bfloat16).float().t() + b1
+    unfused[:, :128] *= 0.5
+    e_fused, e_unfused = _rel(out, ref), _rel(unfused.to(torch.bfloat16), ref)
+    assert e_fused < max(2.0 * e_unfused, 8e-3), (e_fused, e_unfused)
+    assert _cos(out, ref) > 0.9999
+    # GELU after the normalisation (fc1)
+    ops.gemm(hb, w_ln, cvec, out_bf16=out, ln_in=(stats, colsum, D, 1e-5), gelu=True)
+    ref = torch.nn.functional.gelu(y @ w1.t() + b1)
+    assert _rel(out, ref) < 1.5e-2 and _cos(out, ref) > 0.9999
+
+
 def test_gemm_gelu_tails():
     """The fused erf-GELU epilogue on large pre-activations (real Whisper checkpoints have fc1 outliers): GELU(x) -> 0 for
     x << 0 and -> x for x >> 0.  An identity weight makes the accumulator equal the (bf16-exact) input."""
