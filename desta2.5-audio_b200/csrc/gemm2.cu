@@ -19,11 +19,12 @@ constexpr int BM = 128, BN = 256, BNH = 128, BK = 64, UMMA_K = 16;
 constexpr int A_BYTES = BM * BK * 2, B_BYTES = BNH * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;   // 32 KB
 constexpr int EPI_WARP0 = 4, EPI_WARPS = 8, THREADS = 384;
 // two epilogue flavours: bf16 outputs (32 x 32 bf16 boxes) and fp32 outputs with optional fp32 residual (32 x 16 fp32
-// boxes, loaded AND stored by TMA); both stage through two 2 KB boxes per warp, which leaves room for a 5-stage
-// operand ring in either mode (the K = 5120 fc2 GEMM lost 10 % going from 4 to 3 stages)
+// boxes, loaded AND stored by TMA); both stage through two 2 KB boxes per warp (fp32 mode: a third one for the optional
+// bf16 copy of the same rows, 32 x 32 bf16, also TMA-stored), which leaves room for a 5-stage operand ring in either mode
+// (the K = 5120 fc2 GEMM lost 10 % going from 4 to 3 stages)
 constexpr int EPI_BF16 = 0, EPI_F32 = 1;
 __host__ __device__ constexpr int stages_of(int mode) { return 5; }
-__host__ __device__ constexpr int staging_of(int mode) { return 2 * 2048; }
+__host__ __device__ constexpr int staging_of(int mode) { return mode == EPI_F32 ? 3 * 2048 : 2 * 2048; }   // EPI_F32: + one bf16 box
 constexpr int BAR_BYTES = 512;
 __host__ __device__ constexpr int smem_of(int mode) { return stages_of(mode) * STAGE_BYTES + EPI_WARPS * staging_of(mode) + 1024 + BAR_BYTES + EPI_WARPS * 1024; }
 }  // namespace g2
@@ -106,7 +107,8 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2::THREADS, 1)
 gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                         const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const Gemm2Args g) {
+                         const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
+                         const __grid_constant__ CUtensorMap tmD, const Gemm2Args g) {
   using namespace g2;
   constexpr int STAGES = stages_of(MODE);
   constexpr int STAGING_PER_WARP = staging_of(MODE);
@@ -136,6 +138,7 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmC);
     if (MODE == EPI_F32 && g.resid) tma_prefetch_desc(&tmR);
+    if (MODE == EPI_F32 && g.out_bf16) tma_prefetch_desc(&tmD);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 2); mbar_init(&empty[i], 1); }
@@ -401,19 +404,26 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
               }
             }
           }
-          if (g.out_bf16 && row_ok) {                  // bf16 copy of the final rows: tap hand-off / A operand of the next GEMM
-            __nv_bfloat16* o = g.out_bf16 + (size_t)row * g.ld_bf16 + col0;
-            if (full_cols) {
+          if (g.out_bf16) {
+            // bf16 copy of the final rows (tap hand-off / A operand of the next GEMM): third staging box, 32 rows x 32 bf16
+            // (64-byte rows, SWIZZLE_64B), TMA-stored (clips at M / N itself).  Its previous store lies >= 3 bulk groups back.
+            uint8_t* buf = stg + 2 * 2048;
+            if (lane == 0) bulk_wait_read<2>();
+            __syncwarp();
+            uint8_t* rowp = buf + lane * 64;
+            const int sw = (lane >> 1) & 3;
 #pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                uint4 u;
-                u.x = pack_bf16(f[j], f[j + 1]); u.y = pack_bf16(f[j + 2], f[j + 3]);
-                u.z = pack_bf16(f[j + 4], f[j + 5]); u.w = pack_bf16(f[j + 6], f[j + 7]);
-                *reinterpret_cast<uint4*>(o + j) = u;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) if (col0 + j < g.N) o[j] = __float2bfloat16_rn(f[j]);
+            for (int j = 0; j < 4; ++j) {
+              uint4 u;
+              u.x = pack_bf16(f[8 * j], f[8 * j + 1]); u.y = pack_bf16(f[8 * j + 2], f[8 * j + 3]);
+              u.z = pack_bf16(f[8 * j + 4], f[8 * j + 5]); u.w = pack_bf16(f[8 * j + 6], f[8 * j + 7]);
+              *reinterpret_cast<uint4*>(rowp + ((j ^ sw) << 4)) = u;
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmD, buf, col0, row0);
+              bulk_commit();
             }
           }
         }
@@ -450,7 +460,7 @@ static int make_f32_box_map(CUtensorMap* m, const float* base, int M, int N, int
 int launch_gemm_2cta(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const desta_gemm_epilogue* ep,
                      cudaStream_t stream) {
   using namespace g2;
-  CUtensorMap tmA, tmB, tmC, tmR;
+  CUtensorMap tmA, tmB, tmC, tmR, tmD;
   if (make_tmap_2d_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM, BK)) return DESTA_ERR_CUDA;
   if (make_tmap_2d_bf16(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, BNH, BK)) return DESTA_ERR_CUDA;
   const int mode = ep->out_f32 ? EPI_F32 : EPI_BF16;
@@ -465,12 +475,21 @@ int launch_gemm_2cta(const void* A, int lda, const void* W, int ldw, int M, int 
     if (make_tmap(&tmC, ep->out_bf16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B))
       return DESTA_ERR_CUDA;
     tmR = tmC;
+    tmD = tmC;
     g.has_bf16 = 1;
   } else {
     if (make_f32_box_map(&tmC, ep->out_f32, M, N, ep->ld_f32)) return DESTA_ERR_CUDA;
     if (ep->resid) { if (make_f32_box_map(&tmR, ep->resid, M, N, ep->ld_resid)) return DESTA_ERR_CUDA; }
     else tmR = tmC;
+    tmD = tmC;
     g.out_bf16 = (__nv_bfloat16*)ep->out_bf16; g.ld_bf16 = ep->ld_bf16;
+    if (ep->out_bf16) {
+      uint64_t dims[2] = {(uint64_t)N, (uint64_t)M};
+      uint64_t strides[2] = {0, (uint64_t)ep->ld_bf16 * 2};
+      uint32_t box[2] = {32, 32};
+      if (make_tmap(&tmD, ep->out_bf16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B))
+        return DESTA_ERR_CUDA;
+    }
   }
   g.bias = ep->bias; g.resid = ep->resid; g.ld_resid = ep->ld_resid;
   g.pos = ep->pos; g.pos_rows = ep->pos_rows > 0 ? ep->pos_rows : 1;
@@ -499,8 +518,8 @@ int launch_gemm_2cta(const void* A, int lda, const void* W, int ldw, int M, int 
   const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);
   int pairs = num_sms() / 2;
   if (tiles < pairs) pairs = tiles;
-  if (mode == EPI_BF16) gemm_bf16_tn_2cta_kernel<EPI_BF16><<<2 * pairs, THREADS, smem_of(EPI_BF16), stream>>>(tmA, tmB, tmC, tmR, g);
-  else gemm_bf16_tn_2cta_kernel<EPI_F32><<<2 * pairs, THREADS, smem_of(EPI_F32), stream>>>(tmA, tmB, tmC, tmR, g);
+  if (mode == EPI_BF16) gemm_bf16_tn_2cta_kernel<EPI_BF16><<<2 * pairs, THREADS, smem_of(EPI_BF16), stream>>>(tmA, tmB, tmC, tmR, tmD, g);
+  else gemm_bf16_tn_2cta_kernel<EPI_F32><<<2 * pairs, THREADS, smem_of(EPI_F32), stream>>>(tmA, tmB, tmC, tmR, tmD, g);
   return check_launch("gemm_bf16_tn_2cta_kernel");
 }
 

@@ -26,21 +26,34 @@ def timeit(fn, iters=10, warm=3):
 
 def bench_gemm():
     M = 96000
-    for name, N, K, kw in [("qkv", 3840, 1280, dict(scale=0.125, scale_cols=1280)), ("out_proj+res", 1280, 1280, dict(resid=True)),
-                           ("fc1+gelu", 5120, 1280, dict(gelu=True)), ("fc2+res", 1280, 5120, dict(resid=True)),
+    for name, N, K, kw in [("qkv", 3840, 1280, dict(scale=0.125, scale_cols=1280)), ("qkv+ln_in", 3840, 1280, dict(scale=0.125, scale_cols=1280, ln_in=True)),
+                           ("out_proj+res", 1280, 1280, dict(resid=True)), ("out_proj+res+ln", 1280, 1280, dict(resid=True, ln_out=True)),
+                           ("fc1+gelu", 5120, 1280, dict(gelu=True)), ("fc1+gelu+ln_in", 5120, 1280, dict(gelu=True, ln_in=True)),
+                           ("fc2+res", 1280, 5120, dict(resid=True)), ("fc2+res+ln", 1280, 5120, dict(resid=True, ln_out=True)),
                            ("kvproj", 15360, 1280, {}), ("conv2", 1280, 3840, dict(gelu=True)), ("qf_small", 1280, 1280, dict(M=16384))]:
         m = kw.pop("M", M)
         a = torch.randn(m, K, device="cuda").to(torch.bfloat16)
         w = (torch.randn(N, K, device="cuda") * 0.02).to(torch.bfloat16)
         b = torch.randn(N, device="cuda")
+        ln_out, ln_in = kw.pop("ln_out", False), kw.pop("ln_in", False)
         if kw.pop("resid", False):
             h = torch.randn(m, N, device="cuda")
-            fn = lambda: ops.gemm(a, w, b, out_f32=h, resid=h)  # noqa: E731
+            if ln_out:
+                hb = torch.empty(m, N, device="cuda", dtype=torch.bfloat16)
+                st = torch.empty(m, (N + 127) // 128, 2, device="cuda")
+                fn = lambda: ops.gemm(a, w, b, out_f32=h, resid=h, out_bf16=hb, ln_stats_out=st)  # noqa: E731
+            else:
+                fn = lambda: ops.gemm(a, w, b, out_f32=h, resid=h)  # noqa: E731
         else:
             o = torch.empty(m, N, device="cuda", dtype=torch.bfloat16)
-            fn = lambda: ops.gemm(a, w, b, out_bf16=o, **kw)  # noqa: E731
+            if ln_in:
+                st = torch.rand(m, (K + 127) // 128, 2, device="cuda") + 1.0
+                cs = torch.randn(N, device="cuda")
+                fn = lambda: ops.gemm(a, w, b, out_bf16=o, ln_in=(st, cs, K, 1e-5), **kw)  # noqa: E731
+            else:
+                fn = lambda: ops.gemm(a, w, b, out_bf16=o, **kw)  # noqa: E731
         ms = timeit(fn)
-        print(f"gemm {name:14s} M={m} N={N} K={K}: {ms:.3f} ms  {2.0 * m * N * K / ms / 1e9:.0f} TFLOP/s", flush=True)
+        print(f"gemm {name:16s} M={m} N={N} K={K}: {ms:.3f} ms  {2.0 * m * N * K / ms / 1e9:.0f} TFLOP/s", flush=True)
         del a, w
 
 
