@@ -430,6 +430,63 @@ def run_ours(args):
     perception = model.perception
     table = model.llm_model.model.embed_tokens.weight
 
+    def hbm_kernels_alone(fam, wave_dev, ids_dev, trans, positions, n):
+        """The two HBM-judged kernels (north_star: log-mel and splice) timed as kernels: 20 back-to-back launches between two
+        CUDA events, alternating between two resident input / output sets so that no launch finds its data in L2.  The
+        event-bracketed single calls of the instrumented step (kept as `in_step_ms`) also contain the host's launch latency -
+        the log-mel is the first launch of a step on an idle GPU, the splice the last - which says nothing about the kernel."""
+        import ctypes
+        from desta_b200 import ops
+        from desta_b200._lib import SpliceDesc, check, lib
+        iters = 20
+
+        def loop(fn):
+            for k in range(4):
+                fn(k)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for k in range(iters):
+                fn(k)
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / iters
+
+        waves = [wave_dev, wave_dev.clone()]
+        ms_mel = loop(lambda k: ops.logmel(waves[k & 1], w["n_mels"], want_bf16_tm=True, want_f32=False))
+        mel_bytes = n * (480000 * 4 + w["n_mels"] * 3000 * 2)                  # waveform in + bf16 time-major log-mel out
+        if "logmel" in fam:
+            fam["logmel"].update({"in_step_ms": fam["logmel"]["ms"], "ms": round(ms_mel, 4), "achieved": round(mel_bytes / ms_mel / 1e6, 1),
+                                  "algorithmic_bytes": mel_bytes, "frac_of_hbm_peak": round(mel_bytes / ms_mel / 1e6 / hbm_peak, 4),
+                                  "timing": f"{iters} back-to-back launches, two alternating input batches"})
+        del waves
+        feats = [torch.randn(n, w["prompt_size"], w["d_llm"], device=dev) for _ in range(2)]
+        B, S = ids_dev.shape
+        outs = [torch.empty(B, S, w["d_llm"], dtype=torch.bfloat16, device=dev) for _ in range(2)]
+        # descriptors uploaded once (ops.splice uploads them per call with a blocking copy: host work, not the kernel)
+        host, flat, off = (SpliceDesc * n)(), [], 0
+        for i in range(n):
+            t = trans[i].reshape(-1)
+            host[i] = SpliceDesc(int(positions[i][0]), int(positions[i][1]), int(t.numel()), off)
+            off += int(t.numel())
+            flat.append(t)
+        trans_cat = torch.cat(flat).to(device=dev, dtype=torch.int64) if off > 0 else None
+        descs_dev = torch.frombuffer(bytearray(bytes(host)), dtype=torch.int32).to(dev)
+        err = ops._err_word(dev)
+
+        def splice_once(k):
+            check(lib().desta_splice(ops._p(ids_dev), ops._p(table), table.shape[0], ops._p(descs_dev), host, n, ops._p(trans_cat),
+                                     ops._p(feats[k & 1]), 0, w["prompt_size"], ops._p(outs[k & 1]), B, S, w["d_llm"],
+                                     ctypes.c_void_p(err.data_ptr()), ops._stream()), "desta_splice")
+
+        ms_sp = loop(splice_once)
+        n_t = off
+        sp_bytes = B * S * 8 + (B * S - n * w["prompt_size"]) * w["d_llm"] * 2 + n * w["prompt_size"] * w["d_llm"] * 4 + B * S * w["d_llm"] * 2 + n_t * 8
+        if "splice" in fam:
+            fam["splice"].update({"in_step_ms": fam["splice"]["ms"], "ms": round(ms_sp, 4), "achieved": round(sp_bytes / ms_sp / 1e6, 1),
+                                  "algorithmic_bytes": sp_bytes, "frac_of_hbm_peak": round(sp_bytes / ms_sp / 1e6 / hbm_peak, 4),
+                                  "timing": f"{iters} back-to-back launches, two alternating feature / output sets"})
+
     # =========================================================================================== forward (headline)
     def forward_line(n):
         S_len, B_prompts, positions, trans, ids_host = prompts_for(args, w, n, rank)
@@ -526,6 +583,7 @@ def run_ours(args):
         step_resident()
         prof = ops.stop_profile()
         fam, gm, total_ms = family_table(prof)
+        hbm_kernels_alone(fam, wave_dev, ids_dev, trans, positions, n)
         traffic, traffic_note = committed_gemm_traffic(args.workload, n, False)
         step_s = ms * 1e-3 / args.steps
         h2d = wave_host.numel() * 4 + ids_host.numel() * 8

@@ -105,11 +105,11 @@ EXPORTS = {
     "desta_cast_f32_bf16": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "desta_row_hash": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
     "desta_splice_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
-    "desta_im2col_k3": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "desta_im2col_k3": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "desta_layer_mix": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "desta_encoder_workspace_bytes": (c_size_t, [POINTER(Dims), c_int]),
-    "desta_encoder_fwd": (c_int, [POINTER(Dims), POINTER(EncoderWeights), c_void_p, c_int, c_void_p, c_size_t, c_void_p, c_void_p,
-                                  c_void_p]),
+    "desta_encoder_fwd": (c_int, [POINTER(Dims), POINTER(EncoderWeights), c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p,
+                                  c_void_p, c_void_p]),
     "desta_connector_workspace_bytes": (c_size_t, [POINTER(Dims), c_int]),
     "desta_connector_fwd": (c_int, [POINTER(Dims), POINTER(ConnectorWeights), c_void_p, c_int, c_void_p, c_size_t, c_void_p,
                                     c_void_p]),

@@ -86,8 +86,11 @@ layernorm_kernel(const float* __restrict__ x, int ldx, const float* __restrict__
 
 // ---- im2col for Conv1d(k=3, pad=1, stride s) on time-major bf16 input. One thread moves 8 channels (16 B). ----
 __global__ void __launch_bounds__(256)
-im2col_k3_kernel(const uint4* __restrict__ x, int N, int T_in, int C8, int stride, int T_out, uint4* __restrict__ cols) {
+im2col_k3_kernel(const uint4* __restrict__ x, int N, int T_in, int C8, int stride, int T_out, uint4* __restrict__ cols,
+                 const unsigned* __restrict__ clip_max) {
   const size_t total = (size_t)N * T_out * 3 * C8;
+  int floor_n = -1;              // clip whose floor is held in `fl` (recomputed only when the grid-stride loop crosses a clip)
+  uint32_t fl = 0;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % C8);
     const size_t r = i / C8;
@@ -97,7 +100,22 @@ im2col_k3_kernel(const uint4* __restrict__ x, int N, int T_in, int C8, int strid
     const int n = (int)(row / T_out);
     const int t_in = t_out * stride + tap - 1;
     uint4 v = make_uint4(0, 0, 0, 0);
-    if (t_in >= 0 && t_in < T_in) v = x[((size_t)n * T_in + t_in) * C8 + c];
+    if (t_in >= 0 && t_in < T_in) {
+      v = x[((size_t)n * T_in + t_in) * C8 + c];
+      if (clip_max) {
+        // deferred log-mel floor (desta_logmel with out_f32 == NULL): max(L, Lmax - 8) in the affine / bf16 domain
+        if (n != floor_n) {
+          const unsigned u = __ldg(clip_max + n);
+          const float lmax = __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
+          fl = pack_bf16(((lmax - 8.0f) + 4.0f) * 0.25f, ((lmax - 8.0f) + 4.0f) * 0.25f);
+          floor_n = n;
+        }
+        asm("max.bf16x2 %0, %0, %1;" : "+r"(v.x) : "r"(fl));
+        asm("max.bf16x2 %0, %0, %1;" : "+r"(v.y) : "r"(fl));
+        asm("max.bf16x2 %0, %0, %1;" : "+r"(v.z) : "r"(fl));
+        asm("max.bf16x2 %0, %0, %1;" : "+r"(v.w) : "r"(fl));
+      }
+    }
     cols[i] = v;
   }
 }
@@ -151,7 +169,7 @@ extern "C" int desta_layernorm(const float* x, int ldx, const float* gamma, cons
   return check_launch("layernorm_kernel");
 }
 
-extern "C" int desta_im2col_k3(const void* x, int N, int T_in, int C, int stride, void* cols, void* stream) {
+extern "C" int desta_im2col_k3(const void* x, int N, int T_in, int C, int stride, void* cols, const float* mel_clip_max, void* stream) {
   if (!x || !cols) { set_error("desta_im2col_k3: null pointer"); return DESTA_ERR_ARG; }
   if (N <= 0) return DESTA_OK;
   if ((C % 8) || (stride != 1 && stride != 2) || (T_in % stride)) {
@@ -163,7 +181,8 @@ extern "C" int desta_im2col_k3(const void* x, int N, int T_in, int C, int stride
   size_t blocks = (total + 255) / 256;
   const size_t cap = (size_t)num_sms() * 16;
   if (blocks > cap) blocks = cap;
-  im2col_k3_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const uint4*)x, N, T_in, C / 8, stride, T_out, (uint4*)cols);
+  im2col_k3_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const uint4*)x, N, T_in, C / 8, stride, T_out, (uint4*)cols,
+                                                                        (const unsigned*)mel_clip_max);
   return check_launch("im2col_k3_kernel");
 }
 

@@ -109,8 +109,8 @@ extern "C" size_t desta_encoder_workspace_bytes(const desta_dims* dims, int N) {
   return carve_encoder(dims, N, nullptr).bytes;
 }
 
-extern "C" int desta_encoder_fwd(const desta_dims* dims, const desta_encoder_weights* w, const void* mel_tm, int N, void* workspace,
-                                 size_t workspace_bytes, void* taps, float* h, void* stream) {
+extern "C" int desta_encoder_fwd(const desta_dims* dims, const desta_encoder_weights* w, const void* mel_tm, const float* mel_clip_max,
+                                 int N, void* workspace, size_t workspace_bytes, void* taps, float* h, void* stream) {
   RUN(check_dims(dims, "desta_encoder_fwd"));
   if (!w || !w->layers || !mel_tm || !workspace || !taps || !h) { set_error("desta_encoder_fwd: null pointer"); return DESTA_ERR_ARG; }
   if (N <= 0) return DESTA_OK;
@@ -123,10 +123,10 @@ extern "C" int desta_encoder_fwd(const desta_dims* dims, const desta_encoder_wei
   const float q_scale = 1.4426950408889634f / sqrtf((float)(d / H));
   const float attn_scale = 0.6931471805599453f;
   // conv stem as im2col + GEMM: gelu(conv1), gelu(conv2 stride 2) + positions -> fp32 residual stream (:563-570)
-  RUN(desta_im2col_k3(mel_tm, N, 2 * T, dims->n_mels, 1, ws.cols1, stream));
+  RUN(desta_im2col_k3(mel_tm, N, 2 * T, dims->n_mels, 1, ws.cols1, mel_clip_max, stream));
   RUN(gemm(ws.cols1, 3 * dims->n_mels, w->conv1_w, 3 * dims->n_mels, 2 * M, d, 3 * dims->n_mels, w->conv1_b, ws.c1, d, nullptr, 0,
            nullptr, 0, nullptr, 0, 1.f, 0, 1, stream));
-  RUN(desta_im2col_k3(ws.c1, N, 2 * T, d, 2, ws.cols2, stream));
+  RUN(desta_im2col_k3(ws.c1, N, 2 * T, d, 2, ws.cols2, nullptr, stream));
   // LayerNorm folded into the GEMMs around it when the pack carries the gain-folded weights: every residual GEMM
   // (conv2, out_proj, fc2) also writes the bf16 copy of the stream (`hb`; on tap layers that copy IS the tap) and the
   // per-row partial sums, the QKV / fc1 GEMMs read `hb` and normalise in their epilogue.  64 launches and 64 fp32 reads

@@ -235,12 +235,13 @@ def _native_enabled():
     return ops._PROFILE is None        # the per-family CUDA-event profile of bench.py needs the per-op schedule
 
 
-def encoder_forward(enc: EncoderPack, dims: PathDims, ws: Workspace, mel_tm: torch.Tensor, taps=None, h=None):
+def encoder_forward(enc: EncoderPack, dims: PathDims, ws: Workspace, mel_tm: torch.Tensor, taps=None, h=None, mel_floor=None):
     """mel_tm: bf16 time-major log-mel [n, 3000, n_mels] -> taps[k] (bf16 [n*1500, d]) and h (fp32 [n*1500, d]).  One call
     of the native schedule desta_encoder_fwd (same launches, same order as encoder_forward_ops below).
     By default n == ws.N and the outputs are ws.taps / ws.h.  A SUBSET run (scope row n2: only the clips whose encoder
     state is not cached) passes n < ws.N clips with its own compact `taps` [K, n*1500, d] / `h` [n*1500, d] and borrows
-    the byte workspace of the full batch."""
+    the byte workspace of the full batch.  ``mel_floor``: clip-max words of ``ops.logmel(want_f32=False)`` when mel_tm still
+    lacks the per-clip log-mel floor (applied by the conv1 im2col on read)."""
     n = mel_tm.shape[0]
     taps = ws.taps if taps is None else taps
     h = ws.h if h is None else h
@@ -252,16 +253,16 @@ def encoder_forward(enc: EncoderPack, dims: PathDims, ws: Workspace, mel_tm: tor
     if not _native_enabled():
         if n != ws.N or taps is not ws.taps or h is not ws.h:          # per-op schedule: buffers are sized per batch
             sub = Workspace(dims, n, ws.device)
-            encoder_forward_ops(enc, dims, sub, mel_tm)
+            encoder_forward_ops(enc, dims, sub, mel_tm, mel_floor)
             taps.copy_(sub.taps)
             h.copy_(sub.h)
             return
-        return encoder_forward_ops(enc, dims, ws, mel_tm)
+        return encoder_forward_ops(enc, dims, ws, mel_tm, mel_floor)
     wsb = ws.native_ws("encoder")
     ops.STATS["launches"] += 4 + (5 if n * dims.max_pos > 128 else 7) * dims.n_layers
     with ops.device_guard(ops._dev(mel_tm, taps, h, wsb, enc.pos)):
-        check(lib().desta_encoder_fwd(ctypes.byref(ws._c_dims), ctypes.byref(enc.c_weights), ops._p(mel_tm), n, ops._p(wsb), wsb.numel(),
-                                      ops._p(taps), ops._p(h), ops._stream()), "desta_encoder_fwd")
+        check(lib().desta_encoder_fwd(ctypes.byref(ws._c_dims), ctypes.byref(enc.c_weights), ops._p(mel_tm), ops._p(mel_floor), n,
+                                      ops._p(wsb), wsb.numel(), ops._p(taps), ops._p(h), ops._stream()), "desta_encoder_fwd")
 
 
 def connector_forward(con: ConnectorPack, dims: PathDims, ws: Workspace, out_f32: torch.Tensor):
@@ -278,11 +279,11 @@ def connector_forward(con: ConnectorPack, dims: PathDims, ws: Workspace, out_f32
     return out_f32
 
 
-def encoder_forward_ops(enc: EncoderPack, dims: PathDims, ws: Workspace, mel_tm: torch.Tensor):
+def encoder_forward_ops(enc: EncoderPack, dims: PathDims, ws: Workspace, mel_tm: torch.Tensor, mel_floor=None):
     """Per-op schedule of the encoder (one C-ABI call per kernel; profiling / reference for the native schedule)."""
     N, d, T = ws.N, dims.d_model, dims.max_pos
     hd = dims.head_dim
-    ops.im2col_k3(mel_tm, N, 2 * T, dims.n_mels, 1, ws.cols1)
+    ops.im2col_k3(mel_tm, N, 2 * T, dims.n_mels, 1, ws.cols1, mel_floor)
     ops.gemm(ws.cols1, enc.conv1_w, enc.conv1_b, out_bf16=ws.c1, gelu=True)
     ops.im2col_k3(ws.c1, N, 2 * T, d, 2, ws.cols2)
     if N * T > 128:

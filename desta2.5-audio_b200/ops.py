@@ -297,11 +297,15 @@ def splice_bwd(grad_out, descs, Q, dfeats):
         check(lib().desta_splice_bwd(_p(grad_out.contiguous()), _p(dev), len(descs), Q, S, d, _p(dfeats), _stream()), "desta_splice_bwd")
 
 
-def im2col_k3(x, N, T_in, C, stride, cols):
+def im2col_k3(x, N, T_in, C, stride, cols, mel_floor=None):
+    """mel_floor: the clip-max words of ``logmel(..., want_f32=False)`` - the deferred log-mel floor is applied on read."""
     _cuda(x, torch.bfloat16), _cuda(cols, torch.bfloat16)
     assert x.is_contiguous() and cols.is_contiguous() and cols.numel() == N * (T_in // stride) * 3 * C
-    with _op("im2col", 1, cols.numel() * 4, "byte", dev=_dev(x, cols)):
-        check(lib().desta_im2col_k3(_p(x), N, T_in, C, stride, _p(cols), _stream()), "desta_im2col_k3")
+    if mel_floor is not None:
+        _cuda(mel_floor, torch.float32)
+        assert mel_floor.is_contiguous() and mel_floor.numel() >= N
+    with _op("im2col", 1, cols.numel() * 4, "byte", dev=_dev(x, cols, mel_floor)):
+        check(lib().desta_im2col_k3(_p(x), N, T_in, C, stride, _p(cols), _p(mel_floor), _stream()), "desta_im2col_k3")
 
 
 def layer_mix(x, layer_weights, N, Q, out):
@@ -327,21 +331,27 @@ def logmel_plan(n_mels, device):
     return _plans[key]
 
 
-def logmel(wave, n_mels, *, n_valid=None, want_bf16_tm=False):
-    """wave [N,480000] f32 CUDA -> (mel f32 [N,n_mels,3000], optional bf16 time-major [N,3000,n_mels])."""
+def logmel(wave, n_mels, *, n_valid=None, want_bf16_tm=False, want_f32=True):
+    """wave [N,480000] f32 CUDA -> (mel f32 [N,n_mels,3000], optional bf16 time-major [N,3000,n_mels]).
+    ``want_f32=False`` (product path, one launch): returns (None, mel_tm, clip_max) where mel_tm lacks the per-clip floor
+    and clip_max is handed to ``im2col_k3(mel_floor=...)`` / ``engine.encoder_forward(mel_floor=...)``."""
     _cuda(wave, torch.float32)
     assert wave.dim() == 2 and wave.shape[1] == 480000 and wave.is_contiguous()
+    assert want_f32 or want_bf16_tm
     N = wave.shape[0]
     plan = logmel_plan(n_mels, wave.device)
-    out = torch.empty(N, n_mels, 3000, dtype=torch.float32, device=wave.device)
+    out = torch.empty(N, n_mels, 3000, dtype=torch.float32, device=wave.device) if want_f32 else None
     out_tm = torch.empty(N, 3000, n_mels, dtype=torch.bfloat16, device=wave.device) if want_bf16_tm else None
     cmax = torch.empty(max(N, 1), dtype=torch.float32, device=wave.device)
     if n_valid is not None:
         _cuda(n_valid, torch.int32)
-    nbytes = N * (480000 * 4 + n_mels * 3000 * 4)      # algorithmic bytes: waveform in + fp32 log-mel out (SURVEY.md §8d)
+    # algorithmic bytes (SURVEY.md §8d): waveform in + the log-mel tensor the call hands on (fp32 3.456 MB / clip, bf16 2.688)
+    nbytes = N * (480000 * 4 + n_mels * 3000 * (4 if want_f32 else 2))
     STATS["logmel_calls"] = STATS.get("logmel_calls", 0) + 1
-    with _op("logmel", 2, nbytes, "byte", dev=_dev(wave, n_valid, plan)):
+    with _op("logmel", 2 if want_f32 else 1, nbytes, "byte", dev=_dev(wave, n_valid, plan)):
         check(lib().desta_logmel(_p(wave), _p(n_valid), N, n_mels, _p(plan), _p(out), _p(out_tm), _p(cmax), _stream()), "desta_logmel")
+    if not want_f32:
+        return None, out_tm, cmax
     return out, out_tm
 
 

@@ -134,21 +134,23 @@ class WhisperPerceptionB200(nn.Module):
             self._t_versions = versions
         return self._t_pack_obj
 
-    def mel_time_major(self, input_features: torch.Tensor) -> torch.Tensor:
+    def mel_time_major(self, input_features: torch.Tensor):
+        """-> (bf16 time-major log-mel [N, 3000, n_mels], mel_floor).  Waveform input: ONE log-mel launch that leaves the
+        per-clip floor to the conv1 im2col (mel_floor = its clip-max words); reference-style mel input: (layout change, None)."""
         dev = self._device()
         x = input_features
         if x.dim() == 2:                                           # padded waveform from the processor shim
             if x.shape[-1] != ops.N_SAMPLES:
                 raise ValueError(f"waveform input must be padded/truncated to {ops.N_SAMPLES} samples, found {x.shape[-1]}")
             wave = x.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
-            _, mel_tm = ops.logmel(wave, self.dims.n_mels, want_bf16_tm=True)
-            return mel_tm
+            _, mel_tm, mel_floor = ops.logmel(wave, self.dims.n_mels, want_bf16_tm=True, want_f32=False)
+            return mel_tm, mel_floor
         expected = self.dims.max_pos * 2
         if x.shape[-1] != expected:                                # same check / message as modeling_desta25.py:555-560
             raise ValueError(f"Whisper expects the mel input features to be of length {expected}, but found "
                              f"{x.shape[-1]}. Make sure to pad the input mel features to {expected}.")
         # reference-style input (log-mel computed by the caller): layout change only
-        return x.to(device=dev, non_blocking=True).transpose(1, 2).to(torch.bfloat16).contiguous()
+        return x.to(device=dev, non_blocking=True).transpose(1, 2).to(torch.bfloat16).contiguous(), None
 
     @torch.no_grad()
     def _run_encoder(self, input_features: torch.Tensor, ws=None):
@@ -167,7 +169,8 @@ class WhisperPerceptionB200(nn.Module):
         cache, self._clip_cache = self._clip_cache, None           # one-shot: the cache serves the next perception call only
         src = cache.match(input_features) if cache is not None else None
         if src is None or all(j < 0 for j in src):
-            engine.encoder_forward(enc, self.dims, ws, self.mel_time_major(input_features))
+            mel_tm, mel_floor = self.mel_time_major(input_features)
+            engine.encoder_forward(enc, self.dims, ws, mel_tm, mel_floor=mel_floor)
             ws.h_valid = True
             return ws
         K, T, d = len(self.dims.tap_layers), self.dims.max_pos, self.dims.d_model
@@ -179,7 +182,8 @@ class WhisperPerceptionB200(nn.Module):
         if miss:
             sub = input_features.to(dev)[miss].contiguous()
             taps_m = torch.empty(K, len(miss) * T, d, dtype=torch.bfloat16, device=dev)
-            engine.encoder_forward(enc, self.dims, ws, self.mel_time_major(sub), taps=taps_m, h=ws.h[:len(miss) * T])
+            mel_tm, mel_floor = self.mel_time_major(sub)
+            engine.encoder_forward(enc, self.dims, ws, mel_tm, taps=taps_m, h=ws.h[:len(miss) * T], mel_floor=mel_floor)
             taps4.index_copy_(1, torch.tensor(miss, device=dev), taps_m.view(K, len(miss), T, d))
         ws.h_valid = False              # the residual stream of the cached clips was not recomputed (only the ASR pass reads it)
         self.encoder_clips_reused = getattr(self, "encoder_clips_reused", 0) + len(hit)

@@ -34,8 +34,13 @@ const char* desta_last_error(void);
 size_t desta_logmel_plan_bytes(int n_mels);
 int desta_logmel_plan_build(int n_mels, void* host_buf, size_t bytes);
 /* wave [N,480000] f32 (already right-padded/truncated; n_valid[N] optional: samples >= n_valid[i] read as 0).
- * out_f32 [N,n_mels,3000] (reference layout) and/or out_bf16_tm [N,3000,n_mels] (time-major, feeds conv1).
- * clip_max [N] f32 scratch.  plan = device copy of the plan buffer. */
+ * plan = device copy of the plan buffer.  clip_max [N] 32-bit words, written by the call: the per-clip maximum of
+ * log10(mel) in the library's order-preserving encoding.
+ *   out_f32 != NULL: out_f32 [N,n_mels,3000] (reference layout) and, if given, out_bf16_tm [N,3000,n_mels] (time-major)
+ *     receive the final values  (max(L, Lmax - 8) + 4) / 4   (two launches).
+ *   out_f32 == NULL (product path, ONE launch, algorithmic HBM traffic): out_bf16_tm receives (L + 4) / 4 WITHOUT the
+ *     per-clip floor.  The floor commutes with the monotone affine map and with bf16 rounding, so the consumer applies
+ *     max(v, bf16((Lmax - 8 + 4) / 4)) on read: pass clip_max as `mel_clip_max` to desta_im2col_k3 / desta_encoder_fwd. */
 int desta_logmel(const float* wave, const int32_t* n_valid, int N, int n_mels, const void* plan,
                  float* out_f32, void* out_bf16_tm, float* clip_max, void* stream);
 
@@ -93,8 +98,10 @@ int desta_attention(const void* q, int ldq, const void* k, int ldk, const void* 
                     const desta_dropout* drop /* optional: dropout on the attention probabilities */, void* stream);
 
 /* im2col for the conv stem (modeling_desta25.py:563-564): Conv1d(k=3,pad=1,stride s) as GEMM rows.
- * x time-major bf16 [N, T_in, C] -> cols bf16 [N*T_out, 3*C] with column index = tap*C + c  (T_out = T_in/stride). */
-int desta_im2col_k3(const void* x, int N, int T_in, int C, int stride, void* cols, void* stream);
+ * x time-major bf16 [N, T_in, C] -> cols bf16 [N*T_out, 3*C] with column index = tap*C + c  (T_out = T_in/stride).
+ * mel_clip_max: NULL, or the clip_max words of a desta_logmel call with out_f32 == NULL: clip n's values are read as
+ * max(v, bf16((Lmax_n - 8 + 4) / 4)) (the log-mel floor of feature_extraction_whisper.py:157-158, applied here). */
+int desta_im2col_k3(const void* x, int N, int T_in, int C, int stride, void* cols, const float* mel_clip_max, void* stream);
 
 /* Q-Former layer mix (modeling_desta25.py:600-604): out[n,q,:] = sum_k softmax(layer_weights[q,:])[k] * x[k,n,q,:]
  * x fp32 [taps, N*Q, D] -> out fp32 [N*Q, D]. */
@@ -219,10 +226,12 @@ typedef struct desta_encoder_weights {
   const desta_enc_layer* layers;              /* [n_layers] (host array) */
 } desta_encoder_weights;
 size_t desta_encoder_workspace_bytes(const desta_dims* dims, int N);
-/* mel_tm: bf16 time-major log-mel [N, 2*max_pos, n_mels].  taps: bf16 [n_taps, N*max_pos, d].  h: fp32 [N*max_pos, d]
- * residual stream after the last layer (input of the final LayerNorm for the ASR pass). */
-int desta_encoder_fwd(const desta_dims* dims, const desta_encoder_weights* w, const void* mel_tm, int N, void* workspace,
-                      size_t workspace_bytes, void* taps, float* h, void* stream);
+/* mel_tm: bf16 time-major log-mel [N, 2*max_pos, n_mels]; mel_clip_max: NULL if mel_tm is final, else the clip_max words of
+ * the desta_logmel call that produced it without the floor (see desta_logmel / desta_im2col_k3).
+ * taps: bf16 [n_taps, N*max_pos, d].  h: fp32 [N*max_pos, d] residual stream after the last layer (input of the final
+ * LayerNorm for the ASR pass). */
+int desta_encoder_fwd(const desta_dims* dims, const desta_encoder_weights* w, const void* mel_tm, const float* mel_clip_max, int N,
+                      void* workspace, size_t workspace_bytes, void* taps, float* h, void* stream);
 
 typedef struct desta_qf_layer {
   const void* s_qkv_w; const float* s_qkv_b; const void* s_o_w; const float* s_o_b; const float *s_ln_w, *s_ln_b;

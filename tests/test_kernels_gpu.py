@@ -288,6 +288,15 @@ def test_logmel_vs_oracle_and_golden(n_mels, golden_dir):
         noisy[i, min(len(w), 480000):] = 9.0                        # garbage beyond n_valid must be ignored
     mel2, _ = ops.logmel(torch.from_numpy(noisy).cuda(), n_mels, n_valid=lens)
     assert np.array_equal(mel2.cpu().numpy(), mel)
+    # product path: ONE launch, bf16 time-major output without the per-clip floor + clip-max words; the conv1 im2col applies
+    # the floor on read.  max() commutes with the monotone affine map and the bf16 rounding: bit-identical to the two-pass result.
+    none, raw_tm, cmax = ops.logmel(torch.from_numpy(padded).cuda(), n_mels, want_bf16_tm=True, want_f32=False)
+    assert none is None and raw_tm.shape == mel_tm.shape
+    N = len(waves)
+    cols = torch.empty(N * 3000, 3 * n_mels, dtype=torch.bfloat16, device="cuda")
+    ops.im2col_k3(raw_tm, N, 3000, n_mels, 1, cols, mel_floor=cmax)
+    assert torch.equal(cols[:, n_mels:2 * n_mels].reshape(N, 3000, n_mels), mel_tm)      # centre tap = the log-mel itself
+    assert not torch.equal(raw_tm, mel_tm)                                               # the floor did act (silence tails)
 
 
 # ------------------------------------------------------------------ splice

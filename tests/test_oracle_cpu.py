@@ -124,13 +124,22 @@ def test_host_mel_plan_matches_oracle_filters():
         n = L.desta_logmel_plan_bytes(n_mels)
         h = np.zeros(n // 4, dtype=np.int32)
         assert L.desta_logmel_plan_build(n_mels, h.ctypes.data_as(ctypes.c_void_p), n) == 0
-        nm, mw = int(h[0]), int(h[1])
-        off = 16 + 400 + 400 + 402 + 201
-        lo, cnt = h[off:off + nm], h[off + nm:off + 2 * nm]
-        w = h[off + 2 * nm:].view(np.float32).reshape(nm, mw)
-        rec = np.zeros((201, nm), np.float32)
+        # plan layout (csrc/logmel.cu): header[32] | hann/2 [400] | tw1 [20][16] c64 | tw2 [11][16] c64 | meta [nm] int2 | taps float4
+        nm, total4 = int(h[0]), int(h[1])
+        off = 32 + 400 + 640 + 352
+        meta = h[off:off + 2 * nm].reshape(nm, 2)
+        lo, n4, woff = meta[:, 0] & 0xFFFF, meta[:, 0] >> 16, meta[:, 1]
+        w = h[off + 2 * nm:].view(np.float32)
+        assert w.size == 4 * total4 == 4 * int(n4.sum())
+        rec = np.zeros((201 + 4, nm), np.float32)
         for m in range(nm):
-            rec[lo[m]:lo[m] + cnt[m], m] = w[m, :cnt[m]]
-        assert np.array_equal(rec, o_mel.mel_filter_bank(n_mels).astype(np.float32))
-        hann = h[16:416].view(np.float32)
-        assert np.abs(hann - torch.hann_window(400).numpy()).max() < 1e-6
+            rec[lo[m]:lo[m] + 4 * n4[m], m] = w[4 * woff[m]:4 * (woff[m] + n4[m])]      # taps zero-padded to groups of four
+        assert np.all(rec[201:] == 0)
+        assert np.array_equal(rec[:201], o_mel.mel_filter_bank(n_mels).astype(np.float32))
+        hann = h[32:432].view(np.float32)
+        assert np.abs(2.0 * hann - torch.hann_window(400).numpy()).max() < 1e-6      # halved: the real-FFT untangling drops its 1/2
+        split = h[3:14]                                                              # mel range of each of the 10 warps
+        assert split[0] == 0 and split[10] == nm and np.all(np.diff(split) >= 0) and np.all(split % 2 == 0)
+        tw1 = h[32 + 400:32 + 1040].view(np.float32).reshape(20, 16, 2)
+        k1, t = 7, 9
+        assert abs(tw1[k1, t, 0] - np.cos(2 * np.pi * k1 * t / 200)) < 1e-6 and abs(tw1[k1, t, 1] + np.sin(2 * np.pi * k1 * t / 200)) < 1e-6

@@ -93,14 +93,15 @@ def test_native_schedule_equals_per_op_schedule(name):
     wave = torch.from_numpy(np.stack([o_mel.pad_or_truncate(w) for w in waves])).cuda()
     enc, con = p._packs()
     ws = p._workspace(3)
-    mel_tm = p.mel_time_major(wave)
+    mel_tm, mel_floor = p.mel_time_major(wave)
+    assert mel_floor is not None                       # waveform input: the floor is left to the conv1 im2col
     out_native = torch.empty(3 * cfg.prompt_size, cfg.d_llm, device="cuda")
     out_ops = torch.empty_like(out_native)
-    engine.encoder_forward(enc, p.dims, ws, mel_tm)
+    engine.encoder_forward(enc, p.dims, ws, mel_tm, mel_floor=mel_floor)
     engine.connector_forward(con, p.dims, ws, out_native)
     taps_native, h_native = ws.taps.clone(), ws.h.clone()
     ws.taps.zero_(); ws.h.zero_()
-    engine.encoder_forward_ops(enc, p.dims, ws, mel_tm)
+    engine.encoder_forward_ops(enc, p.dims, ws, mel_tm, mel_floor)
     engine.connector_forward_ops(con, p.dims, ws, out_ops)
     assert torch.equal(ws.taps, taps_native) and torch.equal(ws.h, h_native) and torch.equal(out_ops, out_native)
     assert out_native.abs().max().item() > 0
@@ -108,8 +109,8 @@ def test_native_schedule_equals_per_op_schedule(name):
     import ctypes
     from desta_b200._lib import DestaError, lib
     small = torch.empty(16, dtype=torch.uint8, device="cuda")
-    rc = lib().desta_encoder_fwd(ctypes.byref(ws._c_dims), ctypes.byref(enc.c_weights), ctypes.c_void_p(mel_tm.data_ptr()), 3,
-                                 ctypes.c_void_p(small.data_ptr()), 16, ctypes.c_void_p(ws.taps.data_ptr()),
+    rc = lib().desta_encoder_fwd(ctypes.byref(ws._c_dims), ctypes.byref(enc.c_weights), ctypes.c_void_p(mel_tm.data_ptr()),
+                                 ctypes.c_void_p(mel_floor.data_ptr()), 3, ctypes.c_void_p(small.data_ptr()), 16, ctypes.c_void_p(ws.taps.data_ptr()),
                                  ctypes.c_void_p(ws.h.data_ptr()), None)
     assert rc == -1 and b"workspace too small" in lib().desta_last_error()
 

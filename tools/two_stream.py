@@ -24,8 +24,8 @@ enc, con = p._packs()
 
 
 def run(ws, wv, out):
-    _, mel_tm = ops.logmel(wv, p.dims.n_mels, want_bf16_tm=True)
-    engine.encoder_forward(enc, p.dims, ws, mel_tm)
+    _, mel_tm, mel_floor = ops.logmel(wv, p.dims.n_mels, want_bf16_tm=True, want_f32=False)
+    engine.encoder_forward(enc, p.dims, ws, mel_tm, mel_floor=mel_floor)
     engine.connector_forward(con, p.dims, ws, out)
 
 
