@@ -26,12 +26,21 @@ layernorm_bwd_kernel(const float* __restrict__ dy, int lddy, const float* __rest
     const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * ldx);
     const float4* dr = reinterpret_cast<const float4*>(dy + (size_t)row * lddy);
     float4 xv[MAXV], dv[MAXV];
-    float s = 0.f;
+    // all 2 MAXV 16-byte loads of the row are issued before the first use (one memory round trip per row; with the sum in
+    // the same loop the compiler kept load -> use pairs and every pair paid the full DRAM latency: ncu long_scoreboard 6.8)
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
       const int idx = lane + 32 * i;
-      if (idx < nv) { xv[i] = xr[idx]; dv[i] = dr[idx]; s += (xv[i].x + xv[i].y) + (xv[i].z + xv[i].w); }
+      xv[i] = idx < nv ? __ldcs(xr + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int idx = lane + 32 * i;
+      dv[i] = idx < nv ? __ldcs(dr + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) s += (xv[i].x + xv[i].y) + (xv[i].z + xv[i].w);
 #pragma unroll
     for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     const float mean = s / (float)D;
@@ -81,20 +90,30 @@ layernorm_bwd_kernel(const float* __restrict__ dy, int lddy, const float* __rest
       }
     }
   }
+  // warps add their partials to the block's copy one after the other (plain 16-byte read-modify-writes: shared-memory
+  // atomics on the same 2 D addresses from 8 warps cost more than the whole row loop)
+  for (int w = 0; w < nwarp; ++w) {
+    if (warp == w) {
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    const int idx = lane + 32 * i;
-    if (idx < nv) {
-      atomicAdd(&s_red[4 * idx + 0], ag[i].x); atomicAdd(&s_red[4 * idx + 1], ag[i].y);
-      atomicAdd(&s_red[4 * idx + 2], ag[i].z); atomicAdd(&s_red[4 * idx + 3], ag[i].w);
-      atomicAdd(&s_red[D + 4 * idx + 0], ab[i].x); atomicAdd(&s_red[D + 4 * idx + 1], ab[i].y);
-      atomicAdd(&s_red[D + 4 * idx + 2], ab[i].z); atomicAdd(&s_red[D + 4 * idx + 3], ab[i].w);
+      for (int i = 0; i < MAXV; ++i) {
+        const int idx = lane + 32 * i;
+        if (idx < nv) {
+          float4* pg = reinterpret_cast<float4*>(s_red) + idx;
+          float4* pb = reinterpret_cast<float4*>(s_red + D) + idx;
+          float4 a = *pg, b = *pb;
+          a.x += ag[i].x; a.y += ag[i].y; a.z += ag[i].z; a.w += ag[i].w;
+          b.x += ab[i].x; b.y += ab[i].y; b.z += ab[i].z; b.w += ab[i].w;
+          *pg = a; *pb = b;
+        }
+      }
     }
+    __syncthreads();
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < D; i += blockDim.x) {
-    atomicAdd(dgamma + i, s_red[i]);
-    atomicAdd(dbeta + i, s_red[D + i]);
+  // one 16-byte reduction per four columns (red.global.add.v4.f32): with one CTA per SM every address sees <= 148 of them
+  for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+    const float4 a = reinterpret_cast<const float4*>(s_red)[i], b = reinterpret_cast<const float4*>(s_red + D)[i];
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dgamma + 4 * i), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w) : "memory");
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dbeta + 4 * i), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
   }
 }
 
@@ -216,12 +235,16 @@ colsum_vec_kernel(const T* __restrict__ x, int ld, int M, int N, float* __restri
 }
 
 // ---- layer mix backward: dx[k,r,:] = w[q,k] * dm[r,:];  dlw[q,k] = w[q,k] * (g[q,k] - sum_k' w[q,k'] g[q,k']),
-//      g[q,k] = sum_{n,d} dm[n,q,d] * x[k,n,q,d].  One block per query index q. ----
+//      g[q,k] = sum_{n,d} dm[n,q,d] * x[k,n,q,d].  Grid (Q, clip chunks): the softmax backward is linear in g, so every CTA
+//      turns its partial g into a partial dlw and adds it atomically.  16-byte loads / stores. ----
+template <int TAPS>
 __global__ void __launch_bounds__(256)
-layer_mix_bwd_kernel(const float* __restrict__ dm, const float* __restrict__ x, const float* __restrict__ lw, int taps, int N,
-                     int Q, int D, float* __restrict__ dx, float* __restrict__ dlw) {
+layer_mix_bwd_kernel(const float* __restrict__ dm, const float* __restrict__ x, const float* __restrict__ lw, int taps_rt, int N,
+                     int Q, int D, int clips_per_cta, float* __restrict__ dx, float* __restrict__ dlw) {
   __shared__ float s_w[16], s_g[16][8];
+  const int taps = TAPS ? TAPS : taps_rt;
   const int q = blockIdx.x;
+  const int n0 = blockIdx.y * clips_per_cta, n1 = min(N, n0 + clips_per_cta);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
     float mx = -INFINITY, den = 0.f;
@@ -230,24 +253,35 @@ layer_mix_bwd_kernel(const float* __restrict__ dm, const float* __restrict__ x, 
     for (int k = 0; k < taps; ++k) s_w[k] = expf(lw[q * taps + k] - mx) / den;
   }
   __syncthreads();
-  float g[16];
-  for (int k = 0; k < taps; ++k) g[k] = 0.f;
-  const size_t tap_stride = (size_t)N * Q * D;
-  for (int n = 0; n < N; ++n) {
-    const size_t row = ((size_t)n * Q + q) * D;
-    for (int d = threadIdx.x; d < D; d += blockDim.x) {
-      const float v = dm[row + d];
-      for (int k = 0; k < taps; ++k) {
-        g[k] = fmaf(v, x[k * tap_stride + row + d], g[k]);
-        dx[k * tap_stride + row + d] = s_w[k] * v;
+  float g[TAPS ? TAPS : 16], wk[TAPS ? TAPS : 16];
+#pragma unroll
+  for (int k = 0; k < (TAPS ? TAPS : 16); ++k) { g[k] = 0.f; wk[k] = k < taps ? s_w[k] : 0.f; }
+  const size_t tap_stride4 = (size_t)N * Q * D / 4;
+  const int D4 = D >> 2, total = (n1 - n0) * D4;
+  const float4* dm4 = reinterpret_cast<const float4*>(dm);
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  float4* dx4 = reinterpret_cast<float4*>(dx);
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int n = n0 + i / D4, d = i - (i / D4) * D4;
+    const size_t at = ((size_t)n * Q + q) * D4 + d;
+    const float4 v = dm4[at];
+#pragma unroll
+    for (int k = 0; k < (TAPS ? TAPS : 16); ++k) {
+      if (k < taps) {
+        const float4 xv = x4[k * tap_stride4 + at];
+        g[k] += (v.x * xv.x + v.y * xv.y) + (v.z * xv.z + v.w * xv.w);
+        dx4[k * tap_stride4 + at] = make_float4(wk[k] * v.x, wk[k] * v.y, wk[k] * v.z, wk[k] * v.w);
       }
     }
   }
-  for (int k = 0; k < taps; ++k) {
-    float t = g[k];
 #pragma unroll
-    for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-    if (lane == 0) s_g[k][warp] = t;
+  for (int k = 0; k < (TAPS ? TAPS : 16); ++k) {
+    if (k < taps) {
+      float t = g[k];
+#pragma unroll
+      for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      if (lane == 0) s_g[k][warp] = t;
+    }
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -258,7 +292,7 @@ layer_mix_bwd_kernel(const float* __restrict__ dm, const float* __restrict__ x, 
       gk[k] = t;
       dot += s_w[k] * t;
     }
-    for (int k = 0; k < taps; ++k) dlw[q * taps + k] += s_w[k] * (gk[k] - dot);
+    for (int k = 0; k < taps; ++k) atomicAdd(dlw + q * taps + k, s_w[k] * (gk[k] - dot));
   }
 }
 
@@ -291,7 +325,9 @@ extern "C" int desta_layernorm_bwd(const float* dy, int lddy, const float* x, in
     return DESTA_ERR_ARG;
   }
   int grid = (M + 7) / 8;
-  const int cap = num_sms() * 4;
+  // one CTA per SM: the per-CTA dgamma / dbeta partials end in global reductions onto the same 2 D addresses, and
+  // same-address reductions serialise in L2 (592 CTAs: 0.11 ms per call for 147 MB; one per SM: see profiles/r2_train_kernels.md)
+  const int cap = num_sms();
   if (grid > cap) grid = cap;
   const size_t sm = 2 * (size_t)D * 4;
   cudaStream_t s = (cudaStream_t)stream;
@@ -351,7 +387,14 @@ extern "C" int desta_layer_mix_bwd(const float* dm, const float* x, const float*
   if (!dm || !x || !layer_weights || !dx || !dlw) { set_error("desta_layer_mix_bwd: null pointer"); return DESTA_ERR_ARG; }
   if (taps > 16) { set_error("desta_layer_mix_bwd: at most 16 taps"); return DESTA_ERR_ARG; }
   if (N <= 0) return DESTA_OK;
-  layer_mix_bwd_kernel<<<Q, 256, 0, (cudaStream_t)stream>>>(dm, x, layer_weights, taps, N, Q, D, dx, dlw);
+  if (D % 4) { set_error("desta_layer_mix_bwd: D must be a multiple of 4"); return DESTA_ERR_ARG; }
+  // enough (query, clip chunk) CTAs for ~4 per SM
+  int chunks = (4 * num_sms() + Q - 1) / Q;
+  if (chunks > N) chunks = N;
+  const int per = (N + chunks - 1) / chunks;
+  const dim3 grid(Q, (N + per - 1) / per);
+  if (taps == 4) layer_mix_bwd_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(dm, x, layer_weights, taps, N, Q, D, per, dx, dlw);
+  else layer_mix_bwd_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(dm, x, layer_weights, taps, N, Q, D, per, dx, dlw);
   return check_launch("layer_mix_bwd_kernel");
 }
 

@@ -82,6 +82,22 @@ def bench_attn_bwd():
         print(f"attn_bwd {name:9s} B={B} H={H} Tq={Tq} Tk={Tk}: {ms:.3f} ms  {10.0 * B * H * Tq * Tk * 64 / ms / 1e9:.0f} TFLOP/s", flush=True)
 
 
+def bench_train_ew():
+    """HBM-bound kernels of the connector backward at the training shape (32 clips: R = 4 * 32 * 64 = 8192 rows of 1280)."""
+    R, D, K, N, Q = 8192, 1280, 4, 32, 64
+    dy, x = torch.randn(R, D, device="cuda"), torch.randn(R, D, device="cuda")
+    gamma = torch.rand(D, device="cuda") + 0.5
+    dg, db = torch.zeros(D, device="cuda"), torch.zeros(D, device="cuda")
+    dx, dxb = torch.empty(R, D, device="cuda"), torch.empty(R, D, device="cuda", dtype=torch.bfloat16)
+    ms = timeit(lambda: ops.layernorm_bwd(dy, x, gamma, 1e-12, dg, db, dx_f32=dx, dx_bf16=dxb), iters=20)
+    print(f"layernorm_bwd R={R} D={D}: {ms:.4f} ms  {R * D * 14 / ms / 1e6:.0f} GB/s (dy, x read; dx fp32 + bf16 written)", flush=True)
+    dm, xs = torch.randn(N * Q, D, device="cuda"), torch.randn(K, N * Q, D, device="cuda")
+    lw = torch.randn(Q, K, device="cuda")
+    gx, dlw = torch.empty(K, N * Q, D, device="cuda"), torch.zeros(Q, K, device="cuda")
+    ms = timeit(lambda: ops.layer_mix_bwd(dm, xs, lw, N, Q, gx, dlw), iters=20)
+    print(f"layer_mix_bwd K={K} N={N} Q={Q} D={D}: {ms:.4f} ms  {N * Q * D * 4 * (1 + 2 * K) / ms / 1e6:.0f} GB/s", flush=True)
+
+
 def bench_mel():
     for N in (64, 256):
         wave = torch.clamp(0.1 * torch.randn(N, 480000, device="cuda"), -1, 1)
@@ -121,4 +137,4 @@ def bench_resample():
 if __name__ == "__main__":
     which = sys.argv[1:] or ["gemm", "attn", "mel", "splice"]
     for w in which:
-        {"gemm": bench_gemm, "attn": bench_attn, "attn_bwd": bench_attn_bwd, "mel": bench_mel, "splice": bench_splice, "resample": bench_resample}[w]()
+        {"gemm": bench_gemm, "attn": bench_attn, "attn_bwd": bench_attn_bwd, "mel": bench_mel, "train_ew": bench_train_ew, "splice": bench_splice, "resample": bench_resample}[w]()
