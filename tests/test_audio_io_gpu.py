@@ -239,3 +239,20 @@ def test_bad_arguments_fail_loudly():
         ops.decode_resample(pcm, [(0, 10, 0)], 9, 1, 22050, 16000, out)              # unknown sample format
     with pytest.raises(Exception):
         ops.decode_resample(pcm, [(0, 10, 0)], W.S16, 0, 22050, 16000, out)          # zero channels
+
+
+@pytest.mark.parametrize("sr", [8000, 11025, 22050, 24000, 32000, 44100, 48000])
+def test_device_resampler_vs_soxr_fixtures(sr):
+    """The CUDA resampler against the reference's own resampler (librosa soxr_hq fixtures, oracle/make_soxr_fixtures.py);
+    skipped until the fixtures can be generated (no librosa / soxr in the build image: row n3 stays parity-unpinned)."""
+    import os
+    from test_audio_io_cpu import SOXR_FIXTURES, passband_deviation
+    if not os.path.exists(SOXR_FIXTURES):
+        pytest.skip("tests/golden/resample_soxr.npz not generated yet")
+    from oracle.make_soxr_fixtures import fixture_input
+    gold = np.load(SOXR_FIXTURES)[f"y_{sr}"]
+    x = fixture_input(sr)
+    got, m = _run(W.encode(x[:, None].astype(np.float64), W.F32), W.F32, 1, sr, len(x), len(gold) + 64)
+    assert m == len(gold)
+    in_band, transition = passband_deviation(got[:m], gold, sr)
+    assert in_band < 3e-5, f"{sr} Hz: pass-band deviation from soxr_hq {in_band:.2e} (transition band {transition:.2e})"
