@@ -641,7 +641,8 @@ def run_ours(args):
             return train_step
 
         res = {}
-        for sync in (("none", args.grad_sync) if world > 1 else ("none",)):
+        modes = ("overlap", "bucket") if args.grad_sync == "auto" else (args.grad_sync,)
+        for sync in ((("none",) + modes) if world > 1 else ("none",)):
             fn = make_step(sync)
             for _ in range(max(args.warmup, 3)):
                 fn()
@@ -649,7 +650,10 @@ def run_ours(args):
             res[sync] = (ms / args.steps, rank_stats(ms_local / args.steps, world, dev))
             torch.cuda.synchronize()
             time.sleep(0.5)
-        key = args.grad_sync if world > 1 else "none"
+        # "auto": both exchange schedules are timed and the faster one is the step (at 8 GPUs NCCL's 24-channel NVLS kernels
+        # and the persistent all-SM GEMM grids of the backward take turns rather than overlap, so the single bucketed
+        # all-reduce after the backward wins; at 2 GPUs they tie - profiles/r2_train_8gpu_comm.md)
+        key = min(modes, key=lambda m: res[m][0]) if world > 1 else "none"
         step_ms, ranks = res[key]
         fn = make_step(key)
         fn()
@@ -666,7 +670,8 @@ def run_ours(args):
             "comm": {"collective": "NCCL all-reduce (sum) of the fp32 connector-gradient arena, averaged like DDP" if world > 1 else "none (1 GPU)",
                      "bytes_per_step": 4 * n_params if world > 1 else 0, "mode": key if world > 1 else "none",
                      "ms_per_step_without_exchange": round(res["none"][0], 3),
-                     "exposed_ms": round(step_ms - res["none"][0], 3) if world > 1 else 0.0},
+                     "exposed_ms": round(step_ms - res["none"][0], 3) if world > 1 else 0.0,
+                     "ms_per_step_by_mode": {m: round(res[m][0], 3) for m in res}},
             "roofline": roofline_of(gm, total_ms, None, "no capture for the training step"),
             "step_tensor_frac": round(train_flops_per_clip(w) * n / (step_ms * 1e-3) / 1e12 / tf_sust, 4),
             "kernels": fam,
@@ -676,6 +681,22 @@ def run_ours(args):
         del wave_dev, grad_emb
         return line
 
+    if args.sweep:
+        # BASELINE configs[2]: batch sweep (clips per GPU per step) of the forward path at this GPU count, one JSON line per size
+        for n in [int(v) for v in args.sweep.split(",")]:
+            perception._ws = {}
+            torch.cuda.empty_cache()
+            args.check = False
+            line = forward_line(n)
+            keep = ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "dtype", "data", "config", "e2e",
+                    "gpu_launches", "clocks", "rank_ms_per_step", "step_tensor_frac")
+            line = {k: line[k] for k in keep}
+            line["sweep"] = True
+            if rank == 0:
+                print(json.dumps(line), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     if args.mode == "train":
         line = train_line(args.clips)
         line.update({"steps": args.steps, "warmup": max(args.warmup, 3), "higher_is_better": True, "vs_baseline": None, "data": "synthetic",
@@ -737,10 +758,12 @@ def main():
     ap.add_argument("--no-train", action="store_true", help="forward mode: skip the `train` object")
     ap.add_argument("--cpu-clips", type=int, default=8, help="clips in the bounded cpu_baseline sample (~10 s of CPU work on 16 cores)")
     ap.add_argument("--ref-clips", type=int, default=2, help="clips per step of the --impl reference arm")
-    ap.add_argument("--grad-sync", default="overlap", choices=["overlap", "bucket"],
-                    help="training on N > 1 GPUs: all-reduce overlapped with the backward (default) or one flat bucket after it")
+    ap.add_argument("--grad-sync", default="auto", choices=["auto", "overlap", "bucket"],
+                    help="training on N > 1 GPUs: all-reduce overlapped with the backward, one flat bucket after it, or (default) "
+                         "time both and report the faster")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-check", dest="check", action="store_false", help="skip the output check of the benchmark batch")
+    ap.add_argument("--sweep", default="", help="comma-separated clips-per-GPU sizes: one forward line per size (BASELINE configs[2])")
     ap.add_argument("--graph", action="store_true", help="forward mode: replay log-mel + encoder + connector as one CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
