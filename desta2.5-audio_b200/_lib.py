@@ -89,6 +89,7 @@ EXPORTS = {
                                 c_int, c_void_p]),
     "desta_attention": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int,
                                 c_int, c_float, c_void_p, POINTER(Dropout), c_void_p]),
+    "desta_attention_variant": (c_int, [c_int]),
     "desta_gemm_bf16_wgrad": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "desta_attention_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int,
                                     c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,

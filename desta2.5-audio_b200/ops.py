@@ -182,6 +182,11 @@ def attention(q, k, v, out, batch, heads, Tq, Tk, scale, lse=None, drop=None):
                                     batch, heads, Tq, Tk, float(scale), _p(lse), _dp(drop), _stream()), "desta_attention")
 
 
+def attention_variant(v=-1):
+    """Select (v >= 0) or query the kernel variant behind the encoder's attention calls; returns the previous value."""
+    return lib().desta_attention_variant(int(v))
+
+
 def attention_bwd(q, k, v, o, dout, lse, dq, dk, dv, batch, heads, Tq, Tk, scale, drop=None):
     for t in (q, k, v, o, dout, dq, dk, dv):
         _cuda(t, torch.bfloat16)

@@ -97,6 +97,12 @@ int desta_attention(const void* q, int ldq, const void* k, int ldk, const void* 
                     int batch, int heads, int Tq, int Tk, float scale, float* lse /* optional [batch,heads,Tq] */,
                     const desta_dropout* drop /* optional: dropout on the attention probabilities */, void* stream);
 
+/* Kernel variant serving the encoder's calls of desta_attention (scale * log2 e == 1): 0 = four softmax warps, softmax shift
+ * applied by the tensor cores (default); 1 = eight softmax warps with Q in tensor memory, one tile per CTA; 2 = the same,
+ * persistent.  v < 0 only queries.  Returns the previous value.  All variants are tested against the same oracle; the
+ * selector exists for A/B measurements (profiles/r2_attention_unit8.md).  Process-wide; not part of the reference's interface. */
+int desta_attention_variant(int v);
+
 /* im2col for the conv stem (modeling_desta25.py:563-564): Conv1d(k=3,pad=1,stride s) as GEMM rows.
  * x time-major bf16 [N, T_in, C] -> cols bf16 [N*T_out, 3*C] with column index = tap*C + c  (T_out = T_in/stride).
  * mel_clip_max: NULL, or the clip_max words of a desta_logmel call with out_f32 == NULL: clip n's values are read as

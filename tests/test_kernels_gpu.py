@@ -223,13 +223,21 @@ def test_attention_peaky_softmax():
     assert _rel(out, ref) < 2e-2
 
 
+@pytest.fixture(params=[0, 1, 2], ids=["unit4", "unit8", "unit8_persistent"])
+def attn_variant(request):
+    """Run a test under each kernel variant of the encoder's attention (include/desta_b200.h: desta_attention_variant)."""
+    old = ops.attention_variant(request.param)
+    yield request.param
+    ops.attention_variant(old)
+
+
 LN2 = 0.6931471805599453
 
 
 @pytest.mark.parametrize("B,H,Tq,Tk,amp,ramp", [(2, 3, 1500, 1500, 1.0, 0.0), (1, 2, 300, 700, 1.0, 0.0), (2, 2, 64, 1500, 1.5, 0.0),
                                                 (1, 2, 128, 1024, 3.0, 0.0), (1, 2, 256, 960, 1.0, 6.0), (1, 1, 128, 100, 2.0, 0.0),
                                                 (1, 2, 200, 64, 1.0, 0.0), (1, 2, 130, 192, 1.0, 3.0)])
-def test_attention_unit_scale_mode(B, H, Tq, Tk, amp, ramp):
+def test_attention_unit_scale_mode(B, H, Tq, Tk, amp, ramp, attn_variant):
     """scale = ln 2 (scale * log2 e == 1) selects the kernel variant whose softmax shift is applied by the tensor cores
     (the encoder's call: q carries head_dim^-1/2 * log2 e).  Same oracle, same tolerance; lse in the log2 domain.
     `ramp` makes the scores grow along the keys so that later blocks raise the reference (lazy rescale + shift update:
@@ -259,6 +267,43 @@ def test_attention_unit_scale_mode(B, H, Tq, Tk, amp, ramp):
     out2 = torch.zeros_like(out)
     ops.attention((q.float() * 0.5).to(torch.bfloat16), k, v, out2, B, H, Tq, Tk, 2 * LN2)
     assert _rel(out2, ref) < 2e-2
+
+
+@pytest.mark.parametrize("B,H,ramp", [(6, 5, 0.0), (7, 5, 6.0), (9, 4, 0.0)])
+def test_attention_unit_persistent_tiles(B, H, ramp, attn_variant):
+    """Encoder shape (Tq = Tk = 1500 -> 24 key blocks) with more tiles than two CTAs per SM: the eight-warp kernel runs
+    PERSISTENT (a CTA walks several tiles; K / V rings, TMEM and barrier phases carry across the tile boundary; CTAs get
+    unequal tile counts).  `ramp` grows the keys so that later blocks overflow the fixed block-0 reference: those tiles are
+    noted and recomputed by the general path after the loop (several per CTA: the barrier block is invalidated in between).
+    Every output row is checked, and every row of the log-sum-exp."""
+    Tq = Tk = 1500
+    g = torch.Generator(device="cuda").manual_seed(B * 31 + H)
+    d = H * 64
+    q = torch.randn(B * Tq, d, device="cuda", generator=g).to(torch.bfloat16)
+    k = torch.randn(B * Tk, d, device="cuda", generator=g).to(torch.bfloat16)
+    if ramp:
+        growth = torch.linspace(1.0, ramp, Tk, device="cuda").repeat(B)[:, None]
+        growth[: Tk] = 1.0                       # clip 0 stays tame: fast and recomputed tiles side by side in one launch
+        k = (k.float() * growth).to(torch.bfloat16)
+    v = torch.randn(B * Tk, d, device="cuda", generator=g).to(torch.bfloat16)
+    out = torch.zeros(B * Tq, d, device="cuda", dtype=torch.bfloat16)
+    lse = torch.empty(B * H * Tq, device="cuda")
+    ops.attention(q, k, v, out, B, H, Tq, Tk, LN2, lse=lse)
+    qf = q.float().reshape(B, Tq, H, 64).transpose(1, 2)
+    kf = k.float().reshape(B, Tk, H, 64).transpose(1, 2)
+    vf = v.float().reshape(B, Tk, H, 64).transpose(1, 2)
+    s = qf @ kf.transpose(-1, -2) * LN2
+    ref = (torch.softmax(s, -1) @ vf).transpose(1, 2).reshape(B * Tq, d)
+    assert torch.isfinite(out.float()).all()
+    per_row = (out.float() - ref).norm(dim=1) / ref.norm(dim=1).clamp_min(1e-6)
+    assert per_row.max().item() < 3e-2, f"worst row {per_row.argmax().item()} rel err {per_row.max().item()}"
+    assert _rel(out, ref) < 2e-2 and _cos(out, ref) > 0.9995
+    lse_ref = (torch.logsumexp(s, -1) * 1.4426950408889634).reshape(-1)
+    assert (lse - lse_ref).abs().max().item() < 2e-2 * max(1.0, lse_ref.abs().max().item() / 16)
+    # a second launch over the same buffers (barrier / TMEM state is per launch) reproduces the result bit for bit
+    out2 = torch.zeros_like(out)
+    ops.attention(q, k, v, out2, B, H, Tq, Tk, LN2)
+    assert torch.equal(out, out2)
 
 
 # ------------------------------------------------------------------ log-mel

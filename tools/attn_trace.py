@@ -55,8 +55,19 @@ def run():
               f"kv_full wait {buf[0] / ctas / blocks / 5:.0f}, p_ready wait {buf[1] / ctas / blocks / 5:.0f}, MMA loop {buf[3] / ctas / blocks / 5:.0f}, "
               f"softmax s_full wait {buf[2] / ctas / blocks / 5:.0f} (w4 {buf[5] / ctas / blocks / 5:.0f}, w5 {buf[6] / ctas / blocks / 5:.0f}, w3 {buf[7] / ctas / blocks / 5:.0f}), "
               f"softmax loop {buf[4] / ctas / blocks / 5:.0f}", flush=True)
-        tl = (ctypes.c_longlong * (12 * 32))()
-        if hasattr(L, "desta_attention_timeline") and L.desta_attention_timeline(tl) == 0:
+        tl = (ctypes.c_longlong * (16 * 32))()
+        if os.environ.get("DESTA_ATTN_UNIT8", "1") != "0" and scale != 1.0:
+            L.desta_attention_timeline(tl)
+            ev = [[tl[e * 32 + j] for j in range(24)] for e in range(16)]
+            t0 = ev[13][0]
+            rel = lambda v: (v - t0) if v > 0 else -1
+            print("   unit8 timeline of CTA (5,7,30), cycles from kernel entry: init done %d, Q landed %d, S_0 seen %d, shift published %d, "
+                  "loop end %d, last PV done %d, stores issued %d" % tuple(rel(ev[13][k]) for k in range(1, 8)))
+            print("    j | MMA: p_ready seen, PV issued, QK_j issued (s_free seen, K_j seen) | step start w2..w5 (cols 0-31) | w6..w9 (cols 32-63) | w2: got S_j, announced P_j")
+            for j in range(24):
+                print(f"   {j:2d} | {rel(ev[0][j]):6d} {rel(ev[1][j]):6d} {rel(ev[2][j]):6d} ({rel(ev[14][j]):6d} {rel(ev[15][j]):6d}) | " + " ".join(f"{rel(ev[3 + k][j]):6d}" for k in range(4)) + " | "
+                      + " ".join(f"{rel(ev[7 + k][j]):6d}" for k in range(4)) + f" | {rel(ev[11][j]):6d} {rel(ev[12][j]):6d}")
+        elif hasattr(L, "desta_attention_timeline") and L.desta_attention_timeline(tl) == 0:
             ev = [[tl[e * 32 + j] for j in range(24)] for e in range(12)]
             t0 = min(v for row in ev for v in row if v > 0)
             rel = lambda v: (v - t0) if v > 0 else -1
