@@ -241,6 +241,52 @@ __device__ __forceinline__ void softmax_block(const uint32_t (&va)[32], const ui
 // bf16 round-to-nearest-even of a float, returned as float (the shift operand holds bf16 values)
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
+// mbarrier wait without the out-of-line report of mbar_wait: an ABI call inside the softmax loop makes ptxas keep a spill
+// frame for the registers that are live across it (96 registers per thread in this kernel).  Same 2 s guard, plain trap.
+__device__ __forceinline__ void mbar_wait_lean(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+
+// Waits of the two issuing warps.  They wait most of every step (S_{j+2} and P_j V_j are short bursts), so a plain spin on
+// try_wait costs their sub-partitions' softmax warps issue slots, and the hardware sleep (mbar_wait_sleep) puts its wake-up
+// latency on the hand-over chain.  Default: poll with a short nanosleep in between (DESTA_ATTN_MMA_NAP ns).
+// -DDESTA_ATTN_MMA_SLEEP / -DDESTA_ATTN_MMA_SPIN select the other two for A/B runs.
+#ifndef DESTA_ATTN_MMA_NAP
+#define DESTA_ATTN_MMA_NAP 32
+#endif
+__device__ __forceinline__ void mbar_wait_nap(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  int spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(DESTA_ATTN_MMA_NAP);
+    if (++spins > (1 << 25)) __trap();
+  }
+}
+#if defined(DESTA_ATTN_MMA_SLEEP)
+#define MMA_WAIT(bar, par) mbar_wait_sleep(bar, par)
+#elif defined(DESTA_ATTN_MMA_SPIN)
+#define MMA_WAIT(bar, par) mbar_wait_lean(bar, par)
+#else
+#define MMA_WAIT(bar, par) mbar_wait_nap(bar, par)
+#endif
+
+// waits of the MMA warp of the general / four-warp kernels: -DDESTA_ATTN_MMA4=0 hardware sleep (0.993 ms per encoder launch), =1 spin (0.986),
+// =2 (default) poll with a short nanosleep (0.984)
+#ifndef DESTA_ATTN_MMA4
+#define DESTA_ATTN_MMA4 2
+#endif
+#if DESTA_ATTN_MMA4 == 1
+#define AT_MMA_WAIT(bar, par) mbar_wait_lean(bar, par)
+#elif DESTA_ATTN_MMA4 == 2
+#define AT_MMA_WAIT(bar, par) mbar_wait_nap(bar, par)
+#else
+#define AT_MMA_WAIT(bar, par) mbar_wait_sleep(bar, par)
+#endif
+
 // One tile (128 query rows of one (batch, head)) by warps 0-5 of the CTA; every thread of the CTA must call it (it
 // contains __syncthreads).  FALLBACK: called by attn_fwd_unit8_kernel for a tile whose fast pass overflowed - TMEM is
 // already allocated (`tmem_given`), the barriers live in a second block (`bar_off`), warps >= 6 only join the barriers.
@@ -272,7 +318,8 @@ __device__ __forceinline__ void attn_tile_body(const CUtensorMap& tmQ, const CUt
   const bool tl_on = !FALLBACK && q0 == 5 * AT_BQ && head == 7 && batch == 30;
 #endif
 
-  if (a.kv_rows < AT_BKV || a.q_rows < AT_BQ) {
+  const bool early_loads = !(a.kv_rows < AT_BKV || a.q_rows < AT_BQ);
+  if (!early_loads) {
     // short sequences: rows the TMA boxes never write must read as zeros (keys: P = 0 there; queries: finite scores, so
     // that the unused rows of a 64-query Q-Former tile can never send their warps down the rescale path)
     uint4* z = reinterpret_cast<uint4*>(smem);
@@ -297,6 +344,17 @@ __device__ __forceinline__ void attn_tile_body(const CUtensorMap& tmQ, const CUt
     for (int i = 0; i < AT_SBUF; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 128); mbar_init(&pv_done[i], 1); }
     mbar_init(shift_ready, 128);
     fence_barrier_init();
+    if (early_loads) {
+      // full tiles: Q and the first ring of K / V leave before the TMEM allocation and the CTA barrier - the start of a tile is
+      // pure latency (tools/attn_trace.py: ~1 000 cycles from the first TMA instruction to the first scores)
+      mbar_arrive_expect_tx(q_full, a.q_rows * AT_HD * 2);
+      tma_load_3d(sQ, &tmQ, q_full, head * AT_HD, q0, batch);
+      for (int j = 0; j < AT_STAGES && j < n_kv; ++j) {
+        mbar_arrive_expect_tx(&kv_full[j], 2 * a.kv_rows * AT_HD * 2);
+        tma_load_3d(sKV + j * 2 * AT_KV_BYTES, &tmK, &kv_full[j], head * AT_HD, j * AT_BKV, batch);
+        tma_load_3d(sKV + j * 2 * AT_KV_BYTES + AT_KV_BYTES, &tmV, &kv_full[j], head * AT_HD, j * AT_BKV, batch);
+      }
+    }
   }
   if (!FALLBACK && warp == 1) tmem_alloc<AT_TMEM_COLS>(tmem_slot);
   tcgen05_fence_before();
@@ -311,11 +369,11 @@ __device__ __forceinline__ void attn_tile_body(const CUtensorMap& tmQ, const CUt
   // (tools/umma_bench.cu: 48 -> 32 cycles per 128x64x16 TS instruction; the issue loop, not the tensor pipe, was the
   // bottleneck of this kernel).
   if (warp == 0) {
-    if (elect_one()) {
+    if (!early_loads && elect_one()) {
       mbar_arrive_expect_tx(q_full, a.q_rows * AT_HD * 2);
       tma_load_3d(sQ, &tmQ, q_full, head * AT_HD, q0, batch);
     }
-    for (int j = 0; j < n_kv; ++j) {
+    for (int j = early_loads ? (n_kv < AT_STAGES ? n_kv : AT_STAGES) : 0; j < n_kv; ++j) {
       const int st = j % AT_STAGES;
       mbar_wait_sleep(&kv_empty[st], ((j / AT_STAGES) & 1) ^ 1);
       if (elect_one()) {
@@ -334,7 +392,7 @@ __device__ __forceinline__ void attn_tile_body(const CUtensorMap& tmQ, const CUt
     // S_j = Q K_j^T (- shift 1^T in UNIT mode) into buffer j % 3; issued three blocks ahead of the P V product of the buffer
     auto issue_qk = [&](int j) {
       const int st = j % AT_STAGES;
-      { TRACE_T0(); mbar_wait_sleep(&kv_full[st], (j / AT_STAGES) & 1); TRACE_ADD(0); }
+      { TRACE_T0(); AT_MMA_WAIT(&kv_full[st], (j / AT_STAGES) & 1); TRACE_ADD(0); }
       tcgen05_fence_after();
       const uint64_t kdesc = umma_desc_sw128(smem_u32(sKV + st * 2 * AT_KV_BYTES), 16, 1024);
       if (elect_one()) {
@@ -363,7 +421,7 @@ __device__ __forceinline__ void attn_tile_body(const CUtensorMap& tmQ, const CUt
     }
     for (int j = 0; j < n_kv; ++j) {
       const int st = j % AT_STAGES, b = j % AT_SBUF;
-      { TRACE_T0(); mbar_wait_sleep(&p_ready[b], (j / AT_SBUF) & 1); TRACE_ADD(1); }     // P_j in TMEM (over S_j), O rescaled if needed
+      { TRACE_T0(); AT_MMA_WAIT(&p_ready[b], (j / AT_SBUF) & 1); TRACE_ADD(1); }     // P_j in TMEM (over S_j), O rescaled if needed
       TL(0, j);
       tcgen05_fence_after();
       // V stage: 64 key rows x 128 B (64 head-dim values) -> MN-major B operand, 8-row groups 1024 B apart
@@ -381,6 +439,16 @@ __device__ __forceinline__ void attn_tile_body(const CUtensorMap& tmQ, const CUt
       if (j + AT_SBUF < n_kv) { issue_qk(j + AT_SBUF); TL(2, j + AT_SBUF); }   // in-order tensor pipe: overwrites buffer b after P_j V_j
     }
     TRACE_ADD(3);
+  } else if (warp < 6 && q0 + (warp & 3) * 32 >= a.Tq) {
+    // ---- a softmax warp whose 32 rows all lie past Tq (the Q-Former's 64-query tiles: two of four warps; the encoder's last
+    //      q-tile, 1500 = 11 * 128 + 92: one of four).  Rows are independent (O[r] = sum_k P[r,k] V[k]) and these are never
+    //      stored, so whatever the P columns of these lanes hold is harmless: the warp only keeps the hand-over protocol in
+    //      step (an arrival per block, paced by the scores it would have read) and spends no MUFU / issue slots on padding. ----
+    if (UNIT) mbar_arrive(shift_ready);
+    for (int j = 0; j < n_kv; ++j) {
+      mbar_wait_sleep(&s_full[j % AT_SBUF], (j / AT_SBUF) & 1);
+      mbar_arrive(&p_ready[j % AT_SBUF]);
+    }
   } else if (warp < 6) {
     // ---- softmax warps: TMEM lane quarter = warp % 4, one query row per thread ----
     const int quarter = warp & 3;
@@ -689,39 +757,6 @@ constexpr int AT8_TMEM_Q = AT8_TMEM_P + 32;
 constexpr int AT8_KST = 4, AT8_VST = 6;              // K / V rings of 8 KB stages (together the 80 KB of the general kernel's ring)
 static_assert((AT8_KST + AT8_VST) * AT_KV_BYTES == AT_STAGES * 2 * AT_KV_BYTES, "the fallback path reuses the same shared memory");
 static_assert((1 + 2 * AT8_KST + 2 * AT8_VST + 7) * 8 + 16 <= 256, "barrier block");
-
-// mbarrier wait without the out-of-line report of mbar_wait: an ABI call inside the softmax loop makes ptxas keep a spill
-// frame for the registers that are live across it (96 registers per thread in this kernel).  Same 2 s guard, plain trap.
-__device__ __forceinline__ void mbar_wait_lean(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) __trap();
-  }
-}
-
-// Waits of the two issuing warps.  They wait most of every step (S_{j+2} and P_j V_j are short bursts), so a plain spin on
-// try_wait costs their sub-partitions' softmax warps issue slots, and the hardware sleep (mbar_wait_sleep) puts its wake-up
-// latency on the hand-over chain.  Default: poll with a short nanosleep in between (DESTA_ATTN_MMA_NAP ns).
-// -DDESTA_ATTN_MMA_SLEEP / -DDESTA_ATTN_MMA_SPIN select the other two for A/B runs.
-#ifndef DESTA_ATTN_MMA_NAP
-#define DESTA_ATTN_MMA_NAP 32
-#endif
-__device__ __forceinline__ void mbar_wait_nap(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  int spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    __nanosleep(DESTA_ATTN_MMA_NAP);
-    if (++spins > (1 << 25)) __trap();
-  }
-}
-#if defined(DESTA_ATTN_MMA_SLEEP)
-#define MMA_WAIT(bar, par) mbar_wait_sleep(bar, par)
-#elif defined(DESTA_ATTN_MMA_SPIN)
-#define MMA_WAIT(bar, par) mbar_wait_lean(bar, par)
-#else
-#define MMA_WAIT(bar, par) mbar_wait_nap(bar, par)
-#endif
 
 // named barrier of one warp pair (ids 1-4, 64 threads); immediate ids keep the CTA's barrier count at five
 __device__ __forceinline__ void pair_sync(int quarter) {
