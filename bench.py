@@ -535,7 +535,7 @@ def run_ours(args):
 
         # ---- e2e (public): processor(list of numpy clips) -> .to(device) -> _prepare_inputs_for_llm -> D2H ----
         clips = [wave_host[i].numpy() for i in range(n)]    # what AudioSegment.samples / the dataset hand to the processor
-        model.processor.enable_pinned_staging(n, slots=3)
+        model.processor.enable_pinned_staging(n, slots=3, device=dev)    # H2D of a batch starts when it is packed (loader thread)
         pub = {"next": None}
 
         def pack():
@@ -597,8 +597,8 @@ def run_ours(args):
                        "parallelism": f"clips sharded over {world} GPU(s), no data-path collective"},
             "e2e": {"value": 30.0 * n * world / (ms_pub * 1e-3 / args.steps), "unit": "audio-s/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": out_host.numel() * 2, "ms_per_step": ms_pub / args.steps,
-                    "path": "WaveformProcessor(list of numpy clips, pinned slots; next batch packed by a loader thread) -> .to(device) "
-                            "-> installed model._prepare_inputs_for_llm -> D2H of inputs_embeds"},
+                    "path": "WaveformProcessor(list of numpy clips, pinned slots with device prefetch; next batch packed and its H2D copy "
+                            "started by a loader thread) -> .to(device) -> installed model._prepare_inputs_for_llm -> D2H of inputs_embeds"},
             "e2e_staged": {"value": 30.0 * n * world / (ms_st * 1e-3 / args.steps), "unit": "audio-s/s", "h2d_bytes_per_step": h2d,
                            "d2h_bytes_per_step": out_host.numel() * 2, "ms_per_step": ms_st / args.steps,
                            "path": "pre-packed pinned slots (WaveformStager) -> _prepare_inputs_for_llm -> D2H"},

@@ -144,3 +144,50 @@ def test_stager_double_buffer_feeds_the_path():
             want, _ = p(input_features=direct)
             assert torch.equal(got[k], want), k
     assert st.h2d_bytes == 4 * 2 * (480000 * 4 + 4)
+
+
+def test_processor_prefetch_hands_over_the_device_copy():
+    """Scope row n1 behind the reference's own call: `processor(clips).input_features.to(device)` with
+    enable_pinned_staging(device=...) returns the device buffer whose H2D copy started at packing time (loader thread,
+    copy stream); features are bit-identical to a direct transfer over more batches than slots (device buffers are reused),
+    a host tensor modified in place takes the regular copy, and views / other targets behave like plain tensors."""
+    import threading
+    from desta_b200.processor import StagedWaveform, WaveformProcessor
+    cfg = CONFIGS["micro"]
+    W = make_weights(cfg, seed=11, with_table=False)
+    p = build_perception(cfg, W)
+    waves = synth_waves(seed=7, kinds=KINDS)
+    batches = [waves[0:2], waves[2:4], waves[4:6], waves[1:3], waves[3:5], [waves[5], waves[0]], waves[2:4]]
+    proc = WaveformProcessor()
+    proc.enable_pinned_staging(2, slots=3, device="cuda")
+    got, nxt = [], {}
+
+    def pack(k):
+        nxt["f"] = proc(list(batches[k]), sampling_rate=16000, return_tensors="pt").input_features
+
+    pack(0)
+    with torch.no_grad():
+        for k in range(len(batches)):
+            feats = nxt["f"]
+            loader = threading.Thread(target=pack, args=(k + 1,)) if k + 1 < len(batches) else None
+            if loader:
+                loader.start()                                   # next batch packed + prefetched while this one computes
+            assert isinstance(feats, StagedWaveform) and feats.is_pinned() and not feats.is_cuda
+            wave = feats.to("cuda", non_blocking=True)
+            assert wave.is_cuda and wave.shape == (2, 480000) and wave.data_ptr() in [s["dev"].data_ptr() for s in proc._slots]
+            out, _ = p(input_features=wave)
+            got.append(out.clone())
+            if loader:
+                loader.join()
+        for k, b in enumerate(batches):
+            direct = torch.from_numpy(np.stack([o_mel.pad_or_truncate(np.asarray(w, np.float32)) for w in b])).cuda()
+            want, _ = p(input_features=direct)
+            assert torch.equal(got[k], want), k
+    # plain-tensor behaviour everywhere else
+    f = proc(list(batches[0]), sampling_rate=16000, return_tensors="pt").input_features
+    assert f.to(torch.float64).dtype == torch.float64 and not f.to(torch.float64).is_cuda
+    assert f[:1].to("cuda").data_ptr() not in [s["dev"].data_ptr() for s in proc._slots]       # a view is copied normally
+    f.mul_(0.5)                                                  # modified in place after staging: the prefetched copy is stale
+    d = f.to("cuda")
+    assert d.data_ptr() not in [s["dev"].data_ptr() for s in proc._slots]
+    assert torch.equal(d.cpu(), f.as_subclass(torch.Tensor))
