@@ -38,6 +38,11 @@
 // (poly_exp2): the XU pipe is the floor at head_dim 64, and profiles/r2_poly_attention.md shows where the issue slots run
 // out (12.5-25 %: 0.995 ms; 37.5 %: 1.07 ms; 50 %: 1.16 ms).  ex2.approx.f16x2 is no shortcut: MUFU.EX2.F16x2 issues
 // every 16 cycles per warp, i.e. the same 8 cycles per exponential (tools/issue_bench.cu).
+//
+// File map: attn_tile_body<DROP, UNIT, FALLBACK> is the kernel described above (attn_fwd_kernel<DROP, UNIT> wraps it; it is the
+// product path of every call).  attn_fwd_unit8_kernel further down is a second design for the encoder's calls that is NOT the
+// default (desta_attention_variant(): eight softmax warps, Q in tensor memory; it reuses attn_tile_body<.., FALLBACK = true> to
+// recompute a tile whose fixed reference overflowed) - measured slower, kept for A/B runs: profiles/r2_attention_unit8.md.
 #include <math.h>
 #include <stdlib.h>
 
