@@ -90,3 +90,27 @@ def test_device_wave_is_only_trusted_by_identity():
     with np.testing.assert_raises(ValueError):
         w *= 0.5                                                     # the carrier is read-only: no silent drift
     assert w.tolist()[0] == -1.0 and w.device_tensor is marker
+
+
+def test_staged_waveform_is_a_plain_tensor_without_a_device_slot():
+    """processor.StagedWaveform (the pinned batch a prefetching processor hands out) must behave like the host tensor it
+    wraps wherever the hand-over does not apply: dtype / cpu targets, views, arithmetic, numpy interop - and `.to()` of a
+    wrapper whose slot has no device buffer is the regular copy (the CUDA hand-over itself is covered by
+    tests/test_dropin_gpu.py::test_processor_prefetch_hands_over_the_device_copy)."""
+    import numpy as np
+    import torch
+    from desta_b200.processor import StagedWaveform
+    host = torch.arange(24, dtype=torch.float32).reshape(3, 8)
+    t = StagedWaveform.wrap(host, dict(dev=None), None)
+    assert isinstance(t, torch.Tensor) and t.shape == (3, 8) and t.data_ptr() == host.data_ptr()
+    d = t.to(torch.float64)
+    assert type(d) is torch.Tensor and d.dtype == torch.float64 and torch.equal(d, host.double())
+    c = t.to("cpu")
+    assert type(c) is torch.Tensor and torch.equal(c, host)
+    v = t[:2]
+    assert getattr(v, "_slot", None) is None and torch.equal(v.to("cpu"), host[:2])       # views carry no hand-over
+    assert torch.equal((t * 2).as_subclass(torch.Tensor), host * 2)
+    assert np.array_equal(t.numpy(), host.numpy())
+    before = t._staged_version
+    t.add_(1.0)                                       # in-place edit after staging: the version counter moves
+    assert t._version != before
