@@ -306,7 +306,12 @@ def connector_backward(con, conT: ConnectorTPack, dims: PathDims, ws, st: TrainS
         ops.colsum(dx.view(K, N, Q * d)[k], G["prompts"].view(K, Q * d)[k])
     # ---- cross-attention K/V projections of all layers: one weight-gradient GEMM over all taps' rows ----
     ops.gemm_wgrad(st.dkv, ws.taps.view(K * N * T, d), G["kv_w"])
-    ops.colsum(st.dkv, G["kv_b"])
+    # Bias gradients of those projections: only the VALUE halves are summed.  A key bias adds q . b_k to every score of a row,
+    # which the softmax ignores, so its gradient is identically zero (the reference's autograd produces rounding noise
+    # there); the arena is zero already, and half of the 5.9 GB column sum over dK / dV is never read.
+    for l in range(dims.qf_layers):
+        kc = l * 2 * d
+        ops.colsum(st.dkv[:, kc + d:kc + 2 * d], G["kv_b"][kc + d:kc + 2 * d])
     if on_ready is not None:
         a0, a1 = st.global_slice
         on_ready(st.arena[a0:a1])

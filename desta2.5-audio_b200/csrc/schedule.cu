@@ -468,7 +468,10 @@ extern "C" int desta_connector_bwd(const desta_dims* dims, const desta_connector
     RUN(desta_colsum(dx + (size_t)k * N * Q * d, 0, Q * d, N, Q * d, G.prompts + (size_t)k * Q * d, stream));
   // ---- cross-attention K/V projections of all layers: one weight-gradient GEMM over all taps' rows ----
   RUN(desta_gemm_bf16_wgrad(ws.dkv, ldkv, taps, d, K * N * T, ldkv, d, G.kv_w, d, stream));
-  RUN(desta_colsum(ws.dkv, 1, ldkv, K * N * T, ldkv, G.kv_b, stream));
+  // bias gradients: value halves only - a key bias shifts every score of a row alike, the softmax ignores it and its gradient
+  // is identically zero (the arena is zeroed), so half of the column sum over dK / dV is never read
+  for (int l = 0; l < L; ++l)
+    RUN(desta_colsum(ws.dkv + (size_t)l * 2 * d + d, 1, ldkv, K * N * T, d, G.kv_b + (size_t)l * 2 * d + d, stream));
   if (on_ready) on_ready(user, 0, G.global_count);
   return DESTA_OK;
 }
