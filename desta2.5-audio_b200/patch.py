@@ -14,8 +14,11 @@ from .processor import WaveformProcessor
 from .splice import prepare_inputs_for_llm
 
 
-def install(model, wrap_processor: bool = True, patch_audio: bool = False):
-    """patch_audio=True also rebinds the `AudioSegment` name that `generate()` uses (modeling_desta25.py:13, :1553-1557) to
+def install(model, wrap_processor: bool = True, patch_audio: bool = False, staging_clips: int = 0):
+    """staging_clips > 0 (model on a CUDA device): the wrapped processor - also the one `generate()` creates later - packs
+    batches of up to that many clips into pinned slots and starts their host-to-device copy at packing time
+    (`WaveformProcessor.enable_pinned_staging(staging_clips, device=...)`, scope row n1); larger batches take the regular path.
+    patch_audio=True also rebinds the `AudioSegment` name that `generate()` uses (modeling_desta25.py:13, :1553-1557) to
     desta_b200.audio.AudioSegment, so RIFF/WAVE files are decoded, down-mixed and resampled to 16 kHz on the GPU.  It is
     opt-in because it is module-wide and because other containers (flac, mp3 ...) need the reference's libsndfile path."""
     if getattr(model.config, "connector_mode", "qformer_1") != "qformer_1":
@@ -38,11 +41,19 @@ def install(model, wrap_processor: bool = True, patch_audio: bool = False):
             raise RuntimeError(f"{type(model).__module__} has no AudioSegment to replace")
         mod.AudioSegment = AudioSegment
     if wrap_processor:
-        _wrap_processor(model)
+        _wrap_processor(model, staging_clips)
     return model
 
 
-def _wrap_processor(model):
+def _staged(model, proc, staging_clips):
+    if staging_clips > 0 and proc._slots is None:
+        dev = next(model.perception.parameters()).device
+        if dev.type == "cuda":
+            proc.enable_pinned_staging(staging_clips, device=dev)
+    return proc
+
+
+def _wrap_processor(model, staging_clips: int = 0):
     """Boundary b1.  The reference creates `self.processor` lazily: `generate()` calls `_setup_generation()` on its first
     use (modeling_desta25.py:1514-1515 -> :1467-1482, `AutoProcessor.from_pretrained` at :1475), i.e. usually AFTER
     `install(model)`.  So besides wrapping a processor that already exists, `_setup_generation` itself is wrapped: whatever
@@ -50,7 +61,7 @@ def _wrap_processor(model):
     `self.processor(batch_features, sampling_rate=16000, return_tensors="pt").input_features` (:1570, :1583) yields padded
     waveforms for the device log-mel instead of running the CPU WhisperFeatureExtractor."""
     if getattr(model, "processor", None) is not None and not isinstance(model.processor, WaveformProcessor):
-        model.processor = WaveformProcessor(model.processor)
+        model.processor = _staged(model, WaveformProcessor(model.processor), staging_clips)
     setup = getattr(model, "_setup_generation", None)
     if setup is None or getattr(setup, "_desta_b200_wrapped", False):
         return
@@ -59,7 +70,7 @@ def _wrap_processor(model):
         out = setup(*args, **kwargs)
         proc = getattr(self, "processor", None)
         if proc is not None and not isinstance(proc, WaveformProcessor):
-            self.processor = WaveformProcessor(proc)
+            self.processor = _staged(self, WaveformProcessor(proc), staging_clips)
         return out
 
     bound = types.MethodType(_setup_generation, model)

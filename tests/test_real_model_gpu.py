@@ -161,7 +161,7 @@ def test_generate_through_install_runs_the_device_logmel(tmp_path):
     ref, model = _build_real_model()
     refshim.offline_generation(model, CFG.n_mels)
     assert not hasattr(model, "processor")
-    desta_b200.install(model)
+    desta_b200.install(model, staging_clips=8)       # the lazily created processor also gets pinned slots with device prefetch
     llm_generate2 = model.llm_model.generate
 
     def spy2(**kw):
@@ -174,6 +174,8 @@ def test_generate_through_install_runs_the_device_logmel(tmp_path):
     with torch.no_grad():
         out = model.generate(convs, do_sample=False, max_new_tokens=4)
     assert isinstance(model.processor, WaveformProcessor), "generate() created its processor lazily and it was not wrapped"
+    assert model.processor._slots is not None and all(s["dev"] is not None and s["dev"].is_cuda for s in model.processor._slots)
+    assert any(s["ready"] is not None for s in model.processor._slots), "no batch went through the prefetching slots"
     assert model.processor._wrapped.calls == 0, "the CPU WhisperFeatureExtractor still ran on the generate() path"
     assert ops.STATS.get("logmel_calls", 0) > mel0, "logmel_fft_kernel never launched through processor -> perception"
     # ASR pass on clip 0 only + perception on all 4 clips: with per-clip reuse the encoder sees 4 clips, not 5
