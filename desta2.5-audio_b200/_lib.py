@@ -17,7 +17,7 @@ class GemmEpilogue(Structure):
 
 class Dropout(Structure):
     """desta_dropout: keep iff rnd16 >= thr16, kept values * scale; (seed, site, element) -> Philox counter."""
-    _fields_ = [("thr16", c_uint32), ("scale", c_float), ("seed", c_uint64), ("site", c_uint32)]
+    _fields_ = [("thr16", c_uint32), ("scale", c_float), ("seed", c_uint64), ("site", c_uint32), ("row_keep_ratio", c_void_p)]
 
 
 class Dims(Structure):
@@ -90,6 +90,7 @@ EXPORTS = {
     "desta_attention": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int,
                                 c_int, c_float, c_void_p, POINTER(Dropout), c_void_p]),
     "desta_attention_variant": (c_int, [c_int]),
+    "desta_colsum_heads": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "desta_gemm_bf16_wgrad": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "desta_attention_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int,
                                     c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,

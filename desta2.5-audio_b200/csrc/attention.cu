@@ -96,7 +96,7 @@ __device__ __forceinline__ void reg_fence32(uint32_t (&v)[32]) {
                     "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31]));
 }
 
-struct SoftmaxAcc { float l0, l1, m0, m1; };
+struct SoftmaxAcc { float l0, l1, m0, m1, t; };     // t (DROP only): sum of the dropped, rescaled probabilities
 
 
 
@@ -223,6 +223,7 @@ __device__ __forceinline__ void softmax_chunk(const uint32_t (&v)[32], int ch, u
       p1 = (kb & 2) ? p1 * dc.scale : 0.f;
       p2 = (kb & 4) ? p2 * dc.scale : 0.f;
       p3 = (kb & 8) ? p3 * dc.scale : 0.f;
+      acc.t += (p0 + p1) + (p2 + p3);
     }
     pk[i >> 1] = pack_bf16(p0, p1);
     pk[(i >> 1) + 1] = pack_bf16(p2, p3);
@@ -232,8 +233,8 @@ __device__ __forceinline__ void softmax_chunk(const uint32_t (&v)[32], int ch, u
 // Both chunks of a 64-key block from the scores in registers; P written in place over the block's S columns [0, 32).
 template <bool MASKED, bool DROP>
 __device__ __forceinline__ void softmax_block(const uint32_t (&va)[32], const uint32_t (&vb)[32], uint32_t tS, float c, float mc,
-                                              int kv_valid, float& l_blk, float& m_blk, const DropoutCfg& dc, uint64_t grp0) {
-  SoftmaxAcc acc = {0.f, 0.f, -INFINITY, -INFINITY};
+                                              int kv_valid, float& l_blk, float& m_blk, float& t_blk, const DropoutCfg& dc, uint64_t grp0) {
+  SoftmaxAcc acc = {0.f, 0.f, -INFINITY, -INFINITY, 0.f};
   uint32_t pk[16];
   softmax_chunk<MASKED, DROP>(va, 0, pk, c, mc, kv_valid, acc, dc, grp0);
   tmem_st_32x16(tS, pk);            // keys [0, 32): A operand of P V, K-major, two bf16 per column
@@ -241,6 +242,7 @@ __device__ __forceinline__ void softmax_block(const uint32_t (&va)[32], const ui
   tmem_st_32x16(tS + 16, pk);       // keys [32, 64)
   l_blk = acc.l0 + acc.l1;
   m_blk = fmaxf(acc.m0, acc.m1);
+  t_blk = acc.t;
 }
 
 // bf16 round-to-nearest-even of a float, returned as float (the shift operand holds bf16 values)
@@ -462,6 +464,7 @@ __device__ __forceinline__ void attn_tile_body(const CUtensorMap& tmQ, const CUt
     const float c = UNIT ? 1.0f : a.scale_log2;
     // everything below lives in the log2 domain: m_ref = reference exponent of the row (P, l, O are relative to 2^m_ref)
     float m_ref = -INFINITY, l_run = 0.f;
+    float t_run = 0.f;                                  // DROP: running sum of the dropped, rescaled probabilities (same reference)
     // UNIT: shift folded into S by the MMA.  sh_cur = shift this thread last wrote to the operand tile; bk0..2 = the shift
     // block j % 3 was (or will be) computed with - a QK^T issued after this thread's arrival on p_ready[j-3] sees the
     // operand as it was then.
@@ -504,7 +507,7 @@ __device__ __forceinline__ void attn_tile_body(const CUtensorMap& tmQ, const CUt
     };
     // rare: raise the reference to m_blk, rescale O and l, redo the block's exponentials from the registers
     auto rescale = [&](int j, uint32_t (&ca)[32], uint32_t (&cb)[32], uint32_t tS, float baked, int kv_valid, uint64_t grp0,
-                       float m_blk, float& l_blk, bool from_fast_loop) {
+                       float m_blk, float& l_blk, float& t_blk, bool from_fast_loop) {
       float m_new = fmaxf(m_ref, m_blk);
       if (UNIT) m_new = bf16_round(m_new);
       if (j > 0) {
@@ -512,6 +515,7 @@ __device__ __forceinline__ void attn_tile_body(const CUtensorMap& tmQ, const CUt
         tcgen05_fence_after();
         const float f = exp2f(m_ref - m_new);
         l_run *= f;
+        t_run *= f;
 #pragma unroll 1
         for (int ch = 0; ch < 4; ++ch) {
           uint32_t o[16];
@@ -524,7 +528,7 @@ __device__ __forceinline__ void attn_tile_body(const CUtensorMap& tmQ, const CUt
       }
       m_ref = m_new;
       float m_unused;
-      softmax_block<true, DROP>(ca, cb, tS, c, m_ref - baked, kv_valid, l_blk, m_unused, a.drop, grp0);
+      softmax_block<true, DROP>(ca, cb, tS, c, m_ref - baked, kv_valid, l_blk, m_unused, t_blk, a.drop, grp0);
       if (UNIT && m_ref != sh_cur) {
         if (from_fast_loop) bk0 = bk1 = bk2 = sh_cur;   // the fast loop does not track the slots: S_{j+1}, S_{j+2} carry the old shift
         set_shift(j, m_ref);
@@ -562,7 +566,7 @@ __device__ __forceinline__ void attn_tile_body(const CUtensorMap& tmQ, const CUt
       }
       // exp pass against the reference of the PREVIOUS blocks; the block max comes out of the same pass
       const float off = m_ref - baked;                  // p = exp2(c * S - off)
-      SoftmaxAcc acc = {0.f, 0.f, -INFINITY, -INFINITY};
+      SoftmaxAcc acc = {0.f, 0.f, -INFINITY, -INFINITY, 0.f};
       uint32_t pk[16];
       if (kv_valid >= AT_BKV) softmax_chunk<false, DROP>(ca, 0, pk, c, off, kv_valid, acc, a.drop, grp0);
       else softmax_chunk<true, DROP>(ca, 0, pk, c, off, kv_valid, acc, a.drop, grp0);
@@ -574,13 +578,14 @@ __device__ __forceinline__ void attn_tile_body(const CUtensorMap& tmQ, const CUt
       if (kv_valid >= AT_BKV) softmax_chunk<false, DROP>(cb, 1, pk, c, off, kv_valid, acc, a.drop, grp0);
       else softmax_chunk<true, DROP>(cb, 1, pk, c, off, kv_valid, acc, a.drop, grp0);
       tmem_st_32x16(tS + 16, pk);                       // P keys [32,64) over S columns [16,32)
-      float l_blk = acc.l0 + acc.l1;
+      float l_blk = acc.l0 + acc.l1, t_blk = acc.t;
       const float m_blk = fmaxf(acc.m0, acc.m1) * c + baked;      // block max in the log2 domain
       // P is bf16 and O / l are fp32, so exponents up to 2^20 above the reference are harmless; only beyond that is the
       // reference raised (FA-style lazy rescale; the common case never takes the slow path)
       const bool need = (m_blk - m_ref) > 20.0f;
-      if (__builtin_expect(__any_sync(0xffffffffu, need), 0)) rescale(j, ca, cb, tS, baked, kv_valid, grp0, m_blk, l_blk, false);
+      if (__builtin_expect(__any_sync(0xffffffffu, need), 0)) rescale(j, ca, cb, tS, baked, kv_valid, grp0, m_blk, l_blk, t_blk, false);
       l_run += l_blk;
+      if (DROP) t_run += t_blk;
     };
     // UNIT fast step: a full block whose S already carries this row's current reference as shift (S' = s - m_ref):
     // p = ex2(S'), bf16 pack, row sum - nothing else.  A row sum above 2^40 (some p far above the reference, inf included)
@@ -621,7 +626,8 @@ __device__ __forceinline__ void attn_tile_body(const CUtensorMap& tmQ, const CUt
           mx = max3(mx, (i < kv_valid) ? __uint_as_float(ca[i]) : -INFINITY, (i + 1 < kv_valid) ? __uint_as_float(ca[i + 1]) : -INFINITY);
           mx = max3(mx, (32 + i < kv_valid) ? __uint_as_float(cb[i]) : -INFINITY, (33 + i < kv_valid) ? __uint_as_float(cb[i + 1]) : -INFINITY);
         }
-        rescale(j, ca, cb, tS, m_ref, kv_valid, 0, mx + m_ref, l_blk, !tracked);
+        float t_unused = 0.f;
+        rescale(j, ca, cb, tS, m_ref, kv_valid, 0, mx + m_ref, l_blk, t_unused, !tracked);
       }
       l_run += l_blk;
       return need;
@@ -679,6 +685,7 @@ __device__ __forceinline__ void attn_tile_body(const CUtensorMap& tmQ, const CUt
     const float inv = 1.0f / l_run;
     const int row = q0 + r;
     if (a.lse && row < a.Tq) a.lse[((size_t)batch * a.heads + head) * a.Tq + row] = m_ref + log2f(l_run);
+    if (DROP && a.drop.row_ratio && row < a.Tq) a.drop.row_ratio[((size_t)batch * a.heads + head) * a.Tq + row] = t_run * inv;
     __nv_bfloat16* orow = a.out + ((size_t)batch * a.Tq + row) * a.ldo + head * AT_HD;
 #pragma unroll 1
     for (int ch = 0; ch < 2; ++ch) {

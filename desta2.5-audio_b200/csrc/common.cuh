@@ -36,15 +36,17 @@ struct DropoutCfg {
   float scale;         // 1 / (1 - p)
   uint32_t seed_lo, seed_hi;
   uint32_t site;       // which dropout call of the step (layer / position), part of the counter
+  float* row_ratio;    // attention forward only: optional per-row (dropped sum / plain sum) of the probabilities
 };
 inline DropoutCfg make_dropout_cfg(const desta_dropout* d) {
-  DropoutCfg c = {0u, 1.0f, 0u, 0u, 0u};
+  DropoutCfg c = {0u, 1.0f, 0u, 0u, 0u, nullptr};
   if (d && d->thr16) {
     c.thr16 = d->thr16 > 65535u ? 65535u : d->thr16;
     c.scale = d->scale;
     c.seed_lo = (uint32_t)d->seed;
     c.seed_hi = (uint32_t)(d->seed >> 32);
     c.site = d->site;
+    c.row_ratio = d->row_keep_ratio;
   }
   return c;
 }

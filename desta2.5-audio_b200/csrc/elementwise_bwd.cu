@@ -382,6 +382,54 @@ extern "C" int desta_colsum(const void* x, int dtype, int ld, int M, int N, floa
   return check_launch("colsum_kernel");
 }
 
+// out[h*64 + c] += sum over (b, t) of w[(b*heads + h)*Tq + t] * x[(b*Tq + t)*ld + h*64 + c]:  the value-bias gradient of an
+// attention from dO (see desta_colsum_heads in the header).  grid (heads, row chunks), 256 threads = 8 column octets x 32
+// row lanes; one 16-byte load per thread and row, octet partials folded through shared memory, 64 atomics per block.
+__global__ void __launch_bounds__(256) colsum_heads_kernel(const __nv_bfloat16* __restrict__ x, int ld, const float* __restrict__ w,
+                                                           int rows, int heads, int Tq, float* __restrict__ out, int rows_per_block) {
+  __shared__ float part[32][65];
+  const int h = blockIdx.x, oct = threadIdx.x & 7, rl = threadIdx.x >> 3;
+  const int r0 = blockIdx.y * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int r = r0 + rl; r < r1; r += 32) {
+    const uint4 u = *reinterpret_cast<const uint4*>(x + (size_t)r * ld + h * 64 + oct * 8);
+    const int b = r / Tq, t = r - b * Tq;
+    const float wt = w ? __ldg(w + ((size_t)b * heads + h) * Tq + t) : 1.0f;
+    const __nv_bfloat162* v2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __bfloat1622float2(v2[i]);
+      acc[2 * i] = fmaf(wt, f.x, acc[2 * i]);
+      acc[2 * i + 1] = fmaf(wt, f.y, acc[2 * i + 1]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) part[rl][oct * 8 + i] = acc[i];
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float sum = 0.f;
+#pragma unroll 8
+    for (int i = 0; i < 32; ++i) sum += part[i][threadIdx.x];
+    atomicAdd(out + h * 64 + threadIdx.x, sum);
+  }
+}
+
+extern "C" int desta_colsum_heads(const void* x, int ld, const float* w, int batch, int heads, int Tq, float* out, void* stream) {
+  if (!x || !out) { set_error("desta_colsum_heads: null pointer"); return DESTA_ERR_ARG; }
+  if (batch <= 0 || heads <= 0 || Tq <= 0) return DESTA_OK;
+  if ((ld % 8) || ld < heads * 64 || ((uintptr_t)x & 15)) { set_error("desta_colsum_heads: ld must be a multiple of 8 and >= heads*64, x 16-byte aligned"); return DESTA_ERR_ARG; }
+  if (heads > 65535) { set_error("desta_colsum_heads: too many heads"); return DESTA_ERR_ARG; }
+  const long long rows = (long long)batch * Tq;
+  if (rows > 0x7fffffffLL) { set_error("desta_colsum_heads: too many rows"); return DESTA_ERR_ARG; }
+  int row_blocks = (num_sms() * 4 + heads - 1) / heads;
+  int rows_per_block = (int)((rows + row_blocks - 1) / row_blocks);
+  if (rows_per_block < 128) rows_per_block = 128;
+  row_blocks = (int)((rows + rows_per_block - 1) / rows_per_block);
+  if (row_blocks > 65535) { rows_per_block = (int)((rows + 65534) / 65535); row_blocks = (int)((rows + rows_per_block - 1) / rows_per_block); }
+  colsum_heads_kernel<<<dim3(heads, row_blocks), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, ld, w, (int)rows, heads, Tq, out, rows_per_block);
+  return check_launch("colsum_heads_kernel");
+}
+
 extern "C" int desta_layer_mix_bwd(const float* dm, const float* x, const float* layer_weights, int taps, int N, int Q, int D,
                                    float* dx, float* dlw, void* stream) {
   if (!dm || !x || !layer_weights || !dx || !dlw) { set_error("desta_layer_mix_bwd: null pointer"); return DESTA_ERR_ARG; }

@@ -229,7 +229,7 @@ namespace desta {
 
 struct TrainLayer {
   __nv_bfloat16 *x_bf, *qkv, *ao_s, *a_bf, *q_c, *ao_c, *c_bf, *h1, *f;
-  float *x_f32, *lse_s, *t1, *a_f32, *lse_c, *t2, *c_f32, *t3;
+  float *x_f32, *lse_s, *t1, *a_f32, *lse_c, *rr_c, *t2, *c_f32, *t3;
 };
 struct TrainWs {
   __nv_bfloat16 *kv, *x_out_bf, *mix_bf, *dkv, *g_bf_a, *g_bf_b, *g_qkv, *g_ff, *g_h1, *g_out_bf;
@@ -250,6 +250,7 @@ static TrainWs carve_train(const desta_dims* d, int N, void* ws) {
     S.ao_s = (__nv_bfloat16*)c.take(R * D * 2);    S.t1 = (float*)c.take(R * D * 4);
     S.a_bf = (__nv_bfloat16*)c.take(R * D * 2);    S.a_f32 = (float*)c.take(R * D * 4);
     S.q_c = (__nv_bfloat16*)c.take(R * D * 2);     S.lse_c = (float*)c.take(B * H * Q * 4);
+    S.rr_c = (float*)c.take(B * H * Q * 4);         // cross attention: dropped / plain row sums of P (value-bias gradient)
     S.ao_c = (__nv_bfloat16*)c.take(R * D * 2);    S.t2 = (float*)c.take(R * D * 4);
     S.c_bf = (__nv_bfloat16*)c.take(R * D * 2);    S.c_f32 = (float*)c.take(R * D * 4);
     S.h1 = (__nv_bfloat16*)c.take(R * F * 2);      S.f = (__nv_bfloat16*)c.take(R * F * 2);
@@ -304,6 +305,7 @@ static bool site(const desta_dropout_plan* plan, int layer, int which, desta_dro
   out->scale = (float)(1.0 / (1.0 - (double)thr / 65536.0));
   out->seed = plan->seed;
   out->site = (uint32_t)(layer * 8 + which);
+  out->row_keep_ratio = nullptr;
   return true;
 }
 
@@ -360,7 +362,9 @@ extern "C" int desta_connector_train_fwd(const desta_dims* dims, const desta_con
     RUN(desta_layernorm(S.t1, d, P.s_ln_w, P.s_ln_b, 1e-12f, R, d, S.a_bf, d, S.a_f32, d, stream));
     RUN(gemm(S.a_bf, d, P.c_q_w, d, R, d, d, P.c_q_b, S.q_c, d, nullptr, 0, nullptr, 0, nullptr, 0, 1.f, 0, 0, stream));
     const __nv_bfloat16* kl = ws.kv + (size_t)l * 2 * d;
-    RUN(desta_attention(S.q_c, d, kl, ldkv, kl + d, ldkv, S.ao_c, d, B, H, Q, T, scale, S.lse_c, site(plan, l, 2, &dr) ? &dr : nullptr, stream));
+    const bool cross_drop = site(plan, l, 2, &dr);
+    if (cross_drop) dr.row_keep_ratio = S.rr_c;
+    RUN(desta_attention(S.q_c, d, kl, ldkv, kl + d, ldkv, S.ao_c, d, B, H, Q, T, scale, S.lse_c, cross_drop ? &dr : nullptr, stream));
     RUN(dense_res(S.ao_c, d, P.c_o_w, R, d, d, P.c_o_b, S.t2, S.a_f32, plan, l, 3, stream));
     RUN(desta_layernorm(S.t2, d, P.c_ln_w, P.c_ln_b, 1e-12f, R, d, S.c_bf, d, S.c_f32, d, stream));
     RUN(gemm(S.c_bf, d, P.f1_w, d, R, F, d, P.f1_b, S.h1, F, nullptr, 0, nullptr, 0, nullptr, 0, 1.f, 0, 0, stream));   // pre-activation kept
@@ -441,6 +445,9 @@ extern "C" int desta_connector_bwd(const desta_dims* dims, const desta_connector
     RUN(dgrad(ws.g_bf_a, d, PT.c_o, R, d, d, ws.g_bf_b, nullptr, nullptr));                     // d(ao_c)
     const __nv_bfloat16* kl = ws.kv + (size_t)l * 2 * d;
     __nv_bfloat16* dkl = ws.dkv + (size_t)l * 2 * d;
+    // value bias of the K/V projection: O = P~ (X Wv^T + 1 bv^T)  ->  d bv = sum_q (row sum of P~)_q dO_q, a reduction over dO
+    // (row sums: 1 without dropout, rr_c with it) instead of a column sum over this layer's 490 MB of dV
+    RUN(desta_colsum_heads(ws.g_bf_b, d, site(plan, l, 2, &dr) ? S.rr_c : nullptr, B, H, Q, G.kv_b + (size_t)l * 2 * d + d, stream));
     RUN(desta_attention_bwd(S.q_c, d, kl, ldkv, kl + d, ldkv, S.ao_c, d, ws.g_bf_b, d, S.lse_c, ws.g_qkv, 3 * d, dkl, ldkv, dkl + d, ldkv,
                             B, H, Q, T, scale, site(plan, l, 2, &dr) ? &dr : nullptr, stream));
     // q_c = a Wq^T + bq   (dq_c = first d columns of g_qkv)
@@ -468,10 +475,9 @@ extern "C" int desta_connector_bwd(const desta_dims* dims, const desta_connector
     RUN(desta_colsum(dx + (size_t)k * N * Q * d, 0, Q * d, N, Q * d, G.prompts + (size_t)k * Q * d, stream));
   // ---- cross-attention K/V projections of all layers: one weight-gradient GEMM over all taps' rows ----
   RUN(desta_gemm_bf16_wgrad(ws.dkv, ldkv, taps, d, K * N * T, ldkv, d, G.kv_w, d, stream));
-  // bias gradients: value halves only - a key bias shifts every score of a row alike, the softmax ignores it and its gradient
-  // is identically zero (the arena is zeroed), so half of the column sum over dK / dV is never read
-  for (int l = 0; l < L; ++l)
-    RUN(desta_colsum(ws.dkv + (size_t)l * 2 * d + d, 1, ldkv, K * N * T, d, G.kv_b + (size_t)l * 2 * d + d, stream));
+  // bias gradients of those projections: no pass over dK / dV - a key bias shifts every score of a row alike, the softmax
+  // ignores it and its gradient is identically zero (the arena is zeroed); the value-bias gradient was taken from dO per layer
+  // (desta_colsum_heads in the loop above)
   if (on_ready) on_ready(user, 0, G.global_count);
   return DESTA_OK;
 }

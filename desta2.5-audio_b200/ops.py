@@ -158,13 +158,19 @@ def layernorm(x, gamma, beta, eps, *, out_bf16=None, out_f32=None):
                                     _p(out_f32), out_f32.stride(0) if out_f32 is not None else 0, _stream()), "desta_layernorm")
 
 
-def make_dropout(p, seed, site):
-    """desta_dropout for probability p (None when p == 0): thr16 = round(p * 65536), scale = 1 / (1 - thr16 / 65536)."""
+def make_dropout(p, seed, site, row_keep_ratio=None):
+    """desta_dropout for probability p (None when p == 0): thr16 = round(p * 65536), scale = 1 / (1 - thr16 / 65536).
+    row_keep_ratio (attention forward only): fp32 [batch*heads*Tq] that receives sum_k(dropped P) / sum_k(P) per query row;
+    the caller keeps the tensor alive."""
     thr = int(round(float(p) * 65536.0))
     if thr <= 0:
         return None
     thr = min(thr, 65535)
-    return Dropout(thr, 1.0 / (1.0 - thr / 65536.0), int(seed) & 0xFFFFFFFFFFFFFFFF, int(site))
+    if row_keep_ratio is not None:
+        _cuda(row_keep_ratio, torch.float32)
+        assert row_keep_ratio.is_contiguous()
+    return Dropout(thr, 1.0 / (1.0 - thr / 65536.0), int(seed) & 0xFFFFFFFFFFFFFFFF, int(site),
+                   row_keep_ratio.data_ptr() if row_keep_ratio is not None else None)
 
 
 def _dp(drop):
@@ -267,6 +273,19 @@ def colsum(x, out):
     assert out.numel() == N
     with _op("colsum", 1, x.numel() * x.element_size(), "byte", dev=_dev(x, out)):
         check(lib().desta_colsum(_p(x), 0 if x.dtype == torch.float32 else 1, x.stride(0), M, N, _p(out), _stream()), "desta_colsum")
+
+
+def colsum_heads(x, w, batch, heads, Tq, out):
+    """out[h*64+c] += sum_{b,t} w[b,h,t] * x[b*Tq+t, h*64+c]  (x bf16 [batch*Tq, >= heads*64]; w fp32 [batch*heads*Tq] or None = 1):
+    value-bias gradient of an attention from dO."""
+    _cuda(x, torch.bfloat16)
+    _cuda(out, torch.float32)
+    assert x.stride(1) == 1 and x.shape[0] == batch * Tq and out.numel() == heads * 64 and out.is_contiguous()
+    if w is not None:
+        _cuda(w, torch.float32)
+        assert w.is_contiguous() and w.numel() == batch * heads * Tq
+    with _op("colsum", 1, batch * Tq * heads * 64 * 2, "byte", dev=_dev(x, w, out)):
+        check(lib().desta_colsum_heads(_p(x), x.stride(0), _p(w), batch, heads, Tq, _p(out), _stream()), "desta_colsum_heads")
 
 
 def layer_mix_bwd(dm, x, layer_weights, N, Q, dx, dlw):

@@ -81,6 +81,9 @@ typedef struct desta_dropout {
   float scale;
   uint64_t seed;
   uint32_t site;       /* which dropout call of the step (layer / position) */
+  float* row_keep_ratio; /* optional, desta_attention only: [batch,heads,Tq] <- (sum_k dropped, rescaled P) / (sum_k P) per query
+                          * row.  With it the value-bias gradient of the attention is  sum_q ratio_q dO_q  (desta_colsum_heads)
+                          * instead of a column sum over dV. */
 } desta_dropout;
 
 /* LayerNorm over the last dim (fp32 in; fp32 statistics).  out_bf16 and/or out_f32.
@@ -138,6 +141,10 @@ int desta_gelu_fwd(const void* h, void* y, size_t n, void* stream);
 int desta_gelu_bwd(const void* dy, const void* h, void* dh, size_t n, void* stream);
 /* out[j] += sum_m x[m,j]  (bias gradients; dtype 0 = fp32, 1 = bf16). */
 int desta_colsum(const void* x, int dtype, int ld, int M, int N, float* out, void* stream);
+/* out[h*64 + c] += sum_{b,t} w[(b*heads + h)*Tq + t] * x[(b*Tq + t)*ld + h*64 + c]   (x bf16; w == NULL: weights 1).
+ * Value-bias gradient of an attention whose rows of P sum to w (1 without dropout: O = P (X Wv^T + 1 bv^T) carries bv as is),
+ * computed from dO [batch*Tq, heads*64] - replaces the column sum over dV [batch*Tk, heads*64]. */
+int desta_colsum_heads(const void* x, int ld, const float* w, int batch, int heads, int Tq, float* out, void* stream);
 /* Backward of desta_layer_mix: dx [taps,N*Q,D] (written), dlw [Q,taps] (+=). */
 int desta_layer_mix_bwd(const float* dm, const float* x, const float* layer_weights, int taps, int N, int Q, int D, float* dx,
                         float* dlw, void* stream);

@@ -85,6 +85,21 @@ def test_attention_dropout_fwd_bwd(B, H, Tq, Tk, scale):
     ref.backward(do.float())
     for name, x, y in (("dq", dq, qf.grad), ("dk", dk, kf.grad), ("dv", dv, vf.grad)):
         assert _rel(x, y) < 3e-2 and _cos(x, y) > 0.999, f"{name}: rel {_rel(x, y)} cos {_cos(x, y)}"
+    # row_keep_ratio: per query row, the sum of the dropped, rescaled probabilities over their plain sum (same mask, same output)
+    rr = torch.full((B * H * Tq,), -1.0, device="cuda")
+    o2 = torch.empty_like(q)
+    ops.attention(q, k, v, o2, B, H, Tq, Tk, scale, drop=ops.make_dropout(0.1, 4242 + Tk, 9, rr))
+    assert torch.equal(o2, o)
+    ratio_ref = a.detach().sum(-1)                            # [B, H, Tq]: softmax rows sum to 1
+    assert (rr.view(B, H, Tq) - ratio_ref).abs().max().item() < 2e-3
+    # ... which turns the value-bias gradient into a reduction over dO:  sum_k dV[k] = sum_q ratio_q dO_q  per head
+    got = torch.zeros(d, device="cuda")
+    ops.colsum_heads(do, rr, B, H, Tq, got)
+    want = vf.grad.reshape(B, Tk, d).sum((0, 1))
+    assert _rel(got, want) < 2e-2 and _cos(got, want) > 0.9995, (_rel(got, want), _cos(got, want))
+    plain = torch.zeros(d, device="cuda")
+    ops.colsum_heads(do, None, B, H, Tq, plain)               # no weights: a plain column sum of dO
+    assert _rel(plain, do.float().sum(0)) < 1e-3
 
 
 @pytest.mark.parametrize("name,n_clips", [("micro", 3), ("debug", 2), ("l3_slim", 1), ("l3_slim", 2)])     # l3_slim: flagship layer shapes
